@@ -1,0 +1,204 @@
+/*
+ * kmers_b200.h -- C ABI of the B200-native hot path of COMBINE-lab/kmers.
+ *
+ * The reference is a pure-Rust crate with no FFI of its own;
+ * its boundary for this path is the Rust API.  Each entry point below is the
+ * *batched* form of one reference item, cited as file:line under
+ * /root/reference/src.  A Rust maintainer binds these with a build.rs +
+ * `extern "C"` block (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns int32_t: KMB_OK (0) or a negative KMB_ERR_*;
+ *     nothing unwinds or aborts across the boundary.  kmb_last_error(ctx)
+ *     returns the message of the last failure on that ctx.
+ *   - where the reference would panic!/assert! (k > 32, k == 0 ...) the call
+ *     returns KMB_ERR_PANIC instead.
+ *   - a kmb_ctx owns one CUDA stream, pinned staging buffers and the
+ *     device-resident read batch.  One ctx per (host thread, GPU); a ctx is
+ *     not thread-safe; distinct ctxs are independent.
+ *   - pointers named *_out / in may be DEVICE or HOST memory; the library
+ *     looks the pointer up (cudaPointerGetAttributes) and stages host
+ *     pointers through device scratch.  Device outputs stay resident.
+ *   - there is NO CPU fallback: without a CUDA device every compute call
+ *     fails with KMB_ERR_NO_DEVICE.
+ *   - k-mer words: base 0 in bits 1:0 (naive_impl/kmer.rs:234-251); multi-word
+ *     arrays are little-endian word order, flat bit i = bit i%w of word i/w
+ *     (encoding/naive.rs:297-445 goldens).
+ */
+#ifndef KMERS_B200_H
+#define KMERS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMB_VERSION 100
+
+#define KMB_OK 0
+#define KMB_ERR_INVALID_ARG (-1)
+#define KMB_ERR_CUDA (-2)
+#define KMB_ERR_NO_DEVICE (-3)
+#define KMB_ERR_STATE (-4)   /* e.g. no batch loaded */
+#define KMB_ERR_PANIC (-5)   /* the reference would panic here */
+#define KMB_ERR_NOMEM (-6)
+
+/* dense-slot filler for windows CanonicalKmerIterator skips
+ * (canonical_kmer_iterator.rs:55-66); unambiguous because a canonical word /
+ * LexHash of k <= 31 is < 2^62 (and the top word for k <= 63). */
+#define KMB_SENTINEL UINT64_MAX
+
+/* encoding selector: a Naive discriminant byte (encoding/naive.rs:49-74) or
+ * KMB_ENC_XOR10 (struct Xor10, encoding/xor10.rs:12 == Naive::ACTG). */
+#define KMB_ENC_ACGT 0x1E /* Naive::ACGT == naive_impl's A0 C1 G2 T3 (naive_impl/mod.rs:21-24) */
+#define KMB_ENC_ACTG 0x1B /* Naive::ACTG */
+#define KMB_ENC_XOR10 0x100
+
+/* flags for kmb_extract_canonical* */
+#define KMB_F_NO_VALIDATE 0x1u /* Path-E semantics: every window is kept, bytes map by (c>>1)&3 */
+
+/* MatchType, naive_impl/canonical_kmer.rs:7-12 */
+#define KMB_NO_MATCH 0
+#define KMB_IDENTITY_MATCH 1
+#define KMB_TWIN_MATCH 2
+
+typedef struct kmb_ctx kmb_ctx;
+
+/* order-independent digest of one extraction (mirrors the `.sum()` of
+ * benches/simple_benchmark.rs:21, wrapping). */
+typedef struct {
+    uint64_t n_valid;        /* windows the reference iterator emits */
+    uint64_t checksum_canon; /* wrapping sum of their canonical words (all words for k > 32) */
+    uint64_t checksum_hash;  /* wrapping sum of their LexHash words */
+} kmb_digest;
+
+/* ---- library / context ------------------------------------------------ */
+int32_t kmb_version(void);
+/* number of CUDA devices visible, 0 if none / no driver */
+int32_t kmb_device_count(void);
+/* device < 0: current device.  stream == NULL: the ctx creates its own
+ * non-blocking stream; otherwise it borrows the caller's cudaStream_t (so the
+ * ctx can share a stream with torch / other CUDA code). */
+int32_t kmb_ctx_create(int32_t device, void *cuda_stream, kmb_ctx **out);
+int32_t kmb_ctx_destroy(kmb_ctx *ctx);
+const char *kmb_last_error(const kmb_ctx *ctx); /* ctx may be NULL: last ctx-less error of this thread */
+int32_t kmb_ctx_sync(kmb_ctx *ctx);
+void *kmb_ctx_stream(kmb_ctx *ctx);
+/* number of kernels this ctx has launched since creation (bench accounting) */
+uint64_t kmb_ctx_launch_count(const kmb_ctx *ctx);
+
+/* raw memory helpers so an FFI caller needs no CUDA binding of its own */
+int32_t kmb_device_alloc(kmb_ctx *ctx, size_t bytes, void **out);
+int32_t kmb_device_free(kmb_ctx *ctx, void *ptr);
+int32_t kmb_host_alloc_pinned(kmb_ctx *ctx, size_t bytes, void **out);
+int32_t kmb_host_free_pinned(kmb_ctx *ctx, void *ptr);
+/* async on the ctx stream, either direction; kmb_ctx_sync to wait */
+int32_t kmb_memcpy(kmb_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- device-resident read batch --------------------------------------- */
+/* A batch is n_reads reads concatenated without separators.  Either
+ * fixed_len > 0 and offsets == NULL (read r = bytes [r*L, (r+1)*L)), or
+ * offsets has n_reads+1 ascending u64 entries (CSR), offsets[0] == 0.
+ * Replaces the `&[u8]` a caller hands to CanonicalKmerIterator::from_u8_slice
+ * (canonical_kmer_iterator.rs:72-83) / Encoding::encode (encoding/mod.rs:16). */
+
+/* host -> pinned staging -> device, async on the ctx stream */
+int32_t kmb_batch_upload(kmb_ctx *ctx, const uint8_t *bases, uint64_t n_bytes, const uint64_t *offsets,
+                         uint64_t n_reads, uint64_t fixed_len);
+/* zero-copy: borrow caller-owned DEVICE memory (must outlive the batch) */
+int32_t kmb_batch_attach(kmb_ctx *ctx, const uint8_t *dev_bases, uint64_t n_bytes,
+                         const uint64_t *dev_offsets, uint64_t n_reads, uint64_t fixed_len);
+/* synthetic fixed-length reads generated on the device:
+ * x = splitmix64(seed + first_index + i); base i = "ACGT"[x >> 62], or 'N'
+ * when ((x >> 20) & 0xFFFFF) < n_thresh20. */
+int32_t kmb_batch_generate(kmb_ctx *ctx, uint64_t seed, uint64_t first_index, uint64_t n_reads,
+                           uint64_t fixed_len, uint32_t n_thresh20);
+/* copy the resident bases back (host or device dst) */
+int32_t kmb_batch_download(kmb_ctx *ctx, uint8_t *dst, uint64_t n_bytes);
+int32_t kmb_batch_info(const kmb_ctx *ctx, uint64_t *n_bytes, uint64_t *n_reads, uint64_t *fixed_len);
+/* dense slots for window length k: sum over reads of max(0, L_r - k + 1) */
+int32_t kmb_batch_num_slots(kmb_ctx *ctx, uint32_t k, uint64_t *n_slots);
+/* CSR batches: exclusive prefix of per-read window counts (n_reads+1 u64,
+ * host or device dst) -- slot of window `pos` of read r = win_offsets[r] + pos */
+int32_t kmb_batch_window_offsets(kmb_ctx *ctx, uint32_t k, uint64_t *win_offsets_out);
+
+/* ---- the hot path: batched CanonicalKmerIterator ---------------------- */
+/* For every read of the batch, every window position `pos` in increasing
+ * order (canonical_kmer_iterator.rs:42-101): slot = win_offsets[r] + pos.
+ *   canon_out[slot] = CanonicalKmer::get_canonical_word (canonical_kmer.rs:113-119)
+ *   hash_out[slot]  = hash_one(&LexHasherState::new(k), canonical kmer) (hash.rs:10-20, 60-71)
+ *   fw_out / rc_out = get_fw_word / get_rc_word (canonical_kmer.rs:131-139)
+ * Windows the iterator skips (a byte outside ACGTacgt, naive_impl/mod.rs:40-50)
+ * hold KMB_SENTINEL in every output.  Any output pointer may be NULL.
+ * digest (HOST pointer, may be NULL) receives the order-independent digest;
+ * passing it makes the call synchronous.  1 <= k <= 32; k == 32 uses the
+ * intended all-ones mask, not MASK_TABLE[32] == 0. */
+int32_t kmb_extract_canonical(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t *canon_out,
+                              uint64_t *hash_out, uint64_t *fw_out, uint64_t *rc_out,
+                              kmb_digest *digest);
+
+/* EXTENSION (not defined by the reference, parity unpinned): 1 <= k <= 64,
+ * two u64 words per slot (canon_out[2*slot], [2*slot+1]; word 1 most
+ * significant), any encoding.  Built from Encoding::encode + rev_comp::<K>
+ * (encoding/naive.rs:116-154) per window; canonical = unsigned 2k-bit min;
+ * hash = 2k-bit pair reversal (lexicographic rank).  Validation as above
+ * unless KMB_F_NO_VALIDATE. */
+int32_t kmb_extract_canonical_wide(kmb_ctx *ctx, uint32_t k, int32_t enc, uint32_t flags,
+                                   uint64_t *canon_out, uint64_t *hash_out, kmb_digest *digest);
+
+/* Fused, nothing materialised: histogram of emitted windows by the top
+ * hist_bits of the 2k-bit LexHash (1 << hist_bits u64 bins, device or host
+ * dst, ACCUMULATED into when accumulate != 0) + digest.  Config 5 of
+ * BASELINE.json; the bins are what ranks all-reduce. */
+int32_t kmb_histogram(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint32_t hist_bits, uint64_t *hist_out,
+                      int32_t accumulate, kmb_digest *digest);
+
+/* One-shot end-to-end form with HOST buffers: chunks the reads, and overlaps
+ * pinned-staged H2D, the extraction kernel and (when host outputs are given)
+ * the D2H of results.  host_canon / host_hash may be NULL (digest only; the
+ * outputs then stay in device scratch).  Fixed-length reads only. */
+int32_t kmb_extract_canonical_host(kmb_ctx *ctx, const uint8_t *host_bases, uint64_t n_reads,
+                                   uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t *host_canon,
+                                   uint64_t *host_hash, kmb_digest *digest);
+
+/* ---- batched Encoding<P,B> (encoding/mod.rs:14-23) --------------------- */
+/* Encoding::encode of every read of the batch (encoding/naive.rs:116-124,
+ * xor10.rs:52-60): read r becomes ceil(L_r / (word_bits/2)) words of
+ * word_bits in {8,16,32,64,128}, unused high bits 0, written from byte
+ * word_offsets[r] * word_bits/8 of words_out.  No validation.
+ * word_offsets_out (n_reads+1 u64, may be NULL) receives the CSR in words. */
+int32_t kmb_pack(kmb_ctx *ctx, int32_t enc, uint32_t word_bits, void *words_out, uint64_t *word_offsets_out);
+int32_t kmb_pack_num_words(kmb_ctx *ctx, uint32_t word_bits, uint64_t *n_words);
+/* Encoding::decode (encoding/naive.rs:126-136): n_items arrays of
+ * words_per_item words each -> bases_per_item ASCII bytes each, upper case.
+ * bases_per_item == words_per_item*word_bits/2 reproduces the reference's
+ * padding positions. */
+int32_t kmb_unpack(kmb_ctx *ctx, int32_t enc, uint32_t word_bits, const void *words_in, uint64_t n_items,
+                   uint32_t words_per_item, uint32_t bases_per_item, uint8_t *bases_out);
+/* Encoding::rev_comp::<K> (encoding/naive.rs:138-154; xor10.rs:86-103 -- the
+ * swap-loop result for every B, NOT the arithmetic of xor10.rs:75-85, SURVEY
+ * Q2) on n_items arrays of words_per_item words; bits >= 2k are preserved.
+ * k >= 1 (k == 1 is the plain complement; the reference underflows, Q9).
+ * in == out allowed. */
+int32_t kmb_revcomp_words(kmb_ctx *ctx, int32_t enc, uint32_t k, uint32_t word_bits, uint32_t words_per_item,
+                          const void *words_in, void *words_out, uint64_t n_items);
+
+/* ---- batched naive_impl::Kmer word ops (u64, k <= 32) ------------------- */
+/* Kmer::get_reverse_complement_word (naive_impl/kmer.rs:138-147) */
+int32_t kmb_reverse_complement_words(kmb_ctx *ctx, uint32_t k, const uint64_t *in, uint64_t *out, uint64_t n);
+/* Kmer::to_canonical (kmer.rs:68-74); is_canonical_out (u8, may be NULL) = Kmer::is_canonical (kmer.rs:55-58) */
+int32_t kmb_canonical_words(kmb_ctx *ctx, uint32_t k, const uint64_t *in, uint64_t *canon_out,
+                            uint8_t *is_canonical_out, uint64_t n);
+/* hash_one(&LexHasherState::new(k), Kmer) (naive_impl/hash.rs:10-20, 60-71) */
+int32_t kmb_lexhash_words(kmb_ctx *ctx, uint32_t k, const uint64_t *in, uint64_t *out, uint64_t n);
+/* CanonicalKmer::from_u64(words[i], k).get_word_equivalency(others[i])
+ * (canonical_kmer.rs:42-52, 152-161) -> KMB_*_MATCH as u8 */
+int32_t kmb_match_words(kmb_ctx *ctx, uint32_t k, const uint64_t *words, const uint64_t *others,
+                        uint8_t *match_out, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

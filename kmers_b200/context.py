@@ -1,0 +1,315 @@
+"""Host-side mirror of the reference interface, in batched form.
+
+`Context` wraps a `kmb_ctx` (one CUDA stream + the device-resident read batch);
+`ReadBatch` is the batched stand-in for the `&[u8]` a caller hands to
+`CanonicalKmerIterator::from_u8_slice` (naive_impl/canonical_kmer_iterator.rs:72-83)
+or `Encoding::encode` (encoding/mod.rs:16).  PyTorch is used only as the owner
+of device memory and streams; all compute goes through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _native as nv
+from ._native import Digest, KmbError, KmbPanic, check
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _is_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x) -> Optional[int]:
+    """Raw address of a numpy array (host) or torch tensor (host or device)."""
+    if x is None:
+        return None
+    if _is_tensor(x):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    assert x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def _as_u64_host(t) -> np.ndarray:
+    """int64 torch tensor (device or host) -> numpy uint64 view."""
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+@dataclass
+class CanonicalKmers:
+    """Dense-slot result of `ReadBatch.extract_canonical` (SURVEY.md 8d layout).
+
+    Slot `win_offsets[r] + pos` holds the window at `pos` of read `r`; windows
+    the reference iterator skips hold SENTINEL.  Arrays are torch int64 CUDA
+    tensors (bit pattern of the u64 words) or numpy uint64 arrays."""
+    k: int
+    n_slots: int
+    canon: object = None
+    hash: object = None
+    fw: object = None
+    rc: object = None
+    digest: Optional[tuple] = None  # (n_valid, checksum_canon, checksum_hash)
+    words_per_kmer: int = 1
+
+    def host(self, name: str) -> np.ndarray:
+        a = getattr(self, name)
+        if a is None:
+            raise ValueError(f"{name} was not requested")
+        out = _as_u64_host(a) if _is_tensor(a) else a
+        return out.reshape(-1, self.words_per_kmer) if self.words_per_kmer > 1 else out
+
+
+class Context:
+    """One per (host thread, GPU).  Not thread-safe; contexts are independent."""
+
+    def __init__(self, device: int = -1, stream: Optional[int] = None):
+        self._lib = nv.lib()
+        h = C.c_void_p()
+        check(None, self._lib.kmb_ctx_create(device, stream, C.byref(h)))
+        self._h = h
+        self._keep = []  # objects a borrowed batch must outlive
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kmb_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, code: int):
+        check(self._h, code)
+
+    def sync(self):
+        self._ck(self._lib.kmb_ctx_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.kmb_ctx_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.kmb_ctx_launch_count(self._h))
+
+    # ---- batches
+    def upload(self, bases, offsets=None, fixed_len: int = 0, n_reads: Optional[int] = None) -> "ReadBatch":
+        """Host reads -> pinned staging -> device (kmb_batch_upload)."""
+        bases = np.ascontiguousarray(np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray))
+                                     else bases, dtype=np.uint8)
+        offs = None
+        if offsets is not None:
+            offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+            n_reads = offs.size - 1
+        elif n_reads is None:
+            n_reads = bases.size // fixed_len if fixed_len else 0
+        self._ck(self._lib.kmb_batch_upload(self._h, _ptr(bases), bases.size, _ptr(offs), n_reads, fixed_len))
+        self._keep = []
+        return ReadBatch(self, bases.size, n_reads, fixed_len, offs is not None)
+
+    def attach(self, dev_bases, dev_offsets=None, fixed_len: int = 0, n_reads: Optional[int] = None) -> "ReadBatch":
+        """Borrow device-resident reads (torch uint8 CUDA tensor [+ int64 offsets]) with no copy."""
+        n_bytes = dev_bases.numel()
+        if dev_offsets is not None:
+            n_reads = dev_offsets.numel() - 1
+        elif n_reads is None:
+            n_reads = n_bytes // fixed_len if fixed_len else 0
+        self._ck(self._lib.kmb_batch_attach(self._h, _ptr(dev_bases), n_bytes, _ptr(dev_offsets), n_reads, fixed_len))
+        self._keep = [dev_bases, dev_offsets]
+        return ReadBatch(self, n_bytes, n_reads, fixed_len, dev_offsets is not None)
+
+    def generate(self, seed: int, n_reads: int, fixed_len: int, n_thresh20: int = 0, first_index: int = 0) -> "ReadBatch":
+        """Synthetic reads generated on the device (counter-based splitmix64)."""
+        self._ck(self._lib.kmb_batch_generate(self._h, seed, first_index, n_reads, fixed_len, n_thresh20))
+        self._keep = []
+        return ReadBatch(self, n_reads * fixed_len, n_reads, fixed_len, False)
+
+    # ---- one-shot host path (e2e): chunked, H2D / kernel / D2H overlapped
+    def extract_canonical_host(self, host_bases: np.ndarray, n_reads: int, fixed_len: int, k: int, *,
+                               host_canon: Optional[np.ndarray] = None, host_hash: Optional[np.ndarray] = None,
+                               validate: bool = True, digest: bool = True):
+        d = Digest()
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        self._ck(self._lib.kmb_extract_canonical_host(self._h, _ptr(host_bases), n_reads, fixed_len, k, flags,
+                                                      _ptr(host_canon), _ptr(host_hash),
+                                                      C.byref(d) if digest else None))
+        return d.astuple() if digest else None
+
+    # ---- element-wise word ops (naive_impl::Kmer in batch)
+    @staticmethod
+    def _words_in(words, to):
+        """(count, array, destination) for a u64 word array given as torch int64 (device) or numpy."""
+        if _is_tensor(words):
+            return words.numel(), words, to or "device"
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        return w.size, w, to or "host"
+
+    def _alloc(self, n, to, dtype):
+        if to == "device":
+            t = _torch()
+            return t.empty(n, dtype=t.int64 if dtype == np.uint64 else t.uint8, device="cuda")
+        return np.empty(n, dtype=dtype)
+
+    def reverse_complement_words(self, words, k: int, to=None):
+        """Kmer::get_reverse_complement_word (naive_impl/kmer.rs:138-147) on every word."""
+        n, w, to = self._words_in(words, to)
+        out = self._alloc(n, to, np.uint64)
+        self._ck(self._lib.kmb_reverse_complement_words(self._h, k, _ptr(w), _ptr(out), n))
+        self.sync()
+        return out
+
+    def canonical_words(self, words, k: int, to=None):
+        """(Kmer::to_canonical, Kmer::is_canonical) (naive_impl/kmer.rs:55-74) on every word."""
+        n, w, to = self._words_in(words, to)
+        out = self._alloc(n, to, np.uint64)
+        flag = self._alloc(n, to, np.uint8)
+        self._ck(self._lib.kmb_canonical_words(self._h, k, _ptr(w), _ptr(out), _ptr(flag), n))
+        self.sync()
+        return out, flag
+
+    def lexhash_words(self, words, k: int, to=None):
+        """hash_one(&LexHasherState::new(k), kmer) (naive_impl/hash.rs:10-20, 60-71) on every word."""
+        n, w, to = self._words_in(words, to)
+        out = self._alloc(n, to, np.uint64)
+        self._ck(self._lib.kmb_lexhash_words(self._h, k, _ptr(w), _ptr(out), n))
+        self.sync()
+        return out
+
+    def match_words(self, words, others, k: int, to=None):
+        """CanonicalKmer::from_u64(w, k).get_word_equivalency(other) (canonical_kmer.rs:152-161) -> MatchType u8."""
+        n, w, to = self._words_in(words, to)
+        o = others if _is_tensor(others) else np.ascontiguousarray(others, dtype=np.uint64)
+        out = self._alloc(n, to, np.uint8)
+        self._ck(self._lib.kmb_match_words(self._h, k, _ptr(w), _ptr(o), _ptr(out), n))
+        self.sync()
+        return out
+
+    # ---- batched Encoding::decode / rev_comp on arrays [P; B]
+    def unpack(self, enc: int, word_bits: int, words: np.ndarray, n_items: int, words_per_item: int,
+               bases_per_item: Optional[int] = None) -> np.ndarray:
+        """Encoding::decode (encoding/naive.rs:126-136) of n_items arrays; default length reproduces the
+        reference's padding positions."""
+        if bases_per_item is None:
+            bases_per_item = words_per_item * word_bits // 2
+        img = np.ascontiguousarray(words).view(np.uint8).reshape(-1)
+        out = np.empty(n_items * bases_per_item, dtype=np.uint8)
+        self._ck(self._lib.kmb_unpack(self._h, enc, word_bits, _ptr(img), n_items, words_per_item, bases_per_item,
+                                      _ptr(out)))
+        self.sync()
+        return out.reshape(n_items, bases_per_item) if n_items else out
+
+    def revcomp_words(self, enc: int, k: int, word_bits: int, words: np.ndarray, n_items: int,
+                      words_per_item: int) -> np.ndarray:
+        """Encoding::rev_comp::<K> (encoding/naive.rs:138-154) of n_items arrays (byte image in, byte image out)."""
+        img = np.ascontiguousarray(words).view(np.uint8).reshape(-1)
+        out = np.empty_like(img)
+        self._ck(self._lib.kmb_revcomp_words(self._h, enc, k, word_bits, words_per_item, _ptr(img), _ptr(out), n_items))
+        self.sync()
+        return out
+
+
+class ReadBatch:
+    """The device-resident read batch of a Context (one at a time per context)."""
+
+    def __init__(self, ctx: Context, n_bytes: int, n_reads: int, fixed_len: int, ragged: bool):
+        self.ctx = ctx
+        self.n_bytes, self.n_reads, self.fixed_len, self.ragged = n_bytes, n_reads, fixed_len, ragged
+
+    def num_slots(self, k: int) -> int:
+        n = C.c_uint64()
+        self.ctx._ck(self.ctx._lib.kmb_batch_num_slots(self.ctx._h, k, C.byref(n)))
+        return int(n.value)
+
+    def window_offsets(self, k: int) -> np.ndarray:
+        """Exclusive prefix of per-read window counts (n_reads + 1)."""
+        if not self.ragged:
+            w = max(0, self.fixed_len - k + 1)
+            return np.arange(self.n_reads + 1, dtype=np.uint64) * np.uint64(w)
+        out = np.empty(self.n_reads + 1, dtype=np.uint64)
+        self.ctx._ck(self.ctx._lib.kmb_batch_window_offsets(self.ctx._h, k, _ptr(out)))
+        return out
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.n_bytes, dtype=np.uint8)
+        self.ctx._ck(self.ctx._lib.kmb_batch_download(self.ctx._h, _ptr(out), self.n_bytes))
+        return out
+
+    def _alloc(self, n, to):
+        if to == "device":
+            t = _torch()
+            return t.empty(n, dtype=t.int64, device="cuda")
+        return np.empty(n, dtype=np.uint64)
+
+    def extract_canonical(self, k: int, *, want_hash: bool = True, want_fw_rc: bool = False, digest: bool = False,
+                          validate: bool = True, to: str = "device", out: Optional[CanonicalKmers] = None) -> CanonicalKmers:
+        """Batched CanonicalKmerIterator + get_canonical_word + LexHasher (kmb_extract_canonical)."""
+        n = self.num_slots(k)
+        if out is None:
+            out = CanonicalKmers(k=k, n_slots=n)
+            out.canon = self._alloc(n, to)
+            out.hash = self._alloc(n, to) if want_hash else None
+            if want_fw_rc:
+                out.fw, out.rc = self._alloc(n, to), self._alloc(n, to)
+        d = Digest()
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._ck(self.ctx._lib.kmb_extract_canonical(self.ctx._h, k, flags, _ptr(out.canon), _ptr(out.hash),
+                                                         _ptr(out.fw), _ptr(out.rc), C.byref(d) if digest else None))
+        out.digest = d.astuple() if digest else None
+        return out
+
+    def extract_canonical_wide(self, k: int, enc: int = nv.ENC_ACGT, *, want_hash: bool = True, digest: bool = False,
+                               validate: bool = True, to: str = "device") -> CanonicalKmers:
+        """EXTENSION: 1 <= k <= 64, two u64 words per slot (kmb_extract_canonical_wide)."""
+        n = self.num_slots(k)
+        out = CanonicalKmers(k=k, n_slots=n, words_per_kmer=2)
+        out.canon = self._alloc(2 * n, to)
+        out.hash = self._alloc(2 * n, to) if want_hash else None
+        d = Digest()
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._ck(self.ctx._lib.kmb_extract_canonical_wide(self.ctx._h, k, enc, flags, _ptr(out.canon), _ptr(out.hash),
+                                                              C.byref(d) if digest else None))
+        out.digest = d.astuple() if digest else None
+        return out
+
+    def histogram(self, k: int, hist_bits: int, *, hist=None, accumulate: bool = False, digest: bool = True,
+                  validate: bool = True, to: str = "device"):
+        """Fused extraction -> LexHash-prefix histogram + digest, nothing materialised (kmb_histogram)."""
+        if hist is None:
+            hist = self._alloc(1 << hist_bits, to)
+            accumulate = False
+        d = Digest()
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._ck(self.ctx._lib.kmb_histogram(self.ctx._h, k, flags, hist_bits, _ptr(hist), int(accumulate),
+                                                 C.byref(d) if digest else None))
+        return hist, (d.astuple() if digest else None)
+
+    def pack(self, enc: int = nv.ENC_ACGT, word_bits: int = 64, to: str = "host"):
+        """Encoding::encode of every read (kmb_pack).  Returns (byte image, word offsets or None)."""
+        n = C.c_uint64()
+        self.ctx._ck(self.ctx._lib.kmb_pack_num_words(self.ctx._h, word_bits, C.byref(n)))
+        nbytes = int(n.value) * word_bits // 8
+        if to == "device":
+            t = _torch()
+            out = t.empty(nbytes, dtype=t.uint8, device="cuda")
+        else:
+            out = np.empty(nbytes, dtype=np.uint8)
+        woff = np.empty(self.n_reads + 1, dtype=np.uint64) if self.ragged else None
+        self.ctx._ck(self.ctx._lib.kmb_pack(self.ctx._h, enc, word_bits, _ptr(out), _ptr(woff)))
+        return out, woff

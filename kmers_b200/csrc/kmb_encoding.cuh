@@ -1,0 +1,219 @@
+// kmb_encoding.cuh -- batched Encoding<P,B> (encoding/mod.rs:14-23) and the
+// element-wise naive_impl::Kmer word operations, plus the synthetic generator.
+#pragma once
+#include "kmb_device.cuh"
+
+namespace kmb {
+
+// ---------------------------------------------------------------- synthetic reads
+// base i = "ACGT"[splitmix64(seed + first + i) >> 62], 'N' under n_thresh20
+__global__ void __launch_bounds__(256) generate_kernel(uint8_t* out, uint64_t n, uint64_t seed_plus_first,
+                                                       uint32_t n_thresh20) {
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 16 bases each
+    const uint64_t i0 = chunk * 16;
+    if (i0 >= n) return;
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint64_t x = splitmix64(seed_plus_first + i0 + i);
+        uint32_t c = (0x54474341u >> ((uint32_t)(x >> 62) * 8)) & 0xFFu;  // 'A','C','G','T'
+        if (((uint32_t)(x >> 20) & 0xFFFFFu) < n_thresh20) c = 'N';
+        w[i >> 2] |= c << ((i & 3) * 8);
+    }
+    if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(out + i0) & 15u) == 0) {
+        *reinterpret_cast<uint4*>(out + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int i = 0; i < 16 && i0 + i < n; ++i) out[i0 + i] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+    }
+}
+
+// ---------------------------------------------------------------- Encoding::encode (bulk pack)
+// encoding/naive.rs:116-124, xor10.rs:52-60.  Flat little-endian bit layout:
+// output byte b of a read holds bases 4b..4b+3, zero beyond the read; the
+// word width only decides how many padding bytes end the read's region.
+// One thread = 16 bases of one read = one 32-bit store.
+struct PackParams {
+    const uint8_t* bases;
+    const uint64_t* offsets;       // CSR or nullptr
+    const uint64_t* word_offsets;  // CSR in words, or nullptr (fixed)
+    uint64_t n_reads;
+    uint64_t L;                    // fixed length (when offsets == nullptr)
+    uint64_t out_bytes_per_read;   // fixed: ceil(L / bpw) * word_bytes
+    uint32_t word_bytes;
+    uint32_t bases_per_word;
+    uint8_t* out;
+    EncDesc enc;
+};
+
+__device__ __forceinline__ uint32_t pack16_bytes(const uint8_t* src, uint32_t n_avail, const EncDesc& enc) {
+    // n_avail in [1,16] bases really present; missing ones pack as zero bits
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (n_avail == 16 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        uint4 v = ld_stream_v4(src);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if ((uint32_t)i < n_avail) w[i >> 2] |= (uint32_t)__ldg(src + i) << ((i & 3) * 8);
+    }
+    PackedWord pw = pack16<false>(make_uint4(w[0], w[1], w[2], w[3]));
+    uint32_t bits = apply_encoding(pw.bits, enc);
+    if (n_avail < 16) bits &= (1u << (2 * n_avail)) - 1u;  // padding is zero bits, not code(0x00)
+    return bits;
+}
+
+__device__ __forceinline__ void store_packed32(uint8_t* dst, uint64_t byte_off, uint64_t region_bytes, uint32_t bits) {
+    // the read's region may end inside this 32-bit group (word_bits 8/16)
+    if (byte_off + 4 <= region_bytes && (reinterpret_cast<uintptr_t>(dst + byte_off) & 3u) == 0) {
+        *reinterpret_cast<uint32_t*>(dst + byte_off) = bits;
+    } else {
+        for (int b = 0; b < 4 && byte_off + b < region_bytes; ++b) dst[byte_off + b] = (uint8_t)(bits >> (8 * b));
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_fixed_kernel(const PackParams p, uint64_t groups_per_read) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t r = t / groups_per_read;
+    if (r >= p.n_reads) return;
+    const uint64_t g = t - r * groups_per_read;  // 16-base group inside the read's region
+    const uint64_t b0 = g * 16;
+    uint32_t bits = 0;
+    if (b0 < p.L) bits = pack16_bytes(p.bases + r * p.L + b0, (uint32_t)min((uint64_t)16, p.L - b0), p.enc);
+    store_packed32(p.out + r * p.out_bytes_per_read, g * 4, p.out_bytes_per_read, bits);
+}
+
+// CSR: one warp per read
+__global__ void __launch_bounds__(256) pack_csr_kernel(const PackParams p) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (r >= p.n_reads) return;
+    const uint64_t beg = p.offsets[r], len = p.offsets[r + 1] - beg;
+    const uint64_t region = (p.word_offsets[r + 1] - p.word_offsets[r]) * p.word_bytes;
+    uint8_t* dst = p.out + p.word_offsets[r] * p.word_bytes;
+    const uint64_t groups = (region + 3) / 4;
+    for (uint64_t g = lane; g < groups; g += 32) {
+        const uint64_t b0 = g * 16;
+        uint32_t bits = 0;
+        if (b0 < len) bits = pack16_bytes(p.bases + beg + b0, (uint32_t)min((uint64_t)16, len - b0), p.enc);
+        store_packed32(dst, g * 4, region, bits);
+    }
+}
+
+// ---------------------------------------------------------------- Encoding::decode (bulk unpack)
+// encoding/naive.rs:126-136 (bits2nuc :88-96).  dec = the four ASCII letters
+// for codes 0..3 packed in one u32.  One thread = one input byte = 4 bases.
+__global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* in, uint64_t n_items, uint32_t in_bytes_per_item,
+                                                     uint32_t bases_per_item, uint32_t dec, uint8_t* out) {
+    const uint32_t groups = (bases_per_item + 3) / 4;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t item = t / groups;
+    if (item >= n_items) return;
+    const uint32_t g = (uint32_t)(t - item * groups);
+    const uint32_t byte = in[item * in_bytes_per_item + g];
+    uint8_t* dst = out + item * bases_per_item + (uint64_t)g * 4;
+    uint32_t chars = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) chars |= ((dec >> (((byte >> (2 * i)) & 3u) * 8)) & 0xFFu) << (8 * i);
+    const uint32_t n = min(4u, bases_per_item - g * 4);
+    if (n == 4 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+        *reinterpret_cast<uint32_t*>(dst) = chars;
+    } else {
+        for (uint32_t i = 0; i < n; ++i) dst[i] = (uint8_t)(chars >> (8 * i));
+    }
+}
+
+// ---------------------------------------------------------------- Encoding::rev_comp::<K>
+// encoding/naive.rs:138-154 / xor10.rs:86-103: fields 0..K-1 are reversed and
+// complemented, bits >= 2K untouched.  One thread = one item of NW32 32-bit
+// groups (item_bytes may be less than 4*NW32 for u8/u16 word types).
+__device__ __forceinline__ uint32_t get32_signed(const uint32_t* w, int nw, int bitpos) {
+    if (bitpos <= -32) return 0;
+    if (bitpos < 0) return w[0] << (-bitpos);
+    const int idx = bitpos >> 5, sh = bitpos & 31;
+    const uint32_t lo = idx < nw ? w[idx] : 0u, hi = (idx + 1) < nw ? w[idx + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+template <int NW32>
+__global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, uint8_t* out, uint64_t n_items,
+                                                            uint32_t item_bytes, uint32_t K, uint32_t cmask) {
+    const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    const uint8_t* src = in + item * item_bytes;
+    uint8_t* dst = out + item * item_bytes;
+    uint32_t w[NW32];
+    const bool aligned = (item_bytes == 4u * NW32) && ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0);
+    if (aligned) {
+#pragma unroll
+        for (int i = 0; i < NW32; ++i) w[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW32; ++i) {
+            uint32_t v = 0;
+            for (int b = 0; b < 4; ++b)
+                if ((uint32_t)(4 * i + b) < item_bytes) v |= (uint32_t)src[4 * i + b] << (8 * b);
+            w[i] = v;
+        }
+    }
+    uint32_t o[NW32];
+#pragma unroll
+    for (int i = 0; i < NW32; ++i) {
+        const int nvalid = max(0, min(16, (int)K - 16 * i));  // fields of this group below K
+        const uint32_t vmask = nvalid == 16 ? 0xFFFFFFFFu : ((1u << (2 * nvalid)) - 1u);
+        const uint32_t srcbits = get32_signed(w, NW32, 2 * ((int)K - 16 * i - 16));
+        o[i] = (pair_reverse32(srcbits ^ cmask) & vmask) | (w[i] & ~vmask);
+    }
+    if (aligned) {
+#pragma unroll
+        for (int i = 0; i < NW32; ++i) reinterpret_cast<uint32_t*>(dst)[i] = o[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW32; ++i)
+            for (int b = 0; b < 4; ++b)
+                if ((uint32_t)(4 * i + b) < item_bytes) dst[4 * i + b] = (uint8_t)(o[i] >> (8 * b));
+    }
+}
+
+// ---------------------------------------------------------------- naive_impl::Kmer word ops
+// OP 0: get_reverse_complement_word (kmer.rs:138-147)
+// OP 1: to_canonical + is_canonical  (kmer.rs:55-58, 68-74)
+// OP 2: LexHasher                    (hash.rs:60-71)
+// OP 3: get_word_equivalency         (canonical_kmer.rs:42-52, 152-161)
+__device__ __forceinline__ uint64_t rc_word(uint64_t w, uint32_t k) { return pair_reverse64(~w) >> (2 * (32 - k)); }
+
+template <int OP>
+__global__ void __launch_bounds__(256) word_op_kernel(const uint64_t* in, const uint64_t* other, uint64_t* out,
+                                                      uint8_t* out8, uint64_t n, uint32_t k, uint64_t mask) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t w = in[i];
+    if (OP == 0) {
+        out[i] = rc_word(w, k);
+    } else if (OP == 1) {
+        const uint64_t rc = rc_word(w, k);
+        const bool is_canon = w <= rc;  // kmer.rs:57  *self <= rc
+        if (out) out[i] = is_canon ? w : rc;
+        if (out8) out8[i] = is_canon ? 1 : 0;
+    } else if (OP == 2) {
+        out[i] = pair_reverse64(w) >> (2 * (32 - k));
+    } else {
+        const uint64_t fw = w & mask;  // Kmer::from_u64 masks (kmer.rs:45-48), intended mask at k == 32
+        const uint64_t rc = rc_word(fw, k);
+        const uint64_t o = other[i];
+        out8[i] = (fw == o) ? 1 : ((rc == o) ? 2 : 0);
+    }
+}
+
+// per-read window / word counts for the CSR prefix sums
+__global__ void __launch_bounds__(256) read_counts_kernel(const uint64_t* offsets, uint64_t n_reads, uint32_t k_minus_1,
+                                                          uint32_t div, uint64_t* counts) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    if (r == n_reads) { counts[r] = 0; return; }
+    const uint64_t len = offsets[r + 1] - offsets[r];
+    if (div == 0) counts[r] = len > k_minus_1 ? len - k_minus_1 : 0;  // windows
+    else counts[r] = (len + div - 1) / div;                             // packed words
+}
+
+}  // namespace kmb

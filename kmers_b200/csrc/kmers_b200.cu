@@ -1,0 +1,982 @@
+// kmers_b200.cu -- C ABI (include/kmers_b200.h) over the sm_100a kernels.
+// No torch types, no CPU fallback: every compute entry point needs a device.
+#include "../../include/kmers_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include <cub/device/device_scan.cuh>
+
+#include "kmb_encoding.cuh"
+#include "kmb_extract.cuh"
+#include "kmb_extract_wide.cuh"
+
+using namespace kmb;
+
+// ======================================================================= ctx
+struct kmb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D / D2H leg of the pipelined host path
+    std::string err;
+    uint64_t launches = 0;
+
+    // resident batch
+    const uint8_t* d_bases = nullptr;
+    const uint64_t* d_offsets = nullptr;
+    uint8_t* own_bases = nullptr;
+    size_t own_bases_cap = 0;
+    uint64_t* own_offsets = nullptr;
+    size_t own_offsets_cap = 0;
+    uint64_t n_bytes = 0, n_reads = 0, fixed_len = 0;
+    bool have_batch = false;
+
+    // CSR window-offset cache (per k)
+    uint64_t* d_win_offsets = nullptr;
+    size_t win_cap = 0;
+    uint32_t win_k = 0;
+    uint64_t win_total = 0;
+    bool win_valid = false;
+
+    // scratch
+    unsigned long long* d_digest = nullptr;  // 3 words
+    unsigned long long* h_digest = nullptr;  // pinned, 4 words
+    void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap[4] = {0, 0, 0, 0};
+    void* d_cub = nullptr;
+    size_t cub_cap = 0;
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // pipelined host path
+    uint8_t* pipe_in[2] = {nullptr, nullptr};
+    uint64_t* pipe_canon[2] = {nullptr, nullptr};
+    uint64_t* pipe_hash[2] = {nullptr, nullptr};
+    size_t pipe_in_cap = 0, pipe_out_cap = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+
+static thread_local std::string g_err;
+
+static int32_t fail(kmb_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_err = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                    \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMB_ERR_NOMEM : KMB_ERR_CUDA,       \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+#define NEED_CTX(ctx) \
+    do { if (!(ctx)) return fail(nullptr, KMB_ERR_INVALID_ARG, "ctx is NULL"); } while (0)
+
+static int32_t bind(kmb_ctx* ctx) { CK(ctx, cudaSetDevice(ctx->device)); return KMB_OK; }
+#define BIND(ctx) do { int32_t b_ = bind(ctx); if (b_ != KMB_OK) return b_; } while (0)
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+static bool is_pinned_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int32_t grow(kmb_ctx* ctx, void** ptr, size_t* cap, size_t need) {
+    if (*cap >= need && *ptr) return KMB_OK;
+    if (*ptr) { CK(ctx, cudaStreamSynchronize(ctx->stream)); CK(ctx, cudaFree(*ptr)); *ptr = nullptr; *cap = 0; }
+    size_t bytes = need + 256;
+    CK(ctx, cudaMalloc(ptr, bytes));
+    *cap = need;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_version(void) { return KMB_VERSION; }
+
+extern "C" int32_t kmb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int32_t kmb_ctx_create(int32_t device, void* cuda_stream, kmb_ctx** out) {
+    if (!out) return fail(nullptr, KMB_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int n = kmb_device_count();
+    if (n <= 0) return fail(nullptr, KMB_ERR_NO_DEVICE, "no CUDA device: kmers_b200 has no CPU fallback");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
+    }
+    if (device >= n) return fail(nullptr, KMB_ERR_INVALID_ARG, "device %d out of range (%d visible)", device, n);
+    kmb_ctx* ctx = new (std::nothrow) kmb_ctx();
+    if (!ctx) return fail(nullptr, KMB_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+        else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_digest, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_digest, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        int32_t rc = fail(nullptr, KMB_ERR_CUDA, "ctx creation failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        kmb_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
+    if (!ctx) return KMB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    cudaFree(ctx->own_bases);
+    cudaFree(ctx->own_offsets);
+    cudaFree(ctx->d_win_offsets);
+    cudaFree(ctx->d_digest);
+    cudaFreeHost(ctx->h_digest);
+    for (auto& s : ctx->d_scratch) cudaFree(s);
+    cudaFree(ctx->d_cub);
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(ctx->h_stage[i]);
+        cudaFree(ctx->pipe_in[i]);
+        cudaFree(ctx->pipe_canon[i]);
+        cudaFree(ctx->pipe_hash[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+    return KMB_OK;
+}
+
+extern "C" const char* kmb_last_error(const kmb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int32_t kmb_ctx_sync(kmb_ctx* ctx) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" void* kmb_ctx_stream(kmb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t kmb_ctx_launch_count(const kmb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int32_t kmb_device_alloc(kmb_ctx* ctx, size_t bytes, void** out) {
+    NEED_CTX(ctx);
+    if (!out) return fail(ctx, KMB_ERR_INVALID_ARG, "out is NULL");
+    BIND(ctx);
+    CK(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return KMB_OK;
+}
+extern "C" int32_t kmb_device_free(kmb_ctx* ctx, void* ptr) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaFree(ptr));
+    return KMB_OK;
+}
+extern "C" int32_t kmb_host_alloc_pinned(kmb_ctx* ctx, size_t bytes, void** out) {
+    NEED_CTX(ctx);
+    if (!out) return fail(ctx, KMB_ERR_INVALID_ARG, "out is NULL");
+    BIND(ctx);
+    CK(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return KMB_OK;
+}
+extern "C" int32_t kmb_host_free_pinned(kmb_ctx* ctx, void* ptr) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    CK(ctx, cudaFreeHost(ptr));
+    return KMB_OK;
+}
+extern "C" int32_t kmb_memcpy(kmb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (bytes == 0) return KMB_OK;
+    if (!dst || !src) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= encodings
+static bool make_enc(int32_t enc, EncDesc* d, uint32_t* dec_letters) {
+    if (enc == KMB_ENC_XOR10) enc = KMB_ENC_ACTG;  // xor10.rs:17-22 == Naive::ACTG
+    if (enc < 0 || enc > 255) return false;
+    // code of internal x (0=A 1=C 2=T 3=G, encoding/naive.rs:14-16, 78-86)
+    uint32_t code[4];
+    uint32_t seen = 0;
+    for (int x = 0; x < 4; ++x) { code[x] = ((uint32_t)enc >> (6 - 2 * x)) & 3u; seen |= 1u << code[x]; }
+    if (seen != 0xF) return false;  // not one of the 24 permutations
+    for (int b = 0; b < 2; ++b) {
+        uint32_t f00 = (code[0] >> b) & 1, f01 = (code[1] >> b) & 1, f10 = (code[2] >> b) & 1, f11 = (code[3] >> b) & 1;
+        d->k0[b] = f00 ? 0x55555555u : 0u;
+        d->k1[b] = (f01 ^ f00) ? 0x55555555u : 0u;
+        d->k2[b] = (f10 ^ f00) ? 0x55555555u : 0u;
+        d->k3[b] = (f11 ^ f10 ^ f01 ^ f00) ? 0x55555555u : 0u;
+    }
+    d->cmask = (code[0] ^ code[2]) * 0x55555555u;  // complement = XOR constant (naive.rs:98-110)
+    d->is_acgt = (enc == KMB_ENC_ACGT) ? 1u : 0u;
+    if (dec_letters) {
+        static const char letters[4] = {'A', 'C', 'T', 'G'};  // INTERNAL2NUC, naive.rs:19
+        uint32_t dec = 0;
+        for (int x = 0; x < 4; ++x) dec |= (uint32_t)letters[x] << (8 * code[x]);
+        *dec_letters = dec;
+    }
+    return true;
+}
+
+// ======================================================================= batch
+static void drop_batch(kmb_ctx* ctx) {
+    ctx->have_batch = false;
+    ctx->win_valid = false;
+    ctx->d_bases = nullptr;
+    ctx->d_offsets = nullptr;
+}
+
+static int32_t check_shape(kmb_ctx* ctx, uint64_t n_bytes, bool has_offsets, uint64_t n_reads, uint64_t fixed_len) {
+    if (has_offsets == (fixed_len > 0) && !(n_reads == 0 && !has_offsets))
+        return fail(ctx, KMB_ERR_INVALID_ARG, "give either offsets or fixed_len > 0");
+    if (!has_offsets && n_reads * fixed_len != n_bytes)
+        return fail(ctx, KMB_ERR_INVALID_ARG, "n_bytes (%llu) != n_reads * fixed_len (%llu)",
+                    (unsigned long long)n_bytes, (unsigned long long)(n_reads * fixed_len));
+    return KMB_OK;
+}
+
+static int32_t stage_h2d(kmb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return KMB_OK;
+    if (is_pinned_ptr(src) || is_device_ptr(src)) {
+        CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+        return KMB_OK;
+    }
+    const size_t chunk = (size_t)32 << 20;
+    if (ctx->stage_cap < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->h_stage[i]) { CK(ctx, cudaFreeHost(ctx->h_stage[i])); ctx->h_stage[i] = nullptr; }
+            CK(ctx, cudaHostAlloc((void**)&ctx->h_stage[i], chunk, cudaHostAllocDefault));
+        }
+        ctx->stage_cap = chunk;
+    }
+    size_t done = 0;
+    int buf = 0;
+    while (done < bytes) {
+        size_t n = bytes - done < chunk ? bytes - done : chunk;
+        CK(ctx, cudaEventSynchronize(ctx->stage_ev[buf]));  // previous use of this staging buffer drained
+        memcpy(ctx->h_stage[buf], (const uint8_t*)src + done, n);
+        CK(ctx, cudaMemcpyAsync((uint8_t*)dst + done, ctx->h_stage[buf], n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->stage_ev[buf], ctx->stream));
+        done += n;
+        buf ^= 1;
+    }
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_upload(kmb_ctx* ctx, const uint8_t* bases, uint64_t n_bytes, const uint64_t* offsets,
+                                    uint64_t n_reads, uint64_t fixed_len) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    int32_t rc = check_shape(ctx, n_bytes, offsets != nullptr, n_reads, fixed_len);
+    if (rc) return rc;
+    if (n_bytes && !bases) return fail(ctx, KMB_ERR_INVALID_ARG, "bases is NULL");
+    drop_batch(ctx);
+    if ((rc = grow(ctx, (void**)&ctx->own_bases, &ctx->own_bases_cap, n_bytes + 64))) return rc;
+    if ((rc = stage_h2d(ctx, ctx->own_bases, bases, n_bytes))) return rc;
+    ctx->d_bases = ctx->own_bases;
+    if (offsets) {
+        if (offsets[0] != 0 || offsets[n_reads] != n_bytes)
+            return fail(ctx, KMB_ERR_INVALID_ARG, "offsets must start at 0 and end at n_bytes");
+        if ((rc = grow(ctx, (void**)&ctx->own_offsets, &ctx->own_offsets_cap, (n_reads + 1) * 8))) return rc;
+        if ((rc = stage_h2d(ctx, ctx->own_offsets, offsets, (n_reads + 1) * 8))) return rc;
+        ctx->d_offsets = ctx->own_offsets;
+    }
+    ctx->n_bytes = n_bytes; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->have_batch = true;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_attach(kmb_ctx* ctx, const uint8_t* dev_bases, uint64_t n_bytes,
+                                    const uint64_t* dev_offsets, uint64_t n_reads, uint64_t fixed_len) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    int32_t rc = check_shape(ctx, n_bytes, dev_offsets != nullptr, n_reads, fixed_len);
+    if (rc) return rc;
+    if (n_bytes && !is_device_ptr(dev_bases)) return fail(ctx, KMB_ERR_INVALID_ARG, "dev_bases is not device memory");
+    if (dev_offsets && !is_device_ptr(dev_offsets)) return fail(ctx, KMB_ERR_INVALID_ARG, "dev_offsets is not device memory");
+    drop_batch(ctx);
+    ctx->d_bases = dev_bases; ctx->d_offsets = dev_offsets;
+    ctx->n_bytes = n_bytes; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->have_batch = true;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_generate(kmb_ctx* ctx, uint64_t seed, uint64_t first_index, uint64_t n_reads,
+                                      uint64_t fixed_len, uint32_t n_thresh20) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (fixed_len == 0) return fail(ctx, KMB_ERR_INVALID_ARG, "fixed_len must be > 0");
+    const uint64_t n = n_reads * fixed_len;
+    drop_batch(ctx);
+    int32_t rc = grow(ctx, (void**)&ctx->own_bases, &ctx->own_bases_cap, n + 64);
+    if (rc) return rc;
+    if (n) {
+        const uint64_t chunks = (n + 15) / 16;
+        generate_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, ctx->stream>>>(ctx->own_bases, n, seed + first_index,
+                                                                                  n_thresh20);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    ctx->d_bases = ctx->own_bases; ctx->d_offsets = nullptr;
+    ctx->n_bytes = n; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->have_batch = true;
+    return KMB_OK;
+}
+
+#define NEED_BATCH(ctx) \
+    do { if (!(ctx)->have_batch) return fail(ctx, KMB_ERR_STATE, "no read batch resident (upload / attach / generate first)"); } while (0)
+
+extern "C" int32_t kmb_batch_download(kmb_ctx* ctx, uint8_t* dst, uint64_t n_bytes) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (n_bytes > ctx->n_bytes) return fail(ctx, KMB_ERR_INVALID_ARG, "n_bytes exceeds the batch");
+    if (n_bytes == 0) return KMB_OK;
+    CK(ctx, cudaMemcpyAsync(dst, ctx->d_bases, n_bytes, cudaMemcpyDefault, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_info(const kmb_ctx* ctx, uint64_t* n_bytes, uint64_t* n_reads, uint64_t* fixed_len) {
+    if (!ctx) return fail(nullptr, KMB_ERR_INVALID_ARG, "ctx is NULL");
+    if (!ctx->have_batch) return KMB_ERR_STATE;
+    if (n_bytes) *n_bytes = ctx->n_bytes;
+    if (n_reads) *n_reads = ctx->n_reads;
+    if (fixed_len) *fixed_len = ctx->fixed_len;
+    return KMB_OK;
+}
+
+// exclusive prefix (n_reads + 1 entries) of per-read counts; div == 0 -> windows of length k
+static int32_t scan_counts(kmb_ctx* ctx, uint32_t k, uint32_t div, uint64_t* d_out) {
+    const uint64_t n = ctx->n_reads + 1;
+    read_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_offsets, ctx->n_reads, k - 1, div, d_out);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    size_t need = 0;
+    CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, d_out, d_out, (long long)n, ctx->stream));
+    int32_t rc = grow(ctx, &ctx->d_cub, &ctx->cub_cap, need);
+    if (rc) return rc;
+    CK(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub, need, d_out, d_out, (long long)n, ctx->stream));
+    ctx->launches++;
+    return KMB_OK;
+}
+
+// makes ctx->d_win_offsets / win_total valid for k (CSR batches)
+static int32_t ensure_win_offsets(kmb_ctx* ctx, uint32_t k) {
+    if (ctx->win_valid && ctx->win_k == k) return KMB_OK;
+    int32_t rc = grow(ctx, (void**)&ctx->d_win_offsets, &ctx->win_cap, (ctx->n_reads + 1) * 8);
+    if (rc) return rc;
+    if ((rc = scan_counts(ctx, k, 0, ctx->d_win_offsets))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_win_offsets + ctx->n_reads, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->win_total = ctx->h_digest[3];
+    ctx->win_k = k;
+    ctx->win_valid = true;
+    return KMB_OK;
+}
+
+static int32_t num_slots(kmb_ctx* ctx, uint32_t k, uint64_t* out) {
+    if (ctx->d_offsets) {
+        if (ctx->n_reads == 0) { *out = 0; return KMB_OK; }
+        int32_t rc = ensure_win_offsets(ctx, k);
+        if (rc) return rc;
+        *out = ctx->win_total;
+    } else {
+        *out = ctx->fixed_len >= k ? ctx->n_reads * (ctx->fixed_len - k + 1) : 0;
+    }
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_num_slots(kmb_ctx* ctx, uint32_t k, uint64_t* n_slots) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (k < 1 || !n_slots) return fail(ctx, KMB_ERR_INVALID_ARG, "k must be >= 1 and n_slots non-NULL");
+    return num_slots(ctx, k, n_slots);
+}
+
+extern "C" int32_t kmb_batch_window_offsets(kmb_ctx* ctx, uint32_t k, uint64_t* out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (k < 1 || !out) return fail(ctx, KMB_ERR_INVALID_ARG, "k must be >= 1 and out non-NULL");
+    if (!ctx->d_offsets) return fail(ctx, KMB_ERR_STATE, "fixed-length batch: window offset of read r is r * (L - k + 1)");
+    if (ctx->n_reads == 0) {
+        CK(ctx, cudaMemsetAsync(ctx->d_digest + 3, 0, 8, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(out, ctx->d_digest + 3, 8, cudaMemcpyDefault, ctx->stream));
+    } else {
+        int32_t rc = ensure_win_offsets(ctx, k);
+        if (rc) return rc;
+        CK(ctx, cudaMemcpyAsync(out, ctx->d_win_offsets, (ctx->n_reads + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= output staging
+// A caller pointer is either device memory (used in place) or host memory
+// (device scratch now, copied back after the kernels).
+struct OutBuf {
+    void* user = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0;
+    bool host = false;
+};
+
+static int32_t out_prepare(kmb_ctx* ctx, int slot, void* user, size_t bytes, OutBuf* ob) {
+    ob->user = user; ob->bytes = bytes; ob->dev = nullptr; ob->host = false;
+    if (!user || bytes == 0) return KMB_OK;
+    if (is_device_ptr(user)) { ob->dev = user; return KMB_OK; }
+    int32_t rc = grow(ctx, &ctx->d_scratch[slot], &ctx->scratch_cap[slot], bytes);
+    if (rc) return rc;
+    ob->dev = ctx->d_scratch[slot];
+    ob->host = true;
+    return KMB_OK;
+}
+static int32_t out_finish(kmb_ctx* ctx, const OutBuf& ob) {
+    if (ob.host && ob.bytes) CK(ctx, cudaMemcpyAsync(ob.user, ob.dev, ob.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return KMB_OK;
+}
+
+static int32_t digest_begin(kmb_ctx* ctx) {
+    CK(ctx, cudaMemsetAsync(ctx->d_digest, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    return KMB_OK;
+}
+static int32_t digest_end(kmb_ctx* ctx, kmb_digest* digest) {
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest, ctx->d_digest, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    digest->n_valid = ctx->h_digest[0];
+    digest->checksum_canon = ctx->h_digest[1];
+    digest->checksum_hash = ctx->h_digest[2];
+    return KMB_OK;
+}
+
+// ======================================================================= extract (K <= 32)
+static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
+
+template <int MODE>
+static cudaError_t launch_fixed(bool validate, bool digest, bool fwrc, unsigned grid, size_t smem, cudaStream_t st,
+                                const ExtractParams& p) {
+#define KMB_LAUNCH(V, D, F)                                                                          \
+    extract_fixed_kernel<V, D, F, MODE><<<grid, kExtractThreads, smem, st>>>(p);                     \
+    return cudaGetLastError();
+    if (validate) {
+        if (digest) { if (fwrc) { KMB_LAUNCH(true, true, true) } else { KMB_LAUNCH(true, true, false) } }
+        else { if (fwrc) { KMB_LAUNCH(true, false, true) } else { KMB_LAUNCH(true, false, false) } }
+    } else {
+        if (digest) { if (fwrc) { KMB_LAUNCH(false, true, true) } else { KMB_LAUNCH(false, true, false) } }
+        else { if (fwrc) { KMB_LAUNCH(false, false, true) } else { KMB_LAUNCH(false, false, false) } }
+    }
+#undef KMB_LAUNCH
+}
+
+template <int MODE>
+static cudaError_t launch_csr(bool validate, bool digest, bool fwrc, unsigned grid, size_t smem, cudaStream_t st,
+                              const CsrParams& p) {
+#define KMB_LAUNCH(V, D, F)                                                                        \
+    extract_csr_kernel<V, D, F, MODE><<<grid, kExtractThreads, smem, st>>>(p);                     \
+    return cudaGetLastError();
+    if (validate) {
+        if (digest) { if (fwrc) { KMB_LAUNCH(true, true, true) } else { KMB_LAUNCH(true, true, false) } }
+        else { if (fwrc) { KMB_LAUNCH(true, false, true) } else { KMB_LAUNCH(true, false, false) } }
+    } else {
+        if (digest) { if (fwrc) { KMB_LAUNCH(false, true, true) } else { KMB_LAUNCH(false, true, false) } }
+        else { if (fwrc) { KMB_LAUNCH(false, false, true) } else { KMB_LAUNCH(false, false, false) } }
+    }
+#undef KMB_LAUNCH
+}
+
+struct FixedGeom {
+    uint64_t W, total_items;
+    uint32_t rpr, rpr_magic;
+    unsigned grid;
+    size_t smem;
+};
+
+static bool fixed_geom(uint64_t n_reads, uint64_t L, uint32_t k, int span_words, FixedGeom* g) {
+    g->W = L - k + 1;
+    const uint64_t rpr64 = (g->W + kRun - 1) / kRun;
+    if (rpr64 > 0xFFFFFFFFull) return false;
+    g->rpr = (uint32_t)rpr64;
+    g->rpr_magic = g->rpr > 1 ? (uint32_t)((1ull << 32) / g->rpr + 1) : 0;
+    g->total_items = n_reads * rpr64;
+    const uint64_t ctas = (g->total_items + kItemsPerCta - 1) / kItemsPerCta;
+    if (ctas > 0x7FFFFFFFull) return false;
+    g->grid = (unsigned)ctas;
+    // bases a CTA can span: kRun per item, plus up to K+7 extra at each read
+    // boundary, plus the last item's K-1 tail and alignment slack.
+    const uint64_t crossings = kItemsPerCta / g->rpr + 2;
+    const uint64_t span = (uint64_t)kItemsPerCta * kRun + crossings * (k + 7) + k + 32;
+    g->smem = (size_t)((span + 15) / 16 + span_words + 2) * sizeof(uint2);
+    return true;
+}
+
+static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint64_t n_bytes,
+                           uint64_t n_reads, uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* canon,
+                           uint64_t* hash, uint64_t* fw, uint64_t* rc, bool want_digest, unsigned long long* hist,
+                           uint32_t hist_bits, cudaStream_t st) {
+    EncDesc enc;
+    make_enc(KMB_ENC_ACGT, &enc, nullptr);
+    const bool validate = !(flags & KMB_F_NO_VALIDATE);
+    const bool fwrc = fw || rc;
+    const uint32_t mask_lo = mask32(2 * k), mask_hi = k > 16 ? mask32(2 * k - 32) : 0u;
+    const uint32_t shiftD = 2 * (48 - (kRun + k - 1));
+    if (!d_offsets) {
+        if (fixed_len < k || n_reads == 0) return KMB_OK;
+        FixedGeom g;
+        if (!fixed_geom(n_reads, fixed_len, k, 4, &g)) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+        ExtractParams p{};
+        p.bases = d_bases; p.n_bytes = n_bytes; p.L = fixed_len; p.L32 = (uint32_t)fixed_len; p.W = g.W;
+        p.rpr = g.rpr; p.rpr_magic = g.rpr_magic; p.total_items = g.total_items; p.K = k; p.shiftD = shiftD;
+        p.mask_lo = mask_lo; p.mask_hi = mask_hi;
+        p.canon = canon; p.hash = hash; p.fw = fw; p.rc = rc;
+        p.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
+        p.digest = ctx->d_digest; p.hist = hist; p.hist_shift = 2 * k - hist_bits; p.enc = enc;
+        cudaError_t e = hist ? launch_fixed<1>(validate, want_digest, false, g.grid, g.smem, st, p)
+                             : launch_fixed<0>(validate, want_digest, fwrc, g.grid, g.smem, st, p);
+        CK(ctx, e);
+        ctx->launches++;
+    } else {
+        if (n_bytes == 0 || n_reads == 0) return KMB_OK;
+        int32_t r = ensure_win_offsets(ctx, k);
+        if (r) return r;
+        CsrParams p{};
+        p.bases = d_bases; p.n_bytes = n_bytes; p.offsets = d_offsets; p.win_offsets = ctx->d_win_offsets;
+        p.n_reads = n_reads; p.K = k; p.shiftD = shiftD; p.mask_lo = mask_lo; p.mask_hi = mask_hi;
+        p.canon = canon; p.hash = hash; p.fw = fw; p.rc = rc;
+        p.digest = ctx->d_digest; p.hist = hist; p.hist_shift = 2 * k - hist_bits; p.enc = enc;
+        const uint64_t ctas = (n_bytes + kCsrTileBases - 1) / kCsrTileBases;
+        if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+        const size_t smem = (size_t)((kCsrTileBases + k + 32) / 16 + 6) * sizeof(uint2);
+        cudaError_t e = hist ? launch_csr<1>(validate, want_digest, false, (unsigned)ctas, smem, st, p)
+                             : launch_csr<0>(validate, want_digest, fwrc, (unsigned)ctas, smem, st, p);
+        CK(ctx, e);
+        ctx->launches++;
+    }
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_extract_canonical(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint64_t* canon_out,
+                                         uint64_t* hash_out, uint64_t* fw_out, uint64_t* rc_out, kmb_digest* digest) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    // naive_impl/kmer.rs:236-238 panics above 32 bases; k == 0 underflows 2*k-2
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    uint64_t n_slots = 0;
+    int32_t rc = num_slots(ctx, k, &n_slots);
+    if (rc) return rc;
+    OutBuf ob[4];
+    void* user[4] = {canon_out, hash_out, fw_out, rc_out};
+    for (int i = 0; i < 4; ++i)
+        if ((rc = out_prepare(ctx, i, user[i], n_slots * 8, &ob[i]))) return rc;
+    if (digest && (rc = digest_begin(ctx))) return rc;
+    if (n_slots) {
+        rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags,
+                         (uint64_t*)ob[0].dev, (uint64_t*)ob[1].dev, (uint64_t*)ob[2].dev, (uint64_t*)ob[3].dev,
+                         digest != nullptr, nullptr, 0, ctx->stream);
+        if (rc) return rc;
+    }
+    bool any_host = false;
+    for (int i = 0; i < 4; ++i) { if ((rc = out_finish(ctx, ob[i]))) return rc; any_host |= ob[i].host; }
+    if (digest) return digest_end(ctx, digest);
+    if (any_host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint32_t hist_bits, uint64_t* hist_out,
+                                 int32_t accumulate, kmb_digest* digest) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    if (hist_bits < 1 || hist_bits > 2 * k || hist_bits > 28 || !hist_out)
+        return fail(ctx, KMB_ERR_INVALID_ARG, "hist_bits must be in [1, min(2k, 28)] and hist_out non-NULL");
+    const size_t bytes = ((size_t)1 << hist_bits) * 8;
+    OutBuf ob;
+    int32_t rc = out_prepare(ctx, 0, hist_out, bytes, &ob);
+    if (rc) return rc;
+    if (ob.host && accumulate) CK(ctx, cudaMemcpyAsync(ob.dev, hist_out, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!accumulate) CK(ctx, cudaMemsetAsync(ob.dev, 0, bytes, ctx->stream));
+    if (digest && (rc = digest_begin(ctx))) return rc;
+    rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags, nullptr,
+                     nullptr, nullptr, nullptr, digest != nullptr, (unsigned long long*)ob.dev, hist_bits, ctx->stream);
+    if (rc) return rc;
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (digest) return digest_end(ctx, digest);
+    if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= extract wide (extension, K <= 64)
+extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t enc_id, uint32_t flags,
+                                              uint64_t* canon_out, uint64_t* hash_out, kmb_digest* digest) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (k < 1 || k > 64) return fail(ctx, KMB_ERR_INVALID_ARG, "k = %u: the two-word path supports 1 <= k <= 64", k);
+    WideParams p{};
+    if (!make_enc(enc_id, &p.enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
+    uint64_t n_slots = 0;
+    int32_t rc = num_slots(ctx, k, &n_slots);
+    if (rc) return rc;
+    OutBuf oc, oh;
+    if ((rc = out_prepare(ctx, 0, canon_out, n_slots * 16, &oc))) return rc;
+    if ((rc = out_prepare(ctx, 1, hash_out, n_slots * 16, &oh))) return rc;
+    if (digest && (rc = digest_begin(ctx))) return rc;
+    const bool validate = !(flags & KMB_F_NO_VALIDATE);
+    if (n_slots) {
+        p.bases = ctx->d_bases; p.n_bytes = ctx->n_bytes; p.K = k;
+        p.shiftD = 2 * (16 * kWideA - (kRun + k - 1));
+        for (int i = 0; i < 4; ++i) p.mask[i] = 2 * k > 32u * i ? mask32(2 * k - 32 * i) : 0u;
+        p.canon = (uint64_t*)oc.dev; p.hash = (uint64_t*)oh.dev; p.digest = ctx->d_digest;
+        unsigned grid;
+        size_t smem;
+        const bool fixed = ctx->d_offsets == nullptr;
+        if (fixed) {
+            FixedGeom g;
+            if (!fixed_geom(ctx->n_reads, ctx->fixed_len, k, kWideA + 1, &g))
+                return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+            p.L = ctx->fixed_len; p.L32 = (uint32_t)ctx->fixed_len; p.W = g.W; p.rpr = g.rpr; p.rpr_magic = g.rpr_magic;
+            p.total_items = g.total_items;
+            grid = g.grid; smem = g.smem;
+        } else {
+            if ((rc = ensure_win_offsets(ctx, k))) return rc;
+            p.offsets = ctx->d_offsets; p.win_offsets = ctx->d_win_offsets; p.n_reads = ctx->n_reads;
+            const uint64_t ctas = (ctx->n_bytes + kCsrTileBases - 1) / kCsrTileBases;
+            if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+            grid = (unsigned)ctas;
+            smem = (size_t)((kCsrTileBases + k + 32) / 16 + kWideA + 3) * sizeof(uint2);
+        }
+#define KMB_WIDE(KERNEL)                                                                              \
+        do {                                                                                          \
+            if (validate) { if (digest) KERNEL<true, true><<<grid, kExtractThreads, smem, ctx->stream>>>(p);  \
+                            else KERNEL<true, false><<<grid, kExtractThreads, smem, ctx->stream>>>(p); }      \
+            else { if (digest) KERNEL<false, true><<<grid, kExtractThreads, smem, ctx->stream>>>(p);          \
+                   else KERNEL<false, false><<<grid, kExtractThreads, smem, ctx->stream>>>(p); }              \
+        } while (0)
+        if (fixed) KMB_WIDE(extract_wide_fixed_kernel); else KMB_WIDE(extract_wide_csr_kernel);
+#undef KMB_WIDE
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    if ((rc = out_finish(ctx, oc))) return rc;
+    if ((rc = out_finish(ctx, oh))) return rc;
+    if (digest) return digest_end(ctx, digest);
+    if (oc.host || oh.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= pipelined host path
+// Chunks of reads: H2D on the copy stream, kernel on the compute stream, D2H
+// (when host outputs are wanted) back on the copy stream; two buffers in flight.
+extern "C" int32_t kmb_extract_canonical_host(kmb_ctx* ctx, const uint8_t* host_bases, uint64_t n_reads,
+                                              uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* host_canon,
+                                              uint64_t* host_hash, kmb_digest* digest) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    if (fixed_len == 0) return fail(ctx, KMB_ERR_INVALID_ARG, "fixed_len must be > 0");
+    if (n_reads && !host_bases) return fail(ctx, KMB_ERR_INVALID_ARG, "host_bases is NULL");
+    int32_t rc;
+    if (digest && (rc = digest_begin(ctx))) return rc;
+    const uint64_t W = fixed_len >= k ? fixed_len - k + 1 : 0;
+    if (W && n_reads) {
+        // chunk ~64 MiB of output per array so both directions stay busy
+        uint64_t reads_per_chunk = ((uint64_t)64 << 20) / (W * 8);
+        if (reads_per_chunk < 1) reads_per_chunk = 1;
+        // keep chunk slot starts 32-byte aligned for the vector stores
+        reads_per_chunk = (reads_per_chunk + 3) & ~3ull;
+        if (reads_per_chunk > n_reads) reads_per_chunk = n_reads;
+        const size_t in_cap = reads_per_chunk * fixed_len, out_cap = reads_per_chunk * W * 8;
+        const bool want_out = host_canon || host_hash;
+        const bool pinned_in = is_pinned_ptr(host_bases);
+        for (int i = 0; i < 2; ++i) {
+            size_t c0 = ctx->pipe_in_cap, c1 = ctx->pipe_out_cap, c2 = ctx->pipe_out_cap;
+            if ((rc = grow(ctx, (void**)&ctx->pipe_in[i], &c0, in_cap + 64))) return rc;
+            if ((rc = grow(ctx, (void**)&ctx->pipe_canon[i], &c1, out_cap))) return rc;
+            if ((rc = grow(ctx, (void**)&ctx->pipe_hash[i], &c2, out_cap))) return rc;
+            if (i == 1) { ctx->pipe_in_cap = c0; ctx->pipe_out_cap = c1; }
+        }
+        if (!pinned_in && ctx->stage_cap < in_cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (ctx->h_stage[i]) { CK(ctx, cudaFreeHost(ctx->h_stage[i])); ctx->h_stage[i] = nullptr; }
+                CK(ctx, cudaHostAlloc((void**)&ctx->h_stage[i], in_cap, cudaHostAllocDefault));
+            }
+            ctx->stage_cap = in_cap;
+        }
+        // compute stream must not overtake earlier work queued on it by the caller
+        CK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[0], 0));
+        uint64_t done = 0;
+        int buf = 0;
+        uint64_t chunk_idx = 0;
+        while (done < n_reads) {
+            const uint64_t nr = n_reads - done < reads_per_chunk ? n_reads - done : reads_per_chunk;
+            const size_t in_bytes = nr * fixed_len, out_bytes = nr * W * 8;
+            if (chunk_idx >= 2) {
+                // buffer reuse: its kernel (reads pipe_in) and its D2H (reads pipe_out) must be done
+                CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[buf], 0));
+                if (!pinned_in) CK(ctx, cudaEventSynchronize(ctx->ev_in[buf]));
+            }
+            const uint8_t* src = host_bases + done * fixed_len;
+            if (!pinned_in) { memcpy(ctx->h_stage[buf], src, in_bytes); src = ctx->h_stage[buf]; }
+            CK(ctx, cudaMemcpyAsync(ctx->pipe_in[buf], src, in_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(ctx, cudaEventRecord(ctx->ev_in[buf], ctx->copy_stream));
+            CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
+            if (chunk_idx >= 2 && want_out) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[buf], 0));
+            rc = run_extract(ctx, ctx->pipe_in[buf], nullptr, in_bytes, nr, fixed_len, k, flags, ctx->pipe_canon[buf],
+                             ctx->pipe_hash[buf], nullptr, nullptr, digest != nullptr, nullptr, 0, ctx->stream);
+            if (rc) return rc;
+            CK(ctx, cudaEventRecord(ctx->ev_k[buf], ctx->stream));
+            if (want_out) {
+                CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[buf], 0));
+                if (host_canon)
+                    CK(ctx, cudaMemcpyAsync(host_canon + done * W, ctx->pipe_canon[buf], out_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (host_hash)
+                    CK(ctx, cudaMemcpyAsync(host_hash + done * W, ctx->pipe_hash[buf], out_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK(ctx, cudaEventRecord(ctx->ev_out[buf], ctx->copy_stream));
+            }
+            done += nr;
+            buf ^= 1;
+            ++chunk_idx;
+        }
+        CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    }
+    if (digest) return digest_end(ctx, digest);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= batched Encoding<P,B>
+static bool word_bits_ok(uint32_t wb) { return wb == 8 || wb == 16 || wb == 32 || wb == 64 || wb == 128; }
+
+static int32_t pack_total_words(kmb_ctx* ctx, uint32_t word_bits, uint64_t* total, uint64_t** d_word_offsets) {
+    const uint32_t bpw = word_bits / 2;
+    if (!ctx->d_offsets) {
+        *total = ctx->n_reads * ((ctx->fixed_len + bpw - 1) / bpw);
+        if (d_word_offsets) *d_word_offsets = nullptr;
+        return KMB_OK;
+    }
+    int32_t rc = grow(ctx, &ctx->d_scratch[3], &ctx->scratch_cap[3], (ctx->n_reads + 1) * 8);
+    if (rc) return rc;
+    uint64_t* d = (uint64_t*)ctx->d_scratch[3];
+    if ((rc = scan_counts(ctx, 1, bpw, d))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, d + ctx->n_reads, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    *total = ctx->h_digest[3];
+    if (d_word_offsets) *d_word_offsets = d;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_pack_num_words(kmb_ctx* ctx, uint32_t word_bits, uint64_t* n_words) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (!word_bits_ok(word_bits) || !n_words) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128");
+    return pack_total_words(ctx, word_bits, n_words, nullptr);
+}
+
+extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, void* words_out, uint64_t* word_offsets_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (!word_bits_ok(word_bits)) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128");
+    PackParams p{};
+    if (!make_enc(enc_id, &p.enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
+    uint64_t total = 0;
+    uint64_t* d_woff = nullptr;
+    int32_t rc = pack_total_words(ctx, word_bits, &total, &d_woff);
+    if (rc) return rc;
+    const uint32_t word_bytes = word_bits / 8, bpw = word_bits / 2;
+    OutBuf ob;
+    if ((rc = out_prepare(ctx, 0, words_out, total * word_bytes, &ob))) return rc;
+    if (total && words_out) {
+        p.bases = ctx->d_bases; p.offsets = ctx->d_offsets; p.word_offsets = d_woff; p.n_reads = ctx->n_reads;
+        p.L = ctx->fixed_len; p.word_bytes = word_bytes; p.bases_per_word = bpw; p.out = (uint8_t*)ob.dev;
+        if (!ctx->d_offsets) {
+            p.out_bytes_per_read = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;
+            const uint64_t gpr = (p.out_bytes_per_read + 3) / 4;
+            const uint64_t threads = ctx->n_reads * gpr;
+            const uint64_t ctas = (threads + 255) / 256;
+            if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+            pack_fixed_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>(p, gpr);
+        } else {
+            const uint64_t ctas = (ctx->n_reads * 32 + 255) / 256;
+            if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+            pack_csr_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>(p);
+        }
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (word_offsets_out) {
+        if (d_woff) {
+            CK(ctx, cudaMemcpyAsync(word_offsets_out, d_woff, (ctx->n_reads + 1) * 8, cudaMemcpyDefault, ctx->stream));
+        } else {
+            return fail(ctx, KMB_ERR_STATE, "fixed-length batch: word offset of read r is r * ceil(L / (word_bits/2))");
+        }
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// in-buffer: device pointer used in place, host pointer staged into scratch
+static int32_t in_prepare(kmb_ctx* ctx, int slot, const void* user, size_t bytes, const void** dev) {
+    *dev = user;
+    if (!user || bytes == 0 || is_device_ptr(user)) return KMB_OK;
+    int32_t rc = grow(ctx, &ctx->d_scratch[slot], &ctx->scratch_cap[slot], bytes);
+    if (rc) return rc;
+    if ((rc = stage_h2d(ctx, ctx->d_scratch[slot], user, bytes))) return rc;
+    *dev = ctx->d_scratch[slot];
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_unpack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, const void* words_in, uint64_t n_items,
+                              uint32_t words_per_item, uint32_t bases_per_item, uint8_t* bases_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (!word_bits_ok(word_bits)) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128");
+    EncDesc enc;
+    uint32_t dec = 0;
+    if (!make_enc(enc_id, &enc, &dec)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
+    const uint64_t in_bytes_per_item = (uint64_t)words_per_item * (word_bits / 8);
+    if (bases_per_item > in_bytes_per_item * 4) return fail(ctx, KMB_ERR_INVALID_ARG, "bases_per_item exceeds the array capacity");
+    if (n_items == 0 || bases_per_item == 0) return KMB_OK;
+    if (!words_in || !bases_out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    const void* d_in;
+    int32_t rc = in_prepare(ctx, 1, words_in, n_items * in_bytes_per_item, &d_in);
+    if (rc) return rc;
+    OutBuf ob;
+    if ((rc = out_prepare(ctx, 0, bases_out, n_items * bases_per_item, &ob))) return rc;
+    const uint64_t threads = n_items * ((bases_per_item + 3) / 4);
+    const uint64_t ctas = (threads + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    unpack_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items, (uint32_t)in_bytes_per_item,
+                                                          bases_per_item, dec, (uint8_t*)ob.dev);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_revcomp_words(kmb_ctx* ctx, int32_t enc_id, uint32_t k, uint32_t word_bits, uint32_t words_per_item,
+                                     const void* words_in, void* words_out, uint64_t n_items) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (!word_bits_ok(word_bits)) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128");
+    EncDesc enc;
+    if (!make_enc(enc_id, &enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
+    const uint64_t item_bytes = (uint64_t)words_per_item * (word_bits / 8);
+    // K == 0 underflows K*2-2 and 2K > capacity trips the get_bits range assert (encoding/naive.rs:138-147)
+    if (k < 1 || 2ull * k > item_bytes * 8) return fail(ctx, KMB_ERR_PANIC, "k = %u does not fit %u x u%u", k, words_per_item, word_bits);
+    if (item_bytes > 32) return fail(ctx, KMB_ERR_INVALID_ARG, "arrays above 256 bits are not supported");
+    if (n_items == 0) return KMB_OK;
+    if (!words_in || !words_out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    const void* d_in;
+    int32_t rc = in_prepare(ctx, 1, words_in, n_items * item_bytes, &d_in);
+    if (rc) return rc;
+    OutBuf ob;
+    if ((rc = out_prepare(ctx, 0, words_out, n_items * item_bytes, &ob))) return rc;
+    const uint64_t ctas = (n_items + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    const unsigned grid = (unsigned)ctas;
+    const uint8_t* in8 = (const uint8_t*)d_in;
+    uint8_t* out8 = (uint8_t*)ob.dev;
+    const uint32_t ib = (uint32_t)item_bytes;
+    if (item_bytes <= 4) revcomp_items_kernel<1><<<grid, 256, 0, ctx->stream>>>(in8, out8, n_items, ib, k, enc.cmask);
+    else if (item_bytes <= 8) revcomp_items_kernel<2><<<grid, 256, 0, ctx->stream>>>(in8, out8, n_items, ib, k, enc.cmask);
+    else if (item_bytes <= 16) revcomp_items_kernel<4><<<grid, 256, 0, ctx->stream>>>(in8, out8, n_items, ib, k, enc.cmask);
+    else revcomp_items_kernel<8><<<grid, 256, 0, ctx->stream>>>(in8, out8, n_items, ib, k, enc.cmask);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= naive_impl::Kmer word ops
+template <int OP>
+static int32_t word_op(kmb_ctx* ctx, uint32_t k, const uint64_t* in, const uint64_t* other, uint64_t* out, uint8_t* out8,
+                       uint64_t n) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    // 2*(32-k) shifts: k == 0 overflows, k > 32 is unrepresentable (naive_impl/kmer.rs:133)
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    if (n == 0) return KMB_OK;
+    if (!in) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL input");
+    const void *d_in, *d_other = nullptr;
+    int32_t rc = in_prepare(ctx, 2, in, n * 8, &d_in);
+    if (rc) return rc;
+    if (other && (rc = in_prepare(ctx, 3, other, n * 8, &d_other))) return rc;
+    OutBuf o64, o8;
+    if ((rc = out_prepare(ctx, 0, out, n * 8, &o64))) return rc;
+    if ((rc = out_prepare(ctx, 1, out8, n, &o8))) return rc;
+    const uint64_t ctas = (n + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    word_op_kernel<OP><<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint64_t*)d_in, (const uint64_t*)d_other,
+                                                               (uint64_t*)o64.dev, (uint8_t*)o8.dev, n, k, mask);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, o64))) return rc;
+    if ((rc = out_finish(ctx, o8))) return rc;
+    if (o64.host || o8.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_reverse_complement_words(kmb_ctx* ctx, uint32_t k, const uint64_t* in, uint64_t* out, uint64_t n) {
+    if (ctx && n && !out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL output");
+    return word_op<0>(ctx, k, in, nullptr, out, nullptr, n);
+}
+extern "C" int32_t kmb_canonical_words(kmb_ctx* ctx, uint32_t k, const uint64_t* in, uint64_t* canon_out,
+                                       uint8_t* is_canonical_out, uint64_t n) {
+    return word_op<1>(ctx, k, in, nullptr, canon_out, is_canonical_out, n);
+}
+extern "C" int32_t kmb_lexhash_words(kmb_ctx* ctx, uint32_t k, const uint64_t* in, uint64_t* out, uint64_t n) {
+    if (ctx && n && !out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL output");
+    return word_op<2>(ctx, k, in, nullptr, out, nullptr, n);
+}
+extern "C" int32_t kmb_match_words(kmb_ctx* ctx, uint32_t k, const uint64_t* words, const uint64_t* others,
+                                   uint8_t* match_out, uint64_t n) {
+    if (ctx && n && (!others || !match_out)) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    return word_op<3>(ctx, k, words, others, nullptr, match_out, n);
+}

@@ -256,7 +256,8 @@ def count_slots(offsets, n_reads: int, fixed_len: int, k: int) -> int:
 
 
 def extract_canonical(bases: np.ndarray, k: int, *, offsets=None, n_reads=None, fixed_len=0,
-                      strict=False, want_fw_rc=False, hist_bits=0, n_threads=1, materialize=True):
+                      strict=False, want_fw_rc=False, hist_bits=0, n_threads=1, materialize=True,
+                      canon_out=None, hash_out=None):
     """Dense-slot canonical extraction through the restated iterator.
 
     Returns dict(canon, hash, [fw, rc], [hist], n_valid, checksum_canon, checksum_hash)."""
@@ -265,8 +266,8 @@ def extract_canonical(bases: np.ndarray, k: int, *, offsets=None, n_reads=None, 
     if o is not None:
         n_reads = o.size - 1
     n_slots = count_slots(o, n_reads, fixed_len, k)
-    canon = np.empty(n_slots, dtype=np.uint64) if materialize else None
-    hsh = np.empty(n_slots, dtype=np.uint64) if materialize else None
+    canon = canon_out if canon_out is not None else (np.empty(n_slots, dtype=np.uint64) if materialize else None)
+    hsh = hash_out if hash_out is not None else (np.empty(n_slots, dtype=np.uint64) if materialize else None)
     fw = np.empty(n_slots, dtype=np.uint64) if want_fw_rc else None
     rc = np.empty(n_slots, dtype=np.uint64) if want_fw_rc else None
     hist = np.zeros(1 << hist_bits, dtype=np.uint64) if hist_bits else None

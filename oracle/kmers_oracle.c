@@ -506,6 +506,15 @@ typedef struct {
     int status;
 } job_t;
 
+static void fill_sentinel(job_t *jb, uint64_t from, uint64_t to) {
+    for (uint64_t s = from; s < to; ++s) {
+        if (jb->canon_out) jb->canon_out[s] = KO_SENTINEL;
+        if (jb->hash_out) jb->hash_out[s] = KO_SENTINEL;
+        if (jb->fw_out) jb->fw_out[s] = KO_SENTINEL;
+        if (jb->rc_out) jb->rc_out[s] = KO_SENTINEL;
+    }
+}
+
 static void run_iterator_job(job_t *jb) {
     uint64_t slot = jb->slot0;
     unsigned k = jb->k;
@@ -514,19 +523,19 @@ static void run_iterator_job(job_t *jb) {
         uint64_t b = read_begin(jb->offsets, jb->fixed_len, r);
         uint64_t e = read_begin(jb->offsets, jb->fixed_len, r + 1);
         uint64_t w = n_windows(e - b, k);
-        for (uint64_t p = 0; p < w; ++p) {
-            if (jb->canon_out) jb->canon_out[slot + p] = KO_SENTINEL;
-            if (jb->hash_out) jb->hash_out[slot + p] = KO_SENTINEL;
-            if (jb->fw_out) jb->fw_out[slot + p] = KO_SENTINEL;
-            if (jb->rc_out) jb->rc_out[slot + p] = KO_SENTINEL;
-        }
-        /* the caller loop of SURVEY 3 S4: while !exhausted { get(); inc(); } */
+        /* the caller loop of SURVEY 3 S4: while !exhausted { get(); inc(); };
+         * positions come out increasing, the gaps between them (windows the
+         * iterator skipped) are filled with the sentinel. */
         ko_ck_iter it;
         ko_iter_from_u8_slice(&it, jb->bases + b, (size_t)(e - b), (uint8_t)k, jb->strict);
+        uint64_t next = 0; /* first slot of this read not yet written */
         while (!ko_iter_exhausted(&it)) {
             uint64_t canon = ko_ck_get_canonical_word(&it.km);
             uint64_t h = ko_lexhash_word(canon, k);
-            uint64_t s = slot + (uint64_t)it.pos;
+            uint64_t pos = (uint64_t)it.pos;
+            fill_sentinel(jb, slot + next, slot + pos);
+            next = pos + 1;
+            uint64_t s = slot + pos;
             if (jb->canon_out) jb->canon_out[s] = canon;
             if (jb->hash_out) jb->hash_out[s] = h;
             if (jb->fw_out) jb->fw_out[s] = it.km.fw.data;
@@ -537,6 +546,7 @@ static void run_iterator_job(job_t *jb) {
             jb->digest.checksum_hash += h;
             ko_iter_inc(&it);
         }
+        fill_sentinel(jb, slot + next, slot + w);
         slot += w;
     }
 }

@@ -1,0 +1,88 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports
+every symbol include/kmers_b200.h declares, and refuses to compute without a
+GPU (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as ko
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import __graft_entry__ as g
+    g.build()
+    from kmers_b200 import _native
+    return _native
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "kmers_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_all_exported(native):
+    L = native.lib()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/kmers_b200.h but not exported"
+    assert sorted(native.SIGNATURES) == names, "ctypes signature table and header drifted apart"
+    assert L.kmb_version() == 100
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "kmers_b200.h")).read()
+    assert "torch" not in hdr.lower().replace("share a stream with torch", "")
+    assert "at::" not in hdr and "c10::" not in hdr
+    assert 'extern "C"' in hdr
+
+
+def test_fails_loudly_without_gpu(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = native.lib()
+    assert L.kmb_device_count() == 0
+    h = C.c_void_p()
+    assert L.kmb_ctx_create(0, None, C.byref(h)) == native.ERR_NO_DEVICE
+    assert b"no CPU fallback" in L.kmb_last_error(None)
+    import kmers_b200 as kb
+    with pytest.raises(kb.KmbError):
+        kb.Context(0)
+
+
+def test_null_ctx_is_an_error_not_a_crash(native):
+    L = native.lib()
+    assert L.kmb_ctx_sync(None) == native.ERR_INVALID_ARG
+    assert L.kmb_extract_canonical(None, 31, 0, None, None, None, None, None) == native.ERR_INVALID_ARG
+    assert L.kmb_ctx_destroy(None) == native.OK
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "kmers_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "kmers_oracle" not in src, f
+
+
+def test_naive_enum_matches_reference_table():
+    import kmers_b200 as kb
+    assert {m.name: int(m) for m in kb.Naive} == ko.NAIVE  # encoding/naive.rs:49-74
+    assert int(kb.Xor10) == kb.ENC_XOR10
+    # kmer.rs:97-118 choose_number_of_word
+    for wb, cases in {8: [(1, 1), (4, 1), (5, 2)], 16: [(1, 1), (8, 1), (9, 2)], 32: [(1, 1), (16, 1), (17, 2)],
+                      64: [(1, 1), (32, 1), (64, 2)], 128: [(1, 1), (64, 1), (65, 2)]}.items():
+        for k, want in cases:
+            assert kb.word_for_k(wb, k) == want == ko.lib().ko_word_for_k(wb, k)
+    assert [kb.num_bytes(wb, 15) for wb in (8, 16, 32, 64, 128)] == [4, 4, 4, 8, 16]  # kmer.rs:120-153
