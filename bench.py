@@ -188,8 +188,9 @@ def main():
     n_reads, L = args.reads, READ_LEN
     W = L - K + 1
     n_slots = n_reads * W
-    stream = torch.cuda.current_stream()
-    ctx = kb.Context(local_rank, stream=stream.cuda_stream)  # kernels run on torch's current stream -> torch events see them
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)  # torch work, the kernels and the timing events all share this stream
+    ctx = kb.Context(local_rank, stream=stream.cuda_stream)
     # rank r owns reads [r*n_reads, (r+1)*n_reads) of one synthetic data set
     batch = ctx.generate(SEED, n_reads, L, n_thresh20=0, first_index=rank * n_reads * L)
     out = kb.CanonicalKmers(k=K, n_slots=n_slots)

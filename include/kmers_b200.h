@@ -80,7 +80,8 @@ int32_t kmb_version(void);
 int32_t kmb_device_count(void);
 /* device < 0: current device.  stream == NULL: the ctx creates its own
  * non-blocking stream; otherwise it borrows the caller's cudaStream_t (so the
- * ctx can share a stream with torch / other CUDA code). */
+ * ctx can share a stream with torch / other CUDA code).  To borrow the legacy
+ * default stream pass cudaStreamLegacy ((void*)1), not NULL. */
 int32_t kmb_ctx_create(int32_t device, void *cuda_stream, kmb_ctx **out);
 int32_t kmb_ctx_destroy(kmb_ctx *ctx);
 const char *kmb_last_error(const kmb_ctx *ctx); /* ctx may be NULL: last ctx-less error of this thread */

@@ -71,7 +71,11 @@ class Context:
     """One per (host thread, GPU).  Not thread-safe; contexts are independent."""
 
     def __init__(self, device: int = -1, stream: Optional[int] = None):
+        """stream=None: the context owns a private non-blocking stream.  stream=<cudaStream_t handle>
+        (e.g. torch.cuda.current_stream().cuda_stream): borrow it; handle 0 means the legacy default stream."""
         self._lib = nv.lib()
+        if stream is not None and int(stream) == 0:
+            stream = 1  # cudaStreamLegacy
         h = C.c_void_p()
         check(None, self._lib.kmb_ctx_create(device, stream, C.byref(h)))
         self._h = h

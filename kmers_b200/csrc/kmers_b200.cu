@@ -130,6 +130,7 @@ extern "C" int32_t kmb_ctx_create(int32_t device, void* cuda_stream, kmb_ctx** o
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) {
+        // (void*)1 / (void*)2 are cudaStreamLegacy / cudaStreamPerThread: valid borrowed handles
         if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
         else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
     }
@@ -428,7 +429,8 @@ extern "C" int32_t kmb_batch_num_slots(kmb_ctx* ctx, uint32_t k, uint64_t* n_slo
     NEED_CTX(ctx);
     BIND(ctx);
     NEED_BATCH(ctx);
-    if (k < 1 || !n_slots) return fail(ctx, KMB_ERR_INVALID_ARG, "k must be >= 1 and n_slots non-NULL");
+    if (!n_slots) return fail(ctx, KMB_ERR_INVALID_ARG, "n_slots is NULL");
+    if (k < 1) return fail(ctx, KMB_ERR_PANIC, "k = 0: a window needs at least one base (2*k-2 underflows, SURVEY Q14)");
     return num_slots(ctx, k, n_slots);
 }
 
