@@ -1,0 +1,22 @@
+// UNVERIFIED SOURCE (no Rust toolchain in the build image).
+// Compiles the CUDA translation unit for sm_100a and links it plus the CUDA runtime.
+use std::{env, path::PathBuf, process::Command};
+
+fn main() {
+    let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
+    let src = root.join("kmers_b200/csrc/kmers_b200.cu");
+    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
+    let lib = out.join("libkmers_b200.so");
+    let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
+    let status = Command::new(nvcc)
+        .args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o"])
+        .arg(&lib)
+        .arg(&src)
+        .status()
+        .expect("nvcc not runnable");
+    assert!(status.success(), "nvcc failed");
+    println!("cargo:rustc-link-search=native={}", out.display());
+    println!("cargo:rustc-link-lib=dylib=kmers_b200");
+    println!("cargo:rerun-if-changed={}", root.join("kmers_b200/csrc").display());
+    println!("cargo:rerun-if-changed={}", root.join("include/kmers_b200.h").display());
+}

@@ -1,0 +1,62 @@
+//! UNVERIFIED SOURCE.  `extern "C"` view of include/kmers_b200.h (one line per entry point).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+pub const KMB_OK: i32 = 0;
+pub const KMB_ERR_INVALID_ARG: i32 = -1;
+pub const KMB_ERR_CUDA: i32 = -2;
+pub const KMB_ERR_NO_DEVICE: i32 = -3;
+pub const KMB_ERR_STATE: i32 = -4;
+pub const KMB_ERR_PANIC: i32 = -5;
+pub const KMB_ERR_NOMEM: i32 = -6;
+pub const KMB_SENTINEL: u64 = u64::MAX;
+pub const KMB_ENC_XOR10: i32 = 0x100;
+pub const KMB_F_NO_VALIDATE: u32 = 1;
+
+#[repr(C)]
+pub struct kmb_ctx {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Default, Clone, Copy, Debug, PartialEq, Eq)]
+pub struct kmb_digest {
+    pub n_valid: u64,
+    pub checksum_canon: u64,
+    pub checksum_hash: u64,
+}
+
+extern "C" {
+    pub fn kmb_version() -> i32;
+    pub fn kmb_device_count() -> i32;
+    pub fn kmb_ctx_create(device: i32, cuda_stream: *mut c_void, out: *mut *mut kmb_ctx) -> i32;
+    pub fn kmb_ctx_destroy(ctx: *mut kmb_ctx) -> i32;
+    pub fn kmb_last_error(ctx: *const kmb_ctx) -> *const c_char;
+    pub fn kmb_ctx_sync(ctx: *mut kmb_ctx) -> i32;
+    pub fn kmb_ctx_stream(ctx: *mut kmb_ctx) -> *mut c_void;
+    pub fn kmb_ctx_launch_count(ctx: *const kmb_ctx) -> u64;
+    pub fn kmb_device_alloc(ctx: *mut kmb_ctx, bytes: usize, out: *mut *mut c_void) -> i32;
+    pub fn kmb_device_free(ctx: *mut kmb_ctx, ptr: *mut c_void) -> i32;
+    pub fn kmb_host_alloc_pinned(ctx: *mut kmb_ctx, bytes: usize, out: *mut *mut c_void) -> i32;
+    pub fn kmb_host_free_pinned(ctx: *mut kmb_ctx, ptr: *mut c_void) -> i32;
+    pub fn kmb_memcpy(ctx: *mut kmb_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> i32;
+    pub fn kmb_batch_upload(ctx: *mut kmb_ctx, bases: *const u8, n_bytes: u64, offsets: *const u64, n_reads: u64, fixed_len: u64) -> i32;
+    pub fn kmb_batch_attach(ctx: *mut kmb_ctx, dev_bases: *const u8, n_bytes: u64, dev_offsets: *const u64, n_reads: u64, fixed_len: u64) -> i32;
+    pub fn kmb_batch_generate(ctx: *mut kmb_ctx, seed: u64, first_index: u64, n_reads: u64, fixed_len: u64, n_thresh20: u32) -> i32;
+    pub fn kmb_batch_download(ctx: *mut kmb_ctx, dst: *mut u8, n_bytes: u64) -> i32;
+    pub fn kmb_batch_info(ctx: *const kmb_ctx, n_bytes: *mut u64, n_reads: *mut u64, fixed_len: *mut u64) -> i32;
+    pub fn kmb_batch_num_slots(ctx: *mut kmb_ctx, k: u32, n_slots: *mut u64) -> i32;
+    pub fn kmb_batch_window_offsets(ctx: *mut kmb_ctx, k: u32, win_offsets_out: *mut u64) -> i32;
+    pub fn kmb_extract_canonical(ctx: *mut kmb_ctx, k: u32, flags: u32, canon_out: *mut u64, hash_out: *mut u64, fw_out: *mut u64, rc_out: *mut u64, digest: *mut kmb_digest) -> i32;
+    pub fn kmb_extract_canonical_wide(ctx: *mut kmb_ctx, k: u32, enc: i32, flags: u32, canon_out: *mut u64, hash_out: *mut u64, digest: *mut kmb_digest) -> i32;
+    pub fn kmb_histogram(ctx: *mut kmb_ctx, k: u32, flags: u32, hist_bits: u32, hist_out: *mut u64, accumulate: i32, digest: *mut kmb_digest) -> i32;
+    pub fn kmb_extract_canonical_host(ctx: *mut kmb_ctx, host_bases: *const u8, n_reads: u64, fixed_len: u64, k: u32, flags: u32, host_canon: *mut u64, host_hash: *mut u64, digest: *mut kmb_digest) -> i32;
+    pub fn kmb_pack(ctx: *mut kmb_ctx, enc: i32, word_bits: u32, words_out: *mut c_void, word_offsets_out: *mut u64) -> i32;
+    pub fn kmb_pack_num_words(ctx: *mut kmb_ctx, word_bits: u32, n_words: *mut u64) -> i32;
+    pub fn kmb_unpack(ctx: *mut kmb_ctx, enc: i32, word_bits: u32, words_in: *const c_void, n_items: u64, words_per_item: u32, bases_per_item: u32, bases_out: *mut u8) -> i32;
+    pub fn kmb_revcomp_words(ctx: *mut kmb_ctx, enc: i32, k: u32, word_bits: u32, words_per_item: u32, words_in: *const c_void, words_out: *mut c_void, n_items: u64) -> i32;
+    pub fn kmb_reverse_complement_words(ctx: *mut kmb_ctx, k: u32, input: *const u64, out: *mut u64, n: u64) -> i32;
+    pub fn kmb_canonical_words(ctx: *mut kmb_ctx, k: u32, input: *const u64, canon_out: *mut u64, is_canonical_out: *mut u8, n: u64) -> i32;
+    pub fn kmb_lexhash_words(ctx: *mut kmb_ctx, k: u32, input: *const u64, out: *mut u64, n: u64) -> i32;
+    pub fn kmb_match_words(ctx: *mut kmb_ctx, k: u32, words: *const u64, others: *const u64, match_out: *mut u8, n: u64) -> i32;
+}

@@ -1,0 +1,124 @@
+"""BASELINE.json configs at their FULL sizes, checked through size-independent properties (the oracle cannot
+materialise 19 GB in seconds, so: digests from the multi-threaded oracle, sums of the materialised arrays,
+idempotence, hash-of-canonical, strand symmetry, and bit-exact comparison of random chunks)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N_READS, L, K, SEED = 10_000_000, 150, 31, 42
+W = L - K + 1
+
+
+@pytest.fixture(scope="module")
+def full():
+    import torch
+    import kmers_b200 as kb
+    ctx = kb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    batch = ctx.generate(SEED, N_READS, L)
+    res = batch.extract_canonical(K, digest=True, to="device")
+    torch.cuda.synchronize()
+    yield ctx, batch, res
+    ctx.close()
+
+
+def _u64sum(t):
+    return int(t.sum().item()) % 2**64
+
+
+def test_config2_digest_matches_oracle_and_arrays(full):
+    import oracle as ko
+    ctx, batch, res = full
+    assert res.n_slots == N_READS * W
+    # checksum of checksums: device digest == sum of the materialised arrays == multi-threaded oracle digest
+    assert res.digest == (N_READS * W, _u64sum(res.canon), _u64sum(res.hash))
+    bases = ko.generate_bases(SEED, 0, N_READS * L)
+    ref = ko.extract_canonical(bases, K, n_reads=N_READS, fixed_len=L, n_threads=os.cpu_count() or 1, materialize=False)
+    assert res.digest == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+
+
+def test_config2_random_chunks_bit_exact(full):
+    import oracle as ko
+    ctx, batch, res = full
+    rng = np.random.default_rng(0)
+    for r0 in [0, N_READS - 5000] + [int(x) for x in rng.integers(0, N_READS - 5000, size=10)]:
+        bases = ko.generate_bases(SEED, r0 * L, 5000 * L)
+        ref = ko.extract_canonical(bases, K, n_reads=5000, fixed_len=L)
+        sl = slice(r0 * W, (r0 + 5000) * W)
+        assert np.array_equal(res.canon[sl].cpu().numpy().view(np.uint64), ref["canon"])
+        assert np.array_equal(res.hash[sl].cpu().numpy().view(np.uint64), ref["hash"])
+
+
+def test_config2_idempotence_and_hash_of_canonical(full):
+    """to_canonical(canonical) == canonical, is_canonical; LexHasher(canonical) == the hash array."""
+    import torch
+    ctx, batch, res = full
+    c2, flag = ctx.canonical_words(res.canon, K)
+    assert torch.equal(c2, res.canon) and bool(flag.all())
+    assert torch.equal(ctx.lexhash_words(res.canon, K), res.hash)
+    rc = ctx.reverse_complement_words(res.canon, K)
+    # canonical <= its reverse complement as unsigned numbers (both < 2^62, so signed compare is fine)
+    assert bool((res.canon <= rc).all())
+
+
+def test_config2_strand_symmetry(full):
+    """Reverse-complementing every read reverses each read's canonical / hash arrays."""
+    import torch
+    import kmers_b200 as kb
+    ctx, batch, res = full
+    want_c = res.canon.view(N_READS, W).flip(1).contiguous()
+    want_h = res.hash.view(N_READS, W).flip(1).contiguous()
+    bases = torch.from_numpy(batch.download()).cuda()
+    lut = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    for a, b in zip(b"ACGT", b"TGCA"):
+        lut[a] = b
+    rc_reads = lut[bases.view(N_READS, L).flip(1).long()].contiguous().view(-1)
+    del bases
+    with kb.Context(0, stream=torch.cuda.current_stream().cuda_stream) as ctx2:
+        r2 = ctx2.attach(rc_reads, fixed_len=L).extract_canonical(K, to="device")
+        torch.cuda.synchronize()
+        assert torch.equal(r2.canon.view(N_READS, W), want_c)
+        assert torch.equal(r2.hash.view(N_READS, W), want_h)
+
+
+def test_config3_k63_two_words_full_size():
+    """K=63 over the same 10^7 reads: digest == sums of the arrays; random chunks vs the oracle extension."""
+    import torch
+    import kmers_b200 as kb
+    import oracle as ko
+    with kb.Context(0, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        batch = ctx.generate(SEED, N_READS, L)
+        res = batch.extract_canonical_wide(63, want_hash=False, digest=True, to="device")
+        torch.cuda.synchronize()
+        w63 = L - 63 + 1
+        assert res.n_slots == N_READS * w63 and res.digest[0] == N_READS * w63
+        assert res.digest[1] == _u64sum(res.canon)
+        for r0 in (0, 4_321_000, N_READS - 300):
+            bases = ko.generate_bases(SEED, r0 * L, 300 * L)
+            ref = ko.extract_canonical_wide(bases, 63, n_reads=300, fixed_len=L, want_hash=False)
+            got = res.canon[2 * r0 * w63:2 * (r0 + 300) * w63].cpu().numpy().view(np.uint64).reshape(-1, 2)
+            assert np.array_equal(got, ref["canon"])
+
+
+def test_config4_long_reads_full_size():
+    """10^5 x 10 kbp with ~0.1 % N: digest vs the multi-threaded oracle, sums of arrays, chunk compare."""
+    import torch
+    import kmers_b200 as kb
+    import oracle as ko
+    n, Lr = 100_000, 10_000
+    with kb.Context(0, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        batch = ctx.generate(43, n, Lr, n_thresh20=1049)
+        res = batch.extract_canonical(K, digest=True, to="device")
+        torch.cuda.synchronize()
+        valid = res.canon != -1
+        assert res.digest[0] == int(valid.sum().item())
+        assert res.digest[1] == _u64sum(torch.where(valid, res.canon, torch.zeros_like(res.canon)))
+        bases = ko.generate_bases(43, 0, n * Lr, 1049)
+        ref = ko.extract_canonical(bases, K, n_reads=n, fixed_len=Lr, n_threads=os.cpu_count() or 1, materialize=False)
+        assert res.digest == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+        wr = Lr - K + 1
+        for r0 in (0, 77_777, n - 20):
+            ref = ko.extract_canonical(bases[r0 * Lr:(r0 + 20) * Lr], K, n_reads=20, fixed_len=Lr)
+            assert np.array_equal(res.canon[r0 * wr:(r0 + 20) * wr].cpu().numpy().view(np.uint64), ref["canon"])
+            assert np.array_equal(res.hash[r0 * wr:(r0 + 20) * wr].cpu().numpy().view(np.uint64), ref["hash"])
