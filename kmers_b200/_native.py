@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libkmers_b200.so")
+SO_PATH = os.environ.get("KMERS_B200_SO") or os.path.join(_HERE, "libkmers_b200.so")  # env override: kernel experiments
 
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_PANIC, ERR_NOMEM = -1, -2, -3, -4, -5, -6

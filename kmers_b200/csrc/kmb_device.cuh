@@ -19,15 +19,20 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
                  : "l"(p));
     return r;
 }
-// 32-byte (256-bit, sm_100+) streaming store: one full sector per lane.
+// Output stores.  The result arrays are written once and never re-read by the
+// kernel: KMB_ST selects the cache operator (default .cs = streaming / evict-first).
+#ifndef KMB_ST
+#define KMB_ST ".cs"
+#endif
+// 32-byte (256-bit, sm_100+) store: one full sector per lane.
 __device__ __forceinline__ void st_stream_v4u64(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
-    asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+    asm volatile("st.global" KMB_ST ".v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 __device__ __forceinline__ void st_stream_v2u64(uint64_t* p, uint64_t a, uint64_t b) {
-    asm volatile("st.global.cs.v2.b64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    asm volatile("st.global" KMB_ST ".v2.b64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void st_stream_u64(uint64_t* p, uint64_t a) {
-    asm volatile("st.global.cs.b64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+    asm volatile("st.global" KMB_ST ".b64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
 }
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -83,18 +88,20 @@ __device__ __forceinline__ uint32_t pack4_top(uint32_t w) {
     return x * 0x01041040u;
 }
 
-// 4 ASCII bytes -> 4-bit "invalid" mask in bits 31:28 (bit 28+i = byte i is
-// not one of ACGTacgt, naive_impl/mod.rs:40-50).  The 2-bit code already says
-// which letter the byte must be; rebuild that letter and compare.
-__device__ __forceinline__ uint32_t invalid4_top(uint32_t w) {
+// 4 ASCII bytes -> per-byte difference from the letter the byte claims to be;
+// a non-zero byte = not one of ACGTacgt (naive_impl/mod.rs:40-50).  The 2-bit
+// code already says which letter the byte must be; rebuild that letter (upper
+// case) from bits 2:1 and compare with the case-folded byte.
+__device__ __forceinline__ uint32_t letter_diff4(uint32_t w) {
     // expected upper-case byte from bits 2:1 : A 0x41, C 0x43, G 0x47, T 0x45^0x11
     uint32_t e0 = (w & 0x06060606u) | 0x41414141u;
     uint32_t t = (w >> 2) & ~(w >> 1) & 0x01010101u;  // the byte claims to be T
-    uint32_t diff = ((w & 0xDFDFDFDFu) ^ e0) ^ (t * 0x11u);
-    // non-zero byte -> its bit 7
-    uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;
-    // bits 7,15,23,31 -> 28,29,30,31
-    return nz * 0x00204081u;
+    return ((w & 0xDFDFDFDFu) ^ e0) ^ (t * 0x11u);
+}
+// per-byte non-zero -> 4-bit mask in bits 31:28 (bit 28+i = byte i)
+__device__ __forceinline__ uint32_t nonzero4_top(uint32_t diff) {
+    uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;  // non-zero byte -> its bit 7
+    return nz * 0x00204081u;                                                   // bits 7,15,23,31 -> 28..31
 }
 
 struct PackedWord {
@@ -110,11 +117,14 @@ __device__ __forceinline__ PackedWord pack16(uint4 v) {
     r.bits = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
     r.inv = 0;
     if (VALIDATE) {
-        uint32_t acc = invalid4_top(v.w) >> 28;
-        acc = __funnelshift_l(invalid4_top(v.z), acc, 4);
-        acc = __funnelshift_l(invalid4_top(v.y), acc, 4);
-        acc = __funnelshift_l(invalid4_top(v.x), acc, 4);
-        r.inv = acc;
+        const uint32_t d0 = letter_diff4(v.x), d1 = letter_diff4(v.y), d2 = letter_diff4(v.z), d3 = letter_diff4(v.w);
+        if ((d0 | d1 | d2 | d3) != 0u) {  // rare: only then locate the offending bytes
+            uint32_t acc = nonzero4_top(d3) >> 28;
+            acc = __funnelshift_l(nonzero4_top(d2), acc, 4);
+            acc = __funnelshift_l(nonzero4_top(d1), acc, 4);
+            acc = __funnelshift_l(nonzero4_top(d0), acc, 4);
+            r.inv = acc;
+        }
     }
     return r;
 }
@@ -122,7 +132,7 @@ __device__ __forceinline__ PackedWord pack16(uint4 v) {
 // Guarded 16-byte fetch of the flat read stream: vector load when the chunk
 // lies wholly inside [base, base+n), else byte-wise with zeros outside (a zero
 // byte is an invalid base, so nothing outside the batch can form a window).
-__device__ __forceinline__ uint4 load16_guarded(const uint8_t* base, uint64_t n_bytes, const uint8_t* p) {
+__device__ __noinline__ uint4 load16_guarded(const uint8_t* base, uint64_t n_bytes, const uint8_t* p) {
     if (p >= base && p + 16 <= base + n_bytes) return ld_stream_v4(p);
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -146,6 +156,9 @@ __device__ __forceinline__ void shr96(uint32_t& d0, uint32_t& d1, uint32_t& d2, 
         d0 = __funnelshift_r(c0, c1, s); d1 = __funnelshift_r(c1, c2, s); d2 = c2 >> s;
     }
 }
+
+// n / d through a precomputed magic = floor(2^64 / d) + 1 (d >= 2); exact while n * d < 2^64
+__device__ __forceinline__ uint64_t div_magic64(uint64_t n, uint64_t magic) { return __umul64hi(n, magic); }
 
 __device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include <cub/device/device_scan.cuh>
 
@@ -493,40 +494,44 @@ static int32_t digest_end(kmb_ctx* ctx, kmb_digest* digest) {
 // ======================================================================= extract (K <= 32)
 static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
 
-template <int MODE>
-static cudaError_t launch_fixed(bool validate, bool digest, bool fwrc, unsigned grid, size_t smem, cudaStream_t st,
-                                const ExtractParams& p) {
-#define KMB_LAUNCH(V, D, F)                                                                          \
-    extract_fixed_kernel<V, D, F, MODE><<<grid, kExtractThreads, smem, st>>>(p);                     \
-    return cudaGetLastError();
-    if (validate) {
-        if (digest) { if (fwrc) { KMB_LAUNCH(true, true, true) } else { KMB_LAUNCH(true, true, false) } }
-        else { if (fwrc) { KMB_LAUNCH(true, false, true) } else { KMB_LAUNCH(true, false, false) } }
-    } else {
-        if (digest) { if (fwrc) { KMB_LAUNCH(false, true, true) } else { KMB_LAUNCH(false, true, false) } }
-        else { if (fwrc) { KMB_LAUNCH(false, false, true) } else { KMB_LAUNCH(false, false, false) } }
+// Template dispatch: VALIDATE x DIGEST x FWRC x KHI for one MODE.
+template <int MODE, class Params, class Launch>
+static cudaError_t dispatch5(bool validate, bool digest, bool fwrc, bool khi, const Launch& launch) {
+#define KMB_CASE(V, D, F, H) if (validate == V && digest == D && fwrc == F && khi == H) { launch(std::integral_constant<bool, V>{}, std::integral_constant<bool, D>{}, std::integral_constant<bool, F>{}, std::integral_constant<bool, H>{}); return cudaGetLastError(); }
+    KMB_CASE(true, false, false, true) KMB_CASE(true, false, false, false)
+    KMB_CASE(true, true, false, true) KMB_CASE(true, true, false, false)
+    KMB_CASE(false, false, false, true) KMB_CASE(false, false, false, false)
+    KMB_CASE(false, true, false, true) KMB_CASE(false, true, false, false)
+    if (MODE == 0) {
+        KMB_CASE(true, false, true, true) KMB_CASE(true, false, true, false)
+        KMB_CASE(true, true, true, true) KMB_CASE(true, true, true, false)
+        KMB_CASE(false, false, true, true) KMB_CASE(false, false, true, false)
+        KMB_CASE(false, true, true, true) KMB_CASE(false, true, true, false)
     }
-#undef KMB_LAUNCH
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
 }
 
 template <int MODE>
-static cudaError_t launch_csr(bool validate, bool digest, bool fwrc, unsigned grid, size_t smem, cudaStream_t st,
-                              const CsrParams& p) {
-#define KMB_LAUNCH(V, D, F)                                                                        \
-    extract_csr_kernel<V, D, F, MODE><<<grid, kExtractThreads, smem, st>>>(p);                     \
-    return cudaGetLastError();
-    if (validate) {
-        if (digest) { if (fwrc) { KMB_LAUNCH(true, true, true) } else { KMB_LAUNCH(true, true, false) } }
-        else { if (fwrc) { KMB_LAUNCH(true, false, true) } else { KMB_LAUNCH(true, false, false) } }
-    } else {
-        if (digest) { if (fwrc) { KMB_LAUNCH(false, true, true) } else { KMB_LAUNCH(false, true, false) } }
-        else { if (fwrc) { KMB_LAUNCH(false, false, true) } else { KMB_LAUNCH(false, false, false) } }
-    }
-#undef KMB_LAUNCH
+static cudaError_t launch_fixed(bool validate, bool digest, bool fwrc, bool khi, unsigned grid, size_t smem,
+                                cudaStream_t st, const ExtractParams& p) {
+    return dispatch5<MODE, ExtractParams>(validate, digest, fwrc, khi, [&](auto V, auto D, auto F, auto H) {
+        extract_fixed_kernel<decltype(V)::value, decltype(D)::value, (MODE == 0) && decltype(F)::value, MODE, decltype(H)::value>
+            <<<grid, kExtractThreads, smem, st>>>(p);
+    });
+}
+
+template <int MODE>
+static cudaError_t launch_csr(bool validate, bool digest, bool fwrc, bool khi, unsigned grid, size_t smem,
+                              cudaStream_t st, const CsrParams& p) {
+    return dispatch5<MODE, CsrParams>(validate, digest, fwrc, khi, [&](auto V, auto D, auto F, auto H) {
+        extract_csr_kernel<decltype(V)::value, decltype(D)::value, (MODE == 0) && decltype(F)::value, MODE, decltype(H)::value>
+            <<<grid, kExtractThreads, smem, st>>>(p);
+    });
 }
 
 struct FixedGeom {
-    uint64_t W, total_items;
+    uint64_t W, total_items, rpr_magic64;
     uint32_t rpr, rpr_magic;
     unsigned grid;
     size_t smem;
@@ -539,15 +544,31 @@ static bool fixed_geom(uint64_t n_reads, uint64_t L, uint32_t k, int span_words,
     g->rpr = (uint32_t)rpr64;
     g->rpr_magic = g->rpr > 1 ? (uint32_t)((1ull << 32) / g->rpr + 1) : 0;
     g->total_items = n_reads * rpr64;
+    // item / rpr by multiplication is exact while item * rpr < 2^64; otherwise the kernel divides
+    const bool magic_ok = g->rpr > 1 && (double)g->total_items * (double)g->rpr < 9.0e18;
+    g->rpr_magic64 = magic_ok ? (~0ull / g->rpr + 1) : 0;
     const uint64_t ctas = (g->total_items + kItemsPerCta - 1) / kItemsPerCta;
     if (ctas > 0x7FFFFFFFull) return false;
     g->grid = (unsigned)ctas;
-    // bases a CTA can span: kRun per item, plus up to K+7 extra at each read
+    // bases a CTA can span: kRun per item, plus up to K-1 extra at each read
     // boundary, plus the last item's K-1 tail and alignment slack.
     const uint64_t crossings = kItemsPerCta / g->rpr + 2;
     const uint64_t span = (uint64_t)kItemsPerCta * kRun + crossings * (k + 7) + k + 32;
     g->smem = (size_t)((span + 15) / 16 + span_words + 2) * sizeof(uint2);
     return true;
+}
+
+static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
+    WinConst wc{};
+    wc.K = k;
+    wc.shiftD = 2 * (48 - (kRun + k - 1));
+    wc.mask_lo = mask32(2 * k);
+    wc.mask_hi = k > 16 ? mask32(2 * k - 32) : 0u;
+    wc.cmask = enc.cmask;
+    wc.cm_lo = enc.cmask & wc.mask_lo;
+    wc.cm_hi = enc.cmask & wc.mask_hi;
+    wc.kmask = mask32(k);
+    return wc;
 }
 
 static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint64_t n_bytes,
@@ -558,21 +579,21 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, const uint64_t*
     make_enc(KMB_ENC_ACGT, &enc, nullptr);
     const bool validate = !(flags & KMB_F_NO_VALIDATE);
     const bool fwrc = fw || rc;
-    const uint32_t mask_lo = mask32(2 * k), mask_hi = k > 16 ? mask32(2 * k - 32) : 0u;
-    const uint32_t shiftD = 2 * (48 - (kRun + k - 1));
+    const bool khi = k > 16;
+    OutPtrs out{};
+    out.canon = canon; out.hash = hash; out.fw = fw; out.rc = rc;
+    out.digest = ctx->d_digest; out.hist = hist; out.hist_shift = 2 * k - hist_bits;
+    out.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
     if (!d_offsets) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
         FixedGeom g;
         if (!fixed_geom(n_reads, fixed_len, k, 4, &g)) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
         ExtractParams p{};
         p.bases = d_bases; p.n_bytes = n_bytes; p.L = fixed_len; p.L32 = (uint32_t)fixed_len; p.W = g.W;
-        p.rpr = g.rpr; p.rpr_magic = g.rpr_magic; p.total_items = g.total_items; p.K = k; p.shiftD = shiftD;
-        p.mask_lo = mask_lo; p.mask_hi = mask_hi;
-        p.canon = canon; p.hash = hash; p.fw = fw; p.rc = rc;
-        p.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
-        p.digest = ctx->d_digest; p.hist = hist; p.hist_shift = 2 * k - hist_bits; p.enc = enc;
-        cudaError_t e = hist ? launch_fixed<1>(validate, want_digest, false, g.grid, g.smem, st, p)
-                             : launch_fixed<0>(validate, want_digest, fwrc, g.grid, g.smem, st, p);
+        p.rpr = g.rpr; p.rpr_magic = g.rpr_magic; p.rpr_magic64 = g.rpr_magic64; p.total_items = g.total_items;
+        p.wc = make_winconst(k, enc); p.out = out; p.enc = enc;
+        cudaError_t e = hist ? launch_fixed<1>(validate, want_digest, false, khi, g.grid, g.smem, st, p)
+                             : launch_fixed<0>(validate, want_digest, fwrc, khi, g.grid, g.smem, st, p);
         CK(ctx, e);
         ctx->launches++;
     } else {
@@ -581,14 +602,12 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, const uint64_t*
         if (r) return r;
         CsrParams p{};
         p.bases = d_bases; p.n_bytes = n_bytes; p.offsets = d_offsets; p.win_offsets = ctx->d_win_offsets;
-        p.n_reads = n_reads; p.K = k; p.shiftD = shiftD; p.mask_lo = mask_lo; p.mask_hi = mask_hi;
-        p.canon = canon; p.hash = hash; p.fw = fw; p.rc = rc;
-        p.digest = ctx->d_digest; p.hist = hist; p.hist_shift = 2 * k - hist_bits; p.enc = enc;
+        p.n_reads = n_reads; p.wc = make_winconst(k, enc); p.out = out; p.enc = enc;
         const uint64_t ctas = (n_bytes + kCsrTileBases - 1) / kCsrTileBases;
         if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
         const size_t smem = (size_t)((kCsrTileBases + k + 32) / 16 + 6) * sizeof(uint2);
-        cudaError_t e = hist ? launch_csr<1>(validate, want_digest, false, (unsigned)ctas, smem, st, p)
-                             : launch_csr<0>(validate, want_digest, fwrc, (unsigned)ctas, smem, st, p);
+        cudaError_t e = hist ? launch_csr<1>(validate, want_digest, false, khi, (unsigned)ctas, smem, st, p)
+                             : launch_csr<0>(validate, want_digest, fwrc, khi, (unsigned)ctas, smem, st, p);
         CK(ctx, e);
         ctx->launches++;
     }
