@@ -57,12 +57,13 @@ struct ExtractParams {
     const uint8_t* bases;   // flat read stream
     uint64_t n_bytes;       // n_reads * L
     uint64_t L;             // read length
-    uint64_t W;             // windows per read = L - K + 1
-    uint64_t total_items;   // n_reads * rpr
-    uint64_t rpr_magic64;   // floor(2^64 / rpr) + 1 (rpr >= 2), 0 = divide
+    uint64_t W;             // windows (= output slots) per read = L - K + 1
+    uint64_t total_slots;   // n_reads * W
+    uint64_t w_magic64;     // floor(2^64 / W) + 1 (W >= 2), 0 = divide
     uint32_t L32;           // L mod 2^32 (only differences inside a tile are formed)
-    uint32_t rpr;           // work items (runs of kRun windows) per read = ceil(W / kRun)
-    uint32_t rpr_magic;     // floor(2^32 / rpr) + 1, used when 1 < rpr < kItemsPerCta
+    uint32_t W32;           // min(W, 2^32 - 1)
+    uint32_t w_magic;       // floor(2^32 / W) + 1, used when 1 < W < slots per CTA + W
+    uint32_t items_per_cta; // work items per CTA (host-chosen so the staged stretch fits shared memory)
     WinConst wc;
     OutPtrs out;
     EncDesc enc;
@@ -171,15 +172,20 @@ struct Acc {
     uint32_t valid = 0;
 };
 
-// The kRun windows of one item whose slots are consecutive (fixed-length reads):
-// compute, then store with full-sector vector stores when aligned.
-// CHECK: some base of the span is invalid -> per-window validity + sentinel.
-template <bool CHECK, bool DIGEST, bool FWRC, int MODE, bool KHI>
-__device__ __forceinline__ void emit_run(const Span& s, const WinConst& wc, const OutPtrs& o, uint64_t slot0,
-                                         uint32_t nwin, Acc& acc) {
+// The kRun windows of one work item = kRun consecutive, 64-byte-aligned output slots.
+// TWO: the item straddles a read boundary: windows j < n_first come from span A (the tail of
+//      one read), the rest from span B (the head of the next; B is loaded n_first bases early so
+//      the same index j addresses it).
+// CHECK: some base of a span is invalid -> per-window validity + sentinel.
+// nwin: slots of this item that exist (kRun except at the very end of the batch).
+template <bool TWO, bool CHECK, bool DIGEST, bool FWRC, int MODE, bool KHI>
+__device__ __forceinline__ void emit_run(const Span& A, const Span& B, uint32_t n_first, const WinConst& wc,
+                                         const OutPtrs& o, uint64_t slot0, uint32_t nwin, Acc& acc) {
     uint64_t oc[kRun], oh[kRun], ofw[FWRC ? kRun : 1], orc[FWRC ? kRun : 1];
 #pragma unroll
     for (int j = 0; j < kRun; ++j) {
+        Span s = A;
+        if (TWO && (uint32_t)j >= n_first) s = B;
         Window w = make_window<KHI>(s, j, wc);
         bool ok = true;
         if (CHECK) ok = (((uint32_t)(s.inv >> j)) & wc.kmask) == 0u;
@@ -195,7 +201,7 @@ __device__ __forceinline__ void emit_run(const Span& s, const WinConst& wc, cons
         }
     }
     if (MODE != 0) return;
-    if (nwin == kRun && o.vec_ok && (slot0 & 3ull) == 0ull) {
+    if (nwin == kRun && o.vec_ok) {
         if (o.canon) {
             st_stream_v4u64(o.canon + slot0, oc[0], oc[1], oc[2], oc[3]);
             st_stream_v4u64(o.canon + slot0 + 4, oc[4], oc[5], oc[6], oc[7]);
@@ -229,6 +235,26 @@ __device__ __forceinline__ void emit_run(const Span& s, const WinConst& wc, cons
     }
 }
 
+// One window on its own (reads with fewer than kRun windows: an item then spans several reads).
+template <bool VALIDATE, bool DIGEST, bool FWRC, int MODE, bool KHI>
+__device__ __forceinline__ void emit_single(const uint2* tile, uint32_t rel, const WinConst& wc, const OutPtrs& o,
+                                            uint64_t slot, Acc& acc) {
+    const Span s = load_span<VALIDATE>(tile, rel, wc);
+    const Window w = make_window<KHI>(s, 0, wc);
+    const bool ok = !VALIDATE || (((uint32_t)s.inv) & wc.kmask) == 0u;
+    if (DIGEST && ok) { acc.canon += w.canon; acc.hash += w.hash; acc.valid += 1; }
+    if (MODE == 1) {
+        if (ok) atomicAdd(o.hist + (w.hash >> o.hist_shift), 1ull);
+        return;
+    }
+    if (o.canon) st_stream_u64(o.canon + slot, ok ? w.canon : ~0ull);
+    if (o.hash) st_stream_u64(o.hash + slot, ok ? w.hash : ~0ull);
+    if (FWRC) {
+        if (o.fw) st_stream_u64(o.fw + slot, ok ? w.fw : ~0ull);
+        if (o.rc) st_stream_u64(o.rc + slot, ok ? w.rc : ~0ull);
+    }
+}
+
 template <bool DIGEST>
 __device__ __forceinline__ void reduce_digest(unsigned long long (&red)[3][kExtractThreads / 32],
                                               unsigned long long* digest, const Acc& acc) {
@@ -246,52 +272,74 @@ __device__ __forceinline__ void reduce_digest(unsigned long long (&red)[3][kExtr
 
 // ---------------------------------------------------------------------------
 // fixed-length reads.  MODE: 0 = materialise, 1 = fused histogram
+//
+// Work is cut in OUTPUT-slot space: item i = slots [8i, 8i+8), so every item's
+// stores are 64-byte aligned whatever W = L-K+1 is.  Slot s belongs to read
+// s / W at position s % W.  An item lies inside one read (fast path), or
+// straddles one read boundary (two spans), or -- only when W < 8 -- several.
 // ---------------------------------------------------------------------------
+// u / W for a small u (u < W + slots per CTA): 0/1 when W is large, else multiply-high
+__device__ __forceinline__ uint32_t div_w(uint32_t u, const ExtractParams& p, uint32_t slots_per_cta) {
+    if (p.W32 >= slots_per_cta) return (u >= p.W32) ? 1u : 0u;  // u < W + slots_per_cta <= 2W
+    if (p.W32 == 1) return u;
+    return __umulhi(u, p.w_magic);
+}
+
 template <bool VALIDATE, bool DIGEST, bool FWRC, int MODE, bool KHI>
 __global__ void __launch_bounds__(kExtractThreads) extract_fixed_kernel(const ExtractParams p) {
     extern __shared__ uint2 tile[];
     __shared__ unsigned long long red[3][kExtractThreads / 32];
 
-    const uint64_t item0 = (uint64_t)blockIdx.x * kItemsPerCta;
-    const uint32_t n_items = (uint32_t)min((uint64_t)kItemsPerCta, p.total_items - item0);
+    const uint32_t slots_per_cta = p.items_per_cta * kRun;
+    const uint64_t slot_base = (uint64_t)blockIdx.x * slots_per_cta;
+    const uint32_t n_slots = (uint32_t)min((uint64_t)slots_per_cta, p.total_slots - slot_base);
     uint64_t r_first;
-    if (p.rpr == 1) r_first = item0;
-    else if (p.rpr_magic64) r_first = div_magic64(item0, p.rpr_magic64);
-    else r_first = item0 / p.rpr;
-    const uint32_t run_first = (uint32_t)(item0 - r_first * p.rpr);
+    if (p.W == 1) r_first = slot_base;
+    else if (p.w_magic64) r_first = div_magic64(slot_base, p.w_magic64);
+    else r_first = slot_base / p.W;
+    const uint32_t p_first = (uint32_t)(slot_base - r_first * p.W);  // position of the CTA's first window in its read
 
-    // ---- phase 1: pack the stretch [g_start, g_end) of the flat stream
-    const uint64_t g_start = r_first * p.L + (uint64_t)run_first * kRun;
-    const uint32_t gi_last = run_first + n_items - 1;  // last item, counted from run 0 of read r_first
-    uint32_t q_last;
-    if (p.rpr >= (uint32_t)kItemsPerCta) q_last = (gi_last >= p.rpr) ? 1u : 0u;
-    else if (p.rpr == 1) q_last = gi_last;
-    else q_last = __umulhi(gi_last, p.rpr_magic);
-    // span in bases up to the end of the last item's last window (mod 2^32 exact: the span is small)
-    const uint32_t span = q_last * p.L32 + (gi_last - q_last * p.rpr) * kRun - run_first * kRun + kRun + p.wc.K - 1;
+    // ---- phase 1: pack the stretch of the flat stream that holds the CTA's windows
+    const uint64_t g_start = r_first * p.L + p_first;
+    const uint32_t u_last = p_first + n_slots - 1;
+    const uint32_t q_last = div_w(u_last, p, slots_per_cta);
+    // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
+    const uint32_t span = q_last * p.L32 + (u_last - q_last * p.W32) - p_first + p.wc.K;
     const uint8_t* first = p.bases + g_start;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = ((span + mis + 15) >> 4) + 3;  // +3: items read 4 entries
+    const uint32_t n_entries = ((span + mis + 15) >> 4) + 3;  // +3: a span reads 4 entries
     stage_tile<VALIDATE>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
     __syncthreads();
 
-    // ---- phase 2: one item = kRun windows of one read
+    // ---- phase 2
     Acc acc;
+    const uint32_t n_items = (n_slots + kRun - 1) / kRun;
     for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
-        const uint32_t gi = run_first + li;
-        uint32_t q;  // reads crossed since r_first
-        if (p.rpr >= (uint32_t)kItemsPerCta) q = (gi >= p.rpr) ? 1u : 0u;
-        else if (p.rpr == 1) q = gi;
-        else q = __umulhi(gi, p.rpr_magic);
-        const uint32_t run = gi - q * p.rpr;
-        const uint32_t p0 = run * kRun;
-        const uint64_t slot0 = (r_first + q) * p.W + p0;
-        const uint32_t nwin = (uint32_t)min((uint64_t)kRun, p.W - p0);
-        // position of the item's first base relative to tile entry 0 (mod 2^32 exact)
-        const uint32_t rel = q * p.L32 + p0 - run_first * kRun + mis;
-        const Span s = load_span<VALIDATE>(tile, rel, p.wc);
-        if (VALIDATE && s.inv != 0ull) emit_run<true, DIGEST, FWRC, MODE, KHI>(s, p.wc, p.out, slot0, nwin, acc);
-        else emit_run<false, DIGEST, FWRC, MODE, KHI>(s, p.wc, p.out, slot0, nwin, acc);
+        const uint32_t u = p_first + li * kRun;            // first slot, counted from window 0 of read r_first
+        const uint32_t q = div_w(u, p, slots_per_cta);      // reads crossed since r_first
+        const uint32_t pos = u - q * p.W32;                  // window position inside its read
+        const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
+        const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+        const uint32_t rel = q * p.L32 + pos - p_first + mis;  // first base, relative to tile entry 0
+        const uint32_t left = p.W32 - pos;                    // windows left in this read (>= 1)
+        if (left >= (uint32_t)kRun || left >= nwin) {
+            const Span s = load_span<VALIDATE>(tile, rel, p.wc);
+            if (VALIDATE && s.inv != 0ull) emit_run<false, true, DIGEST, FWRC, MODE, KHI>(s, s, kRun, p.wc, p.out, slot0, nwin, acc);
+            else emit_run<false, false, DIGEST, FWRC, MODE, KHI>(s, s, kRun, p.wc, p.out, slot0, nwin, acc);
+        } else if (p.W32 >= (uint32_t)kRun) {
+            // straddles exactly one boundary: windows j >= left start read q+1 at position j - left
+            const Span a = load_span<VALIDATE>(tile, rel, p.wc);
+            const Span b = load_span<VALIDATE>(tile, (q + 1) * p.L32 - p_first + mis - left, p.wc);
+            if (VALIDATE && (a.inv | b.inv) != 0ull) emit_run<true, true, DIGEST, FWRC, MODE, KHI>(a, b, left, p.wc, p.out, slot0, nwin, acc);
+            else emit_run<true, false, DIGEST, FWRC, MODE, KHI>(a, b, left, p.wc, p.out, slot0, nwin, acc);
+        } else {
+            // reads with fewer than kRun windows: window by window
+            for (uint32_t j = 0; j < nwin; ++j) {
+                const uint32_t uj = u + j, qj = div_w(uj, p, slots_per_cta);
+                emit_single<VALIDATE, DIGEST, FWRC, MODE, KHI>(tile, qj * p.L32 + (uj - qj * p.W32) - p_first + mis, p.wc, p.out,
+                                                               slot0 + j, acc);
+            }
+        }
     }
     reduce_digest<DIGEST>(red, p.out.digest, acc);
 }

@@ -530,14 +530,14 @@ static cudaError_t launch_csr(bool validate, bool digest, bool fwrc, bool khi, u
     });
 }
 
-struct FixedGeom {
+struct RunGeom {  // run-per-read geometry (wide kernels)
     uint64_t W, total_items, rpr_magic64;
     uint32_t rpr, rpr_magic;
     unsigned grid;
     size_t smem;
 };
 
-static bool fixed_geom(uint64_t n_reads, uint64_t L, uint32_t k, int span_words, FixedGeom* g) {
+static bool run_geom(uint64_t n_reads, uint64_t L, uint32_t k, int span_words, RunGeom* g) {
     g->W = L - k + 1;
     const uint64_t rpr64 = (g->W + kRun - 1) / kRun;
     if (rpr64 > 0xFFFFFFFFull) return false;
@@ -555,6 +555,41 @@ static bool fixed_geom(uint64_t n_reads, uint64_t L, uint32_t k, int span_words,
     const uint64_t crossings = kItemsPerCta / g->rpr + 2;
     const uint64_t span = (uint64_t)kItemsPerCta * kRun + crossings * (k + 7) + k + 32;
     g->smem = (size_t)((span + 15) / 16 + span_words + 2) * sizeof(uint2);
+    return true;
+}
+
+// slot-space geometry of extract_fixed_kernel
+struct SlotGeom {
+    uint64_t W, total_slots, w_magic64;
+    uint32_t W32, w_magic, items_per_cta;
+    unsigned grid;
+    size_t smem;
+};
+
+static bool slot_geom(uint64_t n_reads, uint64_t L, uint32_t k, SlotGeom* g) {
+    g->W = L - k + 1;
+    if (g->W > 0xFFFF0000ull) return false;  // one read of > 4.29 Gbases: split it (window positions are 32-bit inside a CTA)
+    g->W32 = (uint32_t)g->W;
+    g->total_slots = n_reads * g->W;
+    g->w_magic = g->W32 > 1 ? (uint32_t)((1ull << 32) / g->W32 + 1) : 0;
+    // slot / W by multiplication is exact while slot * W < 2^64; otherwise the kernel divides
+    const bool magic_ok = g->W > 1 && (double)g->total_slots * (double)g->W < 9.0e18;
+    g->w_magic64 = magic_ok ? (~0ull / g->W + 1) : 0;
+    // items per CTA: as many as keep the staged stretch of reads under ~44 KiB of shared memory
+    uint32_t ipc = kItemsPerCta;
+    for (;;) {
+        const uint64_t slots = (uint64_t)ipc * kRun;
+        const uint64_t crossings = slots / g->W + 2;
+        const uint64_t span = slots + crossings * (k - 1) + k + 32;
+        g->smem = (size_t)((span + 15) / 16 + 6) * sizeof(uint2);
+        if (g->smem <= 44 * 1024 || ipc <= 64) break;
+        ipc /= 2;
+    }
+    g->items_per_cta = ipc;
+    const uint64_t items = (g->total_slots + kRun - 1) / kRun;
+    const uint64_t ctas = (items + ipc - 1) / ipc;
+    if (ctas > 0x7FFFFFFFull) return false;
+    g->grid = (unsigned)ctas;
     return true;
 }
 
@@ -586,11 +621,11 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, const uint64_t*
     out.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
     if (!d_offsets) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
-        FixedGeom g;
-        if (!fixed_geom(n_reads, fixed_len, k, 4, &g)) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+        SlotGeom g;
+        if (!slot_geom(n_reads, fixed_len, k, &g)) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
         ExtractParams p{};
-        p.bases = d_bases; p.n_bytes = n_bytes; p.L = fixed_len; p.L32 = (uint32_t)fixed_len; p.W = g.W;
-        p.rpr = g.rpr; p.rpr_magic = g.rpr_magic; p.rpr_magic64 = g.rpr_magic64; p.total_items = g.total_items;
+        p.bases = d_bases; p.n_bytes = n_bytes; p.L = fixed_len; p.L32 = (uint32_t)fixed_len; p.W = g.W; p.W32 = g.W32;
+        p.total_slots = g.total_slots; p.w_magic64 = g.w_magic64; p.w_magic = g.w_magic; p.items_per_cta = g.items_per_cta;
         p.wc = make_winconst(k, enc); p.out = out; p.enc = enc;
         cudaError_t e = hist ? launch_fixed<1>(validate, want_digest, false, khi, g.grid, g.smem, st, p)
                              : launch_fixed<0>(validate, want_digest, fwrc, khi, g.grid, g.smem, st, p);
@@ -692,8 +727,8 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         size_t smem;
         const bool fixed = ctx->d_offsets == nullptr;
         if (fixed) {
-            FixedGeom g;
-            if (!fixed_geom(ctx->n_reads, ctx->fixed_len, k, kWideA + 1, &g))
+            RunGeom g;
+            if (!run_geom(ctx->n_reads, ctx->fixed_len, k, kWideA + 1, &g))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
             p.L = ctx->fixed_len; p.L32 = (uint32_t)ctx->fixed_len; p.W = g.W; p.rpr = g.rpr; p.rpr_magic = g.rpr_magic;
             p.total_items = g.total_items;
