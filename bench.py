@@ -290,9 +290,9 @@ def main():
     # ---- optional final reduction across ranks (checksum / count), NCCL, outside the timed region
     global_digest = list(digest)
     if world > 1:
-        t = torch.tensor([d_ % 2**63 for d_ in digest], dtype=torch.int64, device="cuda")  # counts fit; sums mod 2^63
-        dist.all_reduce(t)
-        global_digest = [int(x) for x in t.tolist()]
+        from kmers_b200.dist import allreduce_histogram
+        _, gd = allreduce_histogram(torch.zeros(1, dtype=torch.int64, device="cuda"), digest)  # wrapping u64 sums over ranks
+        global_digest = list(gd)
 
     cpu = None
     if rank == 0 and not args.no_cpu:

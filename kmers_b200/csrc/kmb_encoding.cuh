@@ -183,25 +183,61 @@ __global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, u
 __device__ __forceinline__ uint64_t rc_word(uint64_t w, uint32_t k) { return pair_reverse64(~w) >> (2 * (32 - k)); }
 
 template <int OP>
-__global__ void __launch_bounds__(256) word_op_kernel(const uint64_t* in, const uint64_t* other, uint64_t* out,
-                                                      uint8_t* out8, uint64_t n, uint32_t k, uint64_t mask) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t w = in[i];
+__device__ __forceinline__ void word_op_one(uint64_t w, uint64_t o, uint32_t k, uint64_t mask, uint64_t& r64, uint8_t& r8) {
+    r64 = 0; r8 = 0;
     if (OP == 0) {
-        out[i] = rc_word(w, k);
+        r64 = rc_word(w, k);
     } else if (OP == 1) {
         const uint64_t rc = rc_word(w, k);
         const bool is_canon = w <= rc;  // kmer.rs:57  *self <= rc
-        if (out) out[i] = is_canon ? w : rc;
-        if (out8) out8[i] = is_canon ? 1 : 0;
+        r64 = is_canon ? w : rc;
+        r8 = is_canon ? 1 : 0;
     } else if (OP == 2) {
-        out[i] = pair_reverse64(w) >> (2 * (32 - k));
+        r64 = pair_reverse64(w) >> (2 * (32 - k));
     } else {
         const uint64_t fw = w & mask;  // Kmer::from_u64 masks (kmer.rs:45-48), intended mask at k == 32
         const uint64_t rc = rc_word(fw, k);
-        const uint64_t o = other[i];
-        out8[i] = (fw == o) ? 1 : ((rc == o) ? 2 : 0);
+        r8 = (fw == o) ? 1 : ((rc == o) ? 2 : 0);
+    }
+}
+
+// One thread = 4 consecutive words: 32-byte loads and stores when the arrays are 32-byte aligned.
+template <int OP>
+__global__ void __launch_bounds__(256) word_op_kernel(const uint64_t* in, const uint64_t* other, uint64_t* out,
+                                                      uint8_t* out8, uint64_t n, uint32_t k, uint64_t mask, uint32_t vec_ok) {
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    uint64_t w[4], o[4] = {0, 0, 0, 0}, r64[4];
+    uint8_t r8[4];
+    const bool full = vec_ok && i0 + 4 <= n;
+    if (full) {
+        const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(in + i0);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        if (OP == 3) {
+            const ulonglong4 u = *reinterpret_cast<const ulonglong4*>(other + i0);
+            o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            w[t] = (i0 + t < n) ? in[i0 + t] : 0;
+            if (OP == 3) o[t] = (i0 + t < n) ? other[i0 + t] : 0;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) word_op_one<OP>(w[t], o[t], k, mask, r64[t], r8[t]);
+    if (full) {
+        if (OP != 3 && out) st_stream_v4u64(out + i0, r64[0], r64[1], r64[2], r64[3]);
+        if ((OP == 1 || OP == 3) && out8)
+            *reinterpret_cast<uint32_t*>(out8 + i0) = (uint32_t)r8[0] | ((uint32_t)r8[1] << 8) | ((uint32_t)r8[2] << 16) | ((uint32_t)r8[3] << 24);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (i0 + t < n) {
+                if (OP != 3 && out) out[i0 + t] = r64[t];
+                if ((OP == 1 || OP == 3) && out8) out8[i0 + t] = r8[t];
+            }
+        }
     }
 }
 

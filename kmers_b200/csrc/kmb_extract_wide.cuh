@@ -9,130 +9,204 @@
 // 2K-bit integers, hash = 2K-bit pair reversal -- the natural extension of
 // naive_impl/canonical_kmer.rs:113-119 and naive_impl/hash.rs:60-71.
 //
-// Same tiling as kmb_extract.cuh, with a 5-word (80-base) span per item.
+// Same structure as kmb_extract.cuh: slot-space work items (8 slots = 128 B of
+// each output array per thread, 32-byte stores), a span of NW32+1 packed words
+// per item, one multiword compare per window, hash by XOR fold.
+// NW32 = live 32-bit words of a k-mer = ceil(2K / 32) in {2, 3, 4} (K <= 32 uses 2).
 #pragma once
 #include "kmb_extract.cuh"
 
 namespace kmb {
 
-constexpr int kWideA = 5;  // 32-bit words of forward span: kRun + 64 - 1 = 71 bases <= 80
+struct WideConst {
+    uint32_t K;
+    uint32_t shiftD;     // 2 * (16 * (NW32 + 1) - (kRun + K - 1))
+    uint32_t mask_a;     // mask of word NW32 - 2
+    uint32_t mask_b;     // mask of word NW32 - 1 (the top live word)
+    uint32_t cmask;      // complement constant replicated over 16 fields
+    uint32_t cm_a, cm_b; // cmask & mask_a / mask_b
+    uint64_t kmask;      // low K bits (window validity)
+};
+
+struct WideOut {
+    uint64_t* canon;  // 2 words per slot
+    uint64_t* hash;   // 2 words per slot
+    unsigned long long* digest;
+    uint32_t vec_ok;
+};
 
 struct WideParams {
-    // geometry (fixed-length batches use the first block, CSR the second)
     const uint8_t* bases;
     uint64_t n_bytes;
-    uint64_t L, W;
-    uint32_t L32, rpr, rpr_magic;
-    uint64_t total_items;
+    // fixed-length geometry (slot space, as ExtractParams)
+    uint64_t L, W, total_slots, w_magic64;
+    uint32_t L32, W32, w_magic, items_per_cta;
+    // CSR geometry
     const uint64_t* offsets;
     const uint64_t* win_offsets;
     uint64_t n_reads;
-    uint32_t K;
-    uint32_t shiftD;     // 2 * (80 - (kRun + K - 1))
-    uint32_t mask[4];    // low 2K bits over four 32-bit words
-    uint64_t* canon;     // 2 words per slot
-    uint64_t* hash;      // 2 words per slot
-    unsigned long long* digest;
+    WideConst wc;
+    WideOut out;
     EncDesc enc;
 };
 
-template <int WS>
-__device__ __forceinline__ void shr_words(uint32_t (&d)[kWideA + 1], const uint32_t (&c)[kWideA], uint32_t s) {
+template <int NW32>
+struct WideSpan {
+    uint32_t a[NW32 + 1];  // forward span, 16 * (NW32 + 1) bases
+    uint32_t d[NW32 + 1];  // reverse complement of its first kRun + K - 1 bases, at bit 0
+    uint64_t inv_lo;       // invalid-base bits 0..63 of the span
+    uint32_t inv_hi;       // bits 64..95
+};
+
+template <int NA, int WS>
+__device__ __forceinline__ void shr_words(uint32_t (&d)[NA], const uint32_t (&c)[NA], uint32_t s) {
 #pragma unroll
-    for (int i = 0; i < kWideA + 1; ++i) {
-        const uint32_t lo = (i + WS) < kWideA ? c[i + WS] : 0u;
-        const uint32_t hi = (i + WS + 1) < kWideA ? c[i + WS + 1] : 0u;
+    for (int i = 0; i < NA; ++i) {
+        const uint32_t lo = (i + WS) < NA ? c[i + WS] : 0u;
+        const uint32_t hi = (i + WS + 1) < NA ? c[i + WS + 1] : 0u;
         d[i] = __funnelshift_r(lo, hi, s);
     }
 }
 
-struct WideSpan {
-    uint32_t a[kWideA + 1];  // forward span (a[kWideA] = 0 pad)
-    uint32_t d[kWideA + 1];  // reverse complement of the first kRun+K-1 bases, at bit 0
-    uint64_t inv_lo, inv_hi; // invalid-base bits of the span
-};
-
-template <bool VALIDATE>
-__device__ __forceinline__ void load_wide_span(const uint2* tile, uint32_t rel, uint32_t cmask, uint32_t shiftD,
-                                               WideSpan& s) {
+template <int NW32, bool VALIDATE>
+__device__ __forceinline__ WideSpan<NW32> load_wide_span(const uint2* tile, uint32_t rel, const WideConst& wc) {
+    constexpr int NA = NW32 + 1;
     const uint32_t e = rel >> 4, o2 = (rel & 15u) * 2;
-    uint2 t[kWideA + 1];
+    uint2 t[NA + 1];
 #pragma unroll
-    for (int i = 0; i < kWideA + 1; ++i) t[i] = tile[e + i];
+    for (int i = 0; i < NA + 1; ++i) t[i] = tile[e + i];
+    WideSpan<NW32> s;
 #pragma unroll
-    for (int i = 0; i < kWideA; ++i) s.a[i] = __funnelshift_r(t[i].x, t[i + 1].x, o2);
-    s.a[kWideA] = 0;
-    uint32_t c[kWideA];
+    for (int i = 0; i < NA; ++i) s.a[i] = __funnelshift_r(t[i].x, t[i + 1].x, o2);
+    uint32_t c[NA];
 #pragma unroll
-    for (int i = 0; i < kWideA; ++i) c[i] = pair_reverse32(s.a[kWideA - 1 - i] ^ cmask);
-    const uint32_t sh = shiftD & 31u;
-    switch (shiftD >> 5) {
-        case 0: shr_words<0>(s.d, c, sh); break;
-        case 1: shr_words<1>(s.d, c, sh); break;
-        case 2: shr_words<2>(s.d, c, sh); break;
-        case 3: shr_words<3>(s.d, c, sh); break;
-        default: shr_words<4>(s.d, c, sh); break;
+    for (int i = 0; i < NA; ++i) c[i] = pair_reverse32(s.a[NA - 1 - i] ^ wc.cmask);
+    const uint32_t sh = wc.shiftD & 31u;
+    switch (wc.shiftD >> 5) {  // kernel-uniform
+        case 0: shr_words<NA, 0>(s.d, c, sh); break;
+        case 1: shr_words<NA, 1>(s.d, c, sh); break;
+        default: shr_words<NA, 2>(s.d, c, sh); break;
     }
     s.inv_lo = 0; s.inv_hi = 0;
     if (VALIDATE) {
-        const uint64_t mlo = (uint64_t)t[0].y | ((uint64_t)t[1].y << 16) | ((uint64_t)t[2].y << 32) | ((uint64_t)t[3].y << 48);
-        const uint64_t mhi = (uint64_t)t[4].y | ((uint64_t)t[5].y << 16);
-        const uint32_t o = o2 >> 1;
-        s.inv_lo = o ? ((mlo >> o) | (mhi << (64 - o))) : mlo;
-        s.inv_hi = mhi >> o;
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < NA + 1; ++i) any |= t[i].y;
+        if (any != 0u) {
+            // 16 * (NA + 1) <= 96 mask bits, shifted down by the item's offset inside entry e
+            const uint64_t m0 = (uint64_t)t[0].y | ((uint64_t)t[1].y << 16) | ((uint64_t)t[2].y << 32) | ((uint64_t)t[3].y << 48);
+            uint64_t m1 = 0;
+            if constexpr (NA + 1 > 4) m1 |= (uint64_t)t[4].y;
+            if constexpr (NA + 1 > 5) m1 |= (uint64_t)t[5].y << 16;
+            const uint32_t o = o2 >> 1;
+            s.inv_lo = o ? ((m0 >> o) | (m1 << (64 - o))) : m0;
+            s.inv_hi = (uint32_t)(m1 >> o);
+        }
     }
+    return s;
 }
 
 struct WideWindow {
-    uint64_t canon[2], hash[2];
-    bool ok;
+    uint64_t c0, c1, h0, h1;
 };
 
-template <bool VALIDATE>
-__device__ __forceinline__ WideWindow wide_window(const WideSpan& s, int j, const WideParams& p) {
-    uint32_t f[4], r[4];
+template <int NW32>
+__device__ __forceinline__ WideWindow wide_window(const WideSpan<NW32>& s, int j, const WideConst& wc) {
+    uint32_t f[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[i] = __funnelshift_r(s.a[i], s.a[i + 1], 2 * j) & p.mask[i];
-        r[i] = __funnelshift_r(s.d[i], s.d[i + 1], 2 * (kRun - 1 - j)) & p.mask[i];
+    for (int i = 0; i < NW32; ++i) {
+        f[i] = __funnelshift_r(s.a[i], s.a[i + 1], 2 * j);
+        r[i] = __funnelshift_r(s.d[i], s.d[i + 1], 2 * (kRun - 1 - j));
     }
-    const uint64_t f0 = mk64(f[0], f[1]), f1 = mk64(f[2], f[3]);
-    const uint64_t r0 = mk64(r[0], r[1]), r1 = mk64(r[2], r[3]);
-    const bool fw_less = (f1 < r1) || (f1 == r1 && f0 < r0);
-    const uint64_t cm = mk64(p.enc.cmask, p.enc.cmask);
+    f[NW32 - 2] &= wc.mask_a; r[NW32 - 2] &= wc.mask_a;
+    f[NW32 - 1] &= wc.mask_b; r[NW32 - 1] &= wc.mask_b;
+    // unsigned compare of the 2K-bit integers, top word first
+    bool fw_less = f[NW32 - 1] < r[NW32 - 1];
+    bool eq = f[NW32 - 1] == r[NW32 - 1];
+#pragma unroll
+    for (int i = NW32 - 2; i >= 0; --i) {
+        fw_less = fw_less || (eq && f[i] < r[i]);
+        eq = eq && f[i] == r[i];
+    }
+    uint32_t c[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < NW32; ++i) {
+        c[i] = fw_less ? f[i] : r[i];
+        const uint32_t cm = (i == NW32 - 1) ? wc.cm_b : ((i == NW32 - 2) ? wc.cm_a : wc.cmask);
+        h[i] = (f[i] ^ r[i] ^ cm) ^ c[i];  // other strand ^ complement constant = pair reversal of the canonical strand
+    }
     WideWindow w;
-    w.canon[0] = fw_less ? f0 : r0;
-    w.canon[1] = fw_less ? f1 : r1;
-    // pair reversal of the canonical strand == complement-constant XOR of the other strand
-    w.hash[0] = ((fw_less ? r0 : f0) ^ cm) & mk64(p.mask[0], p.mask[1]);
-    w.hash[1] = ((fw_less ? r1 : f1) ^ cm) & mk64(p.mask[2], p.mask[3]);
-    w.ok = true;
-    if (VALIDATE) {
-        const uint64_t x = j ? ((s.inv_lo >> j) | (s.inv_hi << (64 - j))) : s.inv_lo;
-        const uint64_t km = p.K >= 64 ? ~0ull : ((1ull << p.K) - 1ull);
-        w.ok = (x & km) == 0ull;
-    }
+    w.c0 = mk64(c[0], c[1]); w.c1 = mk64(c[2], c[3]);
+    w.h0 = mk64(h[0], h[1]); w.h1 = mk64(h[2], h[3]);
     return w;
 }
 
-__device__ __forceinline__ void wide_store(uint64_t* base, uint64_t slot, const uint64_t (&v)[2]) {
-    st_stream_v2u64(base + 2 * slot, v[0], v[1]);
+template <int NW32>
+__device__ __forceinline__ bool wide_ok(const WideSpan<NW32>& s, int j, const WideConst& wc) {
+    const uint64_t x = j ? ((s.inv_lo >> j) | ((uint64_t)s.inv_hi << (64 - j))) : s.inv_lo;
+    return (x & wc.kmask) == 0ull;
 }
 
-template <bool VALIDATE, bool DIGEST>
-__device__ __forceinline__ void wide_emit(const WideParams& p, const WideWindow& w, uint64_t slot, uint64_t& acc_c,
-                                          uint64_t& acc_h, uint32_t& acc_v) {
-    if (DIGEST && w.ok) { acc_c += w.canon[0] + w.canon[1]; acc_h += w.hash[0] + w.hash[1]; acc_v += 1; }
-    const uint64_t ones[2] = {~0ull, ~0ull};
-    if (p.canon) wide_store(p.canon, slot, w.ok ? w.canon : ones);
-    if (p.hash) wide_store(p.hash, slot, w.ok ? w.hash : ones);
+struct WideAcc {
+    uint64_t canon = 0, hash = 0;
+    uint32_t valid = 0;
+};
+
+// kRun consecutive slots (128-byte aligned per array).  TWO / CHECK as in emit_run.
+template <int NW32, bool TWO, bool CHECK, bool DIGEST>
+__device__ __forceinline__ void emit_wide_run(const WideSpan<NW32>& A, const WideSpan<NW32>& B, uint32_t n_first,
+                                              const WideConst& wc, const WideOut& o, uint64_t slot0, uint32_t nwin,
+                                              WideAcc& acc) {
+#pragma unroll
+    for (int j2 = 0; j2 < kRun; j2 += 2) {  // two windows = one 32-byte store per array
+        WideWindow w[2];
+        bool ok[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int j = j2 + t;
+            WideSpan<NW32> s = A;
+            if (TWO && (uint32_t)j >= n_first) s = B;
+            w[t] = wide_window<NW32>(s, j, wc);
+            ok[t] = true;
+            if (CHECK) ok[t] = wide_ok<NW32>(s, j, wc);
+            if (DIGEST && ok[t] && (uint32_t)j < nwin) {
+                acc.canon += w[t].c0 + w[t].c1; acc.hash += w[t].h0 + w[t].h1; acc.valid += 1;
+            }
+            if (CHECK && !ok[t]) { w[t].c0 = w[t].c1 = w[t].h0 = w[t].h1 = ~0ull; }
+        }
+        const uint64_t slot = slot0 + j2;
+        if ((uint32_t)j2 + 1 < nwin && o.vec_ok) {
+            if (o.canon) st_stream_v4u64(o.canon + 2 * slot, w[0].c0, w[0].c1, w[1].c0, w[1].c1);
+            if (o.hash) st_stream_v4u64(o.hash + 2 * slot, w[0].h0, w[0].h1, w[1].h0, w[1].h1);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if ((uint32_t)(j2 + t) < nwin) {
+                    if (o.canon) st_stream_v2u64(o.canon + 2 * (slot + t), w[t].c0, w[t].c1);
+                    if (o.hash) st_stream_v2u64(o.hash + 2 * (slot + t), w[t].h0, w[t].h1);
+                }
+            }
+        }
+    }
+}
+
+template <int NW32, bool VALIDATE, bool DIGEST>
+__device__ __forceinline__ void emit_wide_single(const uint2* tile, uint32_t rel, const WideConst& wc, const WideOut& o,
+                                                 uint64_t slot, WideAcc& acc) {
+    const WideSpan<NW32> s = load_wide_span<NW32, VALIDATE>(tile, rel, wc);
+    WideWindow w = wide_window<NW32>(s, 0, wc);
+    const bool ok = !VALIDATE || wide_ok<NW32>(s, 0, wc);
+    if (DIGEST && ok) { acc.canon += w.c0 + w.c1; acc.hash += w.h0 + w.h1; acc.valid += 1; }
+    if (!ok) { w.c0 = w.c1 = w.h0 = w.h1 = ~0ull; }
+    if (o.canon) st_stream_v2u64(o.canon + 2 * slot, w.c0, w.c1);
+    if (o.hash) st_stream_v2u64(o.hash + 2 * slot, w.h0, w.h1);
 }
 
 template <bool DIGEST>
 __device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][kExtractThreads / 32], unsigned long long* digest,
-                                            uint32_t acc_v, uint64_t acc_c, uint64_t acc_h) {
+                                            const WideAcc& acc) {
     if (!DIGEST) return;
-    uint64_t v = warp_sum64(acc_v), c = warp_sum64(acc_c), h = warp_sum64(acc_h);
+    const uint64_t v = warp_sum64(acc.valid), c = warp_sum64(acc.canon), h = warp_sum64(acc.hash);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { red[0][warp] = v; red[1][warp] = c; red[2][warp] = h; }
     __syncthreads();
@@ -143,62 +217,77 @@ __device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][kExtrac
     }
 }
 
-template <bool VALIDATE, bool DIGEST>
+__device__ __forceinline__ uint32_t wide_div_w(uint32_t u, const WideParams& p, uint32_t slots_per_cta) {
+    if (p.W32 >= slots_per_cta) return (u >= p.W32) ? 1u : 0u;
+    if (p.W32 == 1) return u;
+    return __umulhi(u, p.w_magic);
+}
+
+template <int NW32, bool VALIDATE, bool DIGEST>
 __global__ void __launch_bounds__(kExtractThreads) extract_wide_fixed_kernel(const WideParams p) {
     extern __shared__ uint2 tile[];
     __shared__ unsigned long long red[3][kExtractThreads / 32];
-    const uint64_t item0 = (uint64_t)blockIdx.x * kItemsPerCta;
-    const uint32_t n_items = (uint32_t)min((uint64_t)kItemsPerCta, p.total_items - item0);
-    const uint64_t r_first = item0 / p.rpr;
-    const uint32_t run_first = (uint32_t)(item0 - r_first * p.rpr);
-    const uint64_t g_start = r_first * p.L + (uint64_t)run_first * kRun;
-    const uint64_t last = item0 + n_items - 1;
-    const uint64_t r_last = last / p.rpr;
-    const uint32_t run_last = (uint32_t)(last - r_last * p.rpr);
-    uint64_t g_end = r_last * p.L + (uint64_t)run_last * kRun + kRun + p.K - 1;
-    if (g_end > p.n_bytes) g_end = p.n_bytes;
+    const uint32_t slots_per_cta = p.items_per_cta * kRun;
+    const uint64_t slot_base = (uint64_t)blockIdx.x * slots_per_cta;
+    const uint32_t n_slots = (uint32_t)min((uint64_t)slots_per_cta, p.total_slots - slot_base);
+    uint64_t r_first;
+    if (p.W == 1) r_first = slot_base;
+    else if (p.w_magic64) r_first = div_magic64(slot_base, p.w_magic64);
+    else r_first = slot_base / p.W;
+    const uint32_t p_first = (uint32_t)(slot_base - r_first * p.W);
+    const uint64_t g_start = r_first * p.L + p_first;
+    const uint32_t u_last = p_first + n_slots - 1;
+    const uint32_t q_last = wide_div_w(u_last, p, slots_per_cta);
+    const uint32_t span = q_last * p.L32 + (u_last - q_last * p.W32) - p_first + p.wc.K;
     const uint8_t* first = p.bases + g_start;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = (uint32_t)((g_end - g_start + mis + 15) >> 4) + kWideA;
+    const uint32_t n_entries = ((span + mis + 15) >> 4) + NW32 + 1;  // a span reads NW32 + 2 entries
     stage_tile<VALIDATE>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
     __syncthreads();
 
-    uint64_t acc_c = 0, acc_h = 0;
-    uint32_t acc_v = 0;
+    WideAcc acc;
+    const uint32_t n_items = (n_slots + kRun - 1) / kRun;
     for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
-        const uint32_t gi = run_first + li;
-        uint32_t q;
-        if (p.rpr >= (uint32_t)kItemsPerCta) q = (gi >= p.rpr) ? 1u : 0u;
-        else if (p.rpr == 1) q = gi;
-        else q = __umulhi(gi, p.rpr_magic);
-        const uint32_t run = gi - q * p.rpr;
-        const uint32_t p0 = run * kRun;
-        const uint64_t slot0 = (r_first + q) * p.W + p0;
-        const uint32_t nwin = (uint32_t)min((uint64_t)kRun, p.W - p0);
-        WideSpan s;
-        load_wide_span<VALIDATE>(tile, q * p.L32 + p0 - run_first * kRun + mis, p.enc.cmask, p.shiftD, s);
-#pragma unroll
-        for (int j = 0; j < kRun; ++j) {
-            if ((uint32_t)j < nwin) {
-                WideWindow w = wide_window<VALIDATE>(s, j, p);
-                wide_emit<VALIDATE, DIGEST>(p, w, slot0 + j, acc_c, acc_h, acc_v);
+        const uint32_t u = p_first + li * kRun;
+        const uint32_t q = wide_div_w(u, p, slots_per_cta);
+        const uint32_t pos = u - q * p.W32;
+        const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
+        const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+        const uint32_t rel = q * p.L32 + pos - p_first + mis;
+        const uint32_t left = p.W32 - pos;
+        if (left >= (uint32_t)kRun || left >= nwin) {
+            const WideSpan<NW32> s = load_wide_span<NW32, VALIDATE>(tile, rel, p.wc);
+            if (VALIDATE && (s.inv_lo | s.inv_hi) != 0ull) emit_wide_run<NW32, false, true, DIGEST>(s, s, kRun, p.wc, p.out, slot0, nwin, acc);
+            else emit_wide_run<NW32, false, false, DIGEST>(s, s, kRun, p.wc, p.out, slot0, nwin, acc);
+        } else if (p.W32 >= (uint32_t)kRun) {
+            const WideSpan<NW32> a = load_wide_span<NW32, VALIDATE>(tile, rel, p.wc);
+            const WideSpan<NW32> b = load_wide_span<NW32, VALIDATE>(tile, (q + 1) * p.L32 - p_first + mis - left, p.wc);
+            if (VALIDATE && (a.inv_lo | a.inv_hi | b.inv_lo | b.inv_hi) != 0ull)
+                emit_wide_run<NW32, true, true, DIGEST>(a, b, left, p.wc, p.out, slot0, nwin, acc);
+            else emit_wide_run<NW32, true, false, DIGEST>(a, b, left, p.wc, p.out, slot0, nwin, acc);
+        } else {
+            for (uint32_t j = 0; j < nwin; ++j) {
+                const uint32_t uj = u + j, qj = wide_div_w(uj, p, slots_per_cta);
+                emit_wide_single<NW32, VALIDATE, DIGEST>(tile, qj * p.L32 + (uj - qj * p.W32) - p_first + mis, p.wc, p.out,
+                                                         slot0 + j, acc);
             }
         }
     }
-    wide_reduce<DIGEST>(red, p.digest, acc_v, acc_c, acc_h);
+    wide_reduce<DIGEST>(red, p.out.digest, acc);
 }
 
-template <bool VALIDATE, bool DIGEST>
+// ragged batches: fixed stretches of the flat stream, every window checks its own read
+template <int NW32, bool VALIDATE, bool DIGEST>
 __global__ void __launch_bounds__(kExtractThreads) extract_wide_csr_kernel(const WideParams p) {
     extern __shared__ uint2 tile[];
     __shared__ unsigned long long red[3][kExtractThreads / 32];
     __shared__ uint64_t s_rlo, s_rhi;
     const uint64_t g_start = (uint64_t)blockIdx.x * kCsrTileBases;
     const uint64_t g_stop = min(g_start + (uint64_t)kCsrTileBases, p.n_bytes);
-    const uint64_t g_end = min(g_stop + p.K - 1, p.n_bytes);
+    const uint64_t g_end = min(g_stop + p.wc.K - 1, p.n_bytes);
     const uint8_t* first = p.bases + g_start;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = (uint32_t)((g_end - g_start + mis + 15) >> 4) + kWideA;
+    const uint32_t n_entries = (uint32_t)((g_end - g_start + mis + 15) >> 4) + NW32 + 1;
     stage_tile<VALIDATE>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
     if (threadIdx.x == 0) {
         s_rlo = find_read(p.offsets, 0, p.n_reads - 1, g_start);
@@ -206,13 +295,11 @@ __global__ void __launch_bounds__(kExtractThreads) extract_wide_csr_kernel(const
     }
     __syncthreads();
 
-    uint64_t acc_c = 0, acc_h = 0;
-    uint32_t acc_v = 0;
+    WideAcc acc;
     const uint32_t n_items = (uint32_t)((g_stop - g_start + kRun - 1) / kRun);
     for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
         const uint64_t g0 = g_start + (uint64_t)li * kRun;
-        WideSpan s;
-        load_wide_span<VALIDATE>(tile, li * kRun + mis, p.enc.cmask, p.shiftD, s);
+        const WideSpan<NW32> s = load_wide_span<NW32, VALIDATE>(tile, li * kRun + mis, p.wc);
         uint64_t r = find_read(p.offsets, s_rlo, s_rhi, g0);
         uint64_t r_beg = __ldg(p.offsets + r), r_end = __ldg(p.offsets + r + 1);
         uint64_t w_off = __ldg(p.win_offsets + r);
@@ -226,12 +313,17 @@ __global__ void __launch_bounds__(kExtractThreads) extract_wide_csr_kernel(const
                 r_end = __ldg(p.offsets + r + 1);
                 w_off = __ldg(p.win_offsets + r);
             }
-            if (g + p.K > r_end) continue;
-            WideWindow w = wide_window<VALIDATE>(s, j, p);
-            wide_emit<VALIDATE, DIGEST>(p, w, w_off + (g - r_beg), acc_c, acc_h, acc_v);
+            if (g + p.wc.K > r_end) continue;
+            WideWindow w = wide_window<NW32>(s, j, p.wc);
+            const bool ok = !VALIDATE || wide_ok<NW32>(s, j, p.wc);
+            if (DIGEST && ok) { acc.canon += w.c0 + w.c1; acc.hash += w.h0 + w.h1; acc.valid += 1; }
+            if (!ok) { w.c0 = w.c1 = w.h0 = w.h1 = ~0ull; }
+            const uint64_t slot = w_off + (g - r_beg);
+            if (p.out.canon) st_stream_v2u64(p.out.canon + 2 * slot, w.c0, w.c1);
+            if (p.out.hash) st_stream_v2u64(p.out.hash + 2 * slot, w.h0, w.h1);
         }
     }
-    wide_reduce<DIGEST>(red, p.digest, acc_v, acc_c, acc_h);
+    wide_reduce<DIGEST>(red, p.out.digest, acc);
 }
 
 }  // namespace kmb

@@ -530,34 +530,6 @@ static cudaError_t launch_csr(bool validate, bool digest, bool fwrc, bool khi, u
     });
 }
 
-struct RunGeom {  // run-per-read geometry (wide kernels)
-    uint64_t W, total_items, rpr_magic64;
-    uint32_t rpr, rpr_magic;
-    unsigned grid;
-    size_t smem;
-};
-
-static bool run_geom(uint64_t n_reads, uint64_t L, uint32_t k, int span_words, RunGeom* g) {
-    g->W = L - k + 1;
-    const uint64_t rpr64 = (g->W + kRun - 1) / kRun;
-    if (rpr64 > 0xFFFFFFFFull) return false;
-    g->rpr = (uint32_t)rpr64;
-    g->rpr_magic = g->rpr > 1 ? (uint32_t)((1ull << 32) / g->rpr + 1) : 0;
-    g->total_items = n_reads * rpr64;
-    // item / rpr by multiplication is exact while item * rpr < 2^64; otherwise the kernel divides
-    const bool magic_ok = g->rpr > 1 && (double)g->total_items * (double)g->rpr < 9.0e18;
-    g->rpr_magic64 = magic_ok ? (~0ull / g->rpr + 1) : 0;
-    const uint64_t ctas = (g->total_items + kItemsPerCta - 1) / kItemsPerCta;
-    if (ctas > 0x7FFFFFFFull) return false;
-    g->grid = (unsigned)ctas;
-    // bases a CTA can span: kRun per item, plus up to K-1 extra at each read
-    // boundary, plus the last item's K-1 tail and alignment slack.
-    const uint64_t crossings = kItemsPerCta / g->rpr + 2;
-    const uint64_t span = (uint64_t)kItemsPerCta * kRun + crossings * (k + 7) + k + 32;
-    g->smem = (size_t)((span + 15) / 16 + span_words + 2) * sizeof(uint2);
-    return true;
-}
-
 // slot-space geometry of extract_fixed_kernel
 struct SlotGeom {
     uint64_t W, total_slots, w_magic64;
@@ -566,7 +538,7 @@ struct SlotGeom {
     size_t smem;
 };
 
-static bool slot_geom(uint64_t n_reads, uint64_t L, uint32_t k, SlotGeom* g) {
+static bool slot_geom(uint64_t n_reads, uint64_t L, uint32_t k, SlotGeom* g, uint32_t span_entries = 4) {
     g->W = L - k + 1;
     if (g->W > 0xFFFF0000ull) return false;  // one read of > 4.29 Gbases: split it (window positions are 32-bit inside a CTA)
     g->W32 = (uint32_t)g->W;
@@ -581,7 +553,7 @@ static bool slot_geom(uint64_t n_reads, uint64_t L, uint32_t k, SlotGeom* g) {
         const uint64_t slots = (uint64_t)ipc * kRun;
         const uint64_t crossings = slots / g->W + 2;
         const uint64_t span = slots + crossings * (k - 1) + k + 32;
-        g->smem = (size_t)((span + 15) / 16 + 6) * sizeof(uint2);
+        g->smem = (size_t)((span + 15) / 16 + span_entries + 2) * sizeof(uint2);
         if (g->smem <= 44 * 1024 || ipc <= 64) break;
         ipc /= 2;
     }
@@ -702,6 +674,21 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
 }
 
 // ======================================================================= extract wide (extension, K <= 64)
+template <int NW32>
+static cudaError_t launch_wide(bool fixed, bool validate, bool digest, unsigned grid, size_t smem, cudaStream_t st,
+                               const WideParams& p) {
+#define KMB_WIDE(KERNEL)                                                                                   \
+    do {                                                                                                   \
+        if (validate) { if (digest) KERNEL<NW32, true, true><<<grid, kExtractThreads, smem, st>>>(p);       \
+                        else KERNEL<NW32, true, false><<<grid, kExtractThreads, smem, st>>>(p); }           \
+        else { if (digest) KERNEL<NW32, false, true><<<grid, kExtractThreads, smem, st>>>(p);               \
+               else KERNEL<NW32, false, false><<<grid, kExtractThreads, smem, st>>>(p); }                   \
+    } while (0)
+    if (fixed) KMB_WIDE(extract_wide_fixed_kernel); else KMB_WIDE(extract_wide_csr_kernel);
+#undef KMB_WIDE
+    return cudaGetLastError();
+}
+
 extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t enc_id, uint32_t flags,
                                               uint64_t* canon_out, uint64_t* hash_out, kmb_digest* digest) {
     NEED_CTX(ctx);
@@ -719,19 +706,26 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
     if (digest && (rc = digest_begin(ctx))) return rc;
     const bool validate = !(flags & KMB_F_NO_VALIDATE);
     if (n_slots) {
-        p.bases = ctx->d_bases; p.n_bytes = ctx->n_bytes; p.K = k;
-        p.shiftD = 2 * (16 * kWideA - (kRun + k - 1));
-        for (int i = 0; i < 4; ++i) p.mask[i] = 2 * k > 32u * i ? mask32(2 * k - 32 * i) : 0u;
-        p.canon = (uint64_t*)oc.dev; p.hash = (uint64_t*)oh.dev; p.digest = ctx->d_digest;
+        const int nw32 = k <= 32 ? 2 : (k <= 48 ? 3 : 4);  // live 32-bit words of a k-mer
+        uint32_t mask[4];
+        for (int i = 0; i < 4; ++i) mask[i] = 2 * k > 32u * i ? mask32(2 * k - 32 * i) : 0u;
+        p.bases = ctx->d_bases; p.n_bytes = ctx->n_bytes;
+        p.wc.K = k;
+        p.wc.shiftD = 2 * (16 * (nw32 + 1) - (kRun + k - 1));
+        p.wc.mask_a = mask[nw32 - 2]; p.wc.mask_b = mask[nw32 - 1];
+        p.wc.cmask = p.enc.cmask; p.wc.cm_a = p.enc.cmask & p.wc.mask_a; p.wc.cm_b = p.enc.cmask & p.wc.mask_b;
+        p.wc.kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+        p.out.canon = (uint64_t*)oc.dev; p.out.hash = (uint64_t*)oh.dev; p.out.digest = ctx->d_digest;
+        p.out.vec_ok = ((((uintptr_t)oc.dev | (uintptr_t)oh.dev) & 31u) == 0) ? 1u : 0u;
         unsigned grid;
         size_t smem;
         const bool fixed = ctx->d_offsets == nullptr;
         if (fixed) {
-            RunGeom g;
-            if (!run_geom(ctx->n_reads, ctx->fixed_len, k, kWideA + 1, &g))
-                return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
-            p.L = ctx->fixed_len; p.L32 = (uint32_t)ctx->fixed_len; p.W = g.W; p.rpr = g.rpr; p.rpr_magic = g.rpr_magic;
-            p.total_items = g.total_items;
+            SlotGeom g;
+            if (!slot_geom(ctx->n_reads, ctx->fixed_len, k, &g, nw32 + 2))
+                return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
+            p.L = ctx->fixed_len; p.L32 = (uint32_t)ctx->fixed_len; p.W = g.W; p.W32 = g.W32; p.total_slots = g.total_slots;
+            p.w_magic64 = g.w_magic64; p.w_magic = g.w_magic; p.items_per_cta = g.items_per_cta;
             grid = g.grid; smem = g.smem;
         } else {
             if ((rc = ensure_win_offsets(ctx, k))) return rc;
@@ -739,18 +733,12 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
             const uint64_t ctas = (ctx->n_bytes + kCsrTileBases - 1) / kCsrTileBases;
             if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
             grid = (unsigned)ctas;
-            smem = (size_t)((kCsrTileBases + k + 32) / 16 + kWideA + 3) * sizeof(uint2);
+            smem = (size_t)((kCsrTileBases + k + 32) / 16 + nw32 + 4) * sizeof(uint2);
         }
-#define KMB_WIDE(KERNEL)                                                                              \
-        do {                                                                                          \
-            if (validate) { if (digest) KERNEL<true, true><<<grid, kExtractThreads, smem, ctx->stream>>>(p);  \
-                            else KERNEL<true, false><<<grid, kExtractThreads, smem, ctx->stream>>>(p); }      \
-            else { if (digest) KERNEL<false, true><<<grid, kExtractThreads, smem, ctx->stream>>>(p);          \
-                   else KERNEL<false, false><<<grid, kExtractThreads, smem, ctx->stream>>>(p); }              \
-        } while (0)
-        if (fixed) KMB_WIDE(extract_wide_fixed_kernel); else KMB_WIDE(extract_wide_csr_kernel);
-#undef KMB_WIDE
-        CK(ctx, cudaGetLastError());
+        cudaError_t e = nw32 == 2 ? launch_wide<2>(fixed, validate, digest != nullptr, grid, smem, ctx->stream, p)
+                      : nw32 == 3 ? launch_wide<3>(fixed, validate, digest != nullptr, grid, smem, ctx->stream, p)
+                                  : launch_wide<4>(fixed, validate, digest != nullptr, grid, smem, ctx->stream, p);
+        CK(ctx, e);
         ctx->launches++;
     }
     if ((rc = out_finish(ctx, oc))) return rc;
@@ -1006,11 +994,12 @@ static int32_t word_op(kmb_ctx* ctx, uint32_t k, const uint64_t* in, const uint6
     OutBuf o64, o8;
     if ((rc = out_prepare(ctx, 0, out, n * 8, &o64))) return rc;
     if ((rc = out_prepare(ctx, 1, out8, n, &o8))) return rc;
-    const uint64_t ctas = (n + 255) / 256;
+    const uint64_t ctas = ((n + 3) / 4 + 255) / 256;
     if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
     const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const uint32_t vec_ok = ((((uintptr_t)d_in | (uintptr_t)d_other | (uintptr_t)o64.dev) & 31u) == 0 && ((uintptr_t)o8.dev & 3u) == 0) ? 1u : 0u;
     word_op_kernel<OP><<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint64_t*)d_in, (const uint64_t*)d_other,
-                                                               (uint64_t*)o64.dev, (uint8_t*)o8.dev, n, k, mask);
+                                                               (uint64_t*)o64.dev, (uint8_t*)o8.dev, n, k, mask, vec_ok);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     if ((rc = out_finish(ctx, o64))) return rc;
