@@ -2,6 +2,7 @@
 // element-wise naive_impl::Kmer word operations, plus the synthetic generator.
 #pragma once
 #include "kmb_device.cuh"
+#include "kmb_geometry.cuh"
 
 namespace kmb {
 
@@ -82,6 +83,65 @@ __global__ void __launch_bounds__(256) pack_fixed_kernel(const PackParams p, uin
     store_packed32(p.out + r * p.out_bytes_per_read, g * 4, p.out_bytes_per_read, bits);
 }
 
+// Fixed-length reads whose packed region is a whole number of 32-bit groups: the same two-phase
+// shape as the extraction kernel.  A CTA owns kPackGroups consecutive OUTPUT groups (coalesced 4-byte
+// stores); it stages the stretch of reads they cover into shared memory with aligned 16-byte loads,
+// then every group is one funnel-shift extract of two packed entries.
+constexpr int kPackGroups = 2048;
+
+struct PackTileParams {
+    const uint8_t* bases;
+    uint64_t n_bytes;
+    uint64_t L;
+    uint64_t total_groups;  // n_reads * gpr
+    uint64_t gpr_magic64;   // floor(2^64 / gpr) + 1 (gpr >= 2), 0 = divide
+    uint32_t L32;
+    uint32_t gpr;           // 32-bit output groups per read
+    uint32_t gpr_magic;     // floor(2^32 / gpr) + 1
+    uint32_t* out;
+    EncDesc enc;
+};
+
+__device__ __forceinline__ uint32_t div_gpr(uint32_t u, const PackTileParams& p) {
+    if (p.gpr >= (uint32_t)kPackGroups) return (u >= p.gpr) ? 1u : 0u;
+    if (p.gpr == 1) return u;
+    return __umulhi(u, p.gpr_magic);
+}
+
+__global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) {
+    extern __shared__ uint2 tile[];
+    const uint64_t grp_base = (uint64_t)blockIdx.x * kPackGroups;
+    const uint32_t n_groups = (uint32_t)min((uint64_t)kPackGroups, p.total_groups - grp_base);
+    uint64_t r_first;
+    if (p.gpr == 1) r_first = grp_base;
+    else if (p.gpr_magic64) r_first = div_magic64(grp_base, p.gpr_magic64);
+    else r_first = grp_base / p.gpr;
+    const uint32_t g_first = (uint32_t)(grp_base - r_first * p.gpr);
+    // bases from the first group's first base to the end of the last group's read (or of its 16 bases)
+    const uint64_t b_start = r_first * p.L + min((uint64_t)g_first * 16, p.L);
+    const uint32_t u_last = g_first + n_groups - 1, q_last = div_gpr(u_last, p);
+    const uint64_t g_last = u_last - q_last * p.gpr;
+    const uint64_t b_end = (r_first + q_last) * p.L + min(g_last * 16 + 16, p.L);
+    const uint8_t* first = p.bases + b_start;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
+    const uint32_t n_entries = (uint32_t)((b_end - b_start + mis + 15) >> 4) + 1;  // +1: a group reads 2 entries
+    stage_tile<false>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
+    __syncthreads();
+    for (uint32_t li = threadIdx.x; li < n_groups; li += blockDim.x) {
+        const uint32_t u = g_first + li, q = div_gpr(u, p);
+        const uint64_t b0 = (uint64_t)(u - q * p.gpr) * 16;  // first base of the group inside its read
+        uint32_t bits = 0;
+        if (b0 < p.L) {
+            const uint32_t rel = (uint32_t)((r_first + q) * p.L + b0 - b_start) + mis;
+            const uint32_t e = rel >> 4, o2 = (rel & 15u) * 2;
+            bits = __funnelshift_r(tile[e].x, tile[e + 1].x, o2);
+            const uint64_t left = p.L - b0;
+            if (left < 16) bits &= (1u << (2 * (uint32_t)left)) - 1u;  // padding is zero bits (naive.rs:117 mem::zeroed)
+        }
+        p.out[grp_base + li] = bits;
+    }
+}
+
 // CSR: one warp per read
 __global__ void __launch_bounds__(256) pack_csr_kernel(const PackParams p) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -144,7 +204,18 @@ __global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, u
     uint32_t w[NW32];
     const bool aligned = (item_bytes == 4u * NW32) && ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0);
-    if (aligned) {
+    constexpr int VB = NW32 >= 4 ? 16 : 4 * NW32;  // widest natural vector for the item
+    const bool vec = aligned && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (VB - 1)) == 0;
+    if (vec && NW32 >= 4) {
+#pragma unroll
+        for (int i = 0; i < NW32 / 4; ++i) {
+            const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    } else if (vec && NW32 == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src);
+        w[0] = v.x; w[1] = v.y;
+    } else if (aligned) {
 #pragma unroll
         for (int i = 0; i < NW32; ++i) w[i] = reinterpret_cast<const uint32_t*>(src)[i];
     } else {
@@ -164,7 +235,13 @@ __global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, u
         const uint32_t srcbits = get32_signed(w, NW32, 2 * ((int)K - 16 * i - 16));
         o[i] = (pair_reverse32(srcbits ^ cmask) & vmask) | (w[i] & ~vmask);
     }
-    if (aligned) {
+    if (vec && NW32 >= 4) {
+#pragma unroll
+        for (int i = 0; i < NW32 / 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    } else if (vec && NW32 == 2) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+    } else if (aligned) {
 #pragma unroll
         for (int i = 0; i < NW32; ++i) reinterpret_cast<uint32_t*>(dst)[i] = o[i];
     } else {

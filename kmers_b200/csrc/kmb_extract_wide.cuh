@@ -36,18 +36,8 @@ struct WideOut {
 };
 
 struct WideParams {
-    const uint8_t* bases;
-    uint64_t n_bytes;
-    // fixed-length geometry (slot space, as ExtractParams)
-    uint64_t L, W, total_slots, w_magic64;
-    uint32_t L32, W32, w_magic, items_per_cta;
-    // CSR geometry
-    const uint64_t* offsets;
-    const uint64_t* win_offsets;
-    uint64_t n_reads;
     WideConst wc;
     WideOut out;
-    EncDesc enc;
 };
 
 template <int NW32>
@@ -175,7 +165,7 @@ __device__ __forceinline__ void emit_wide_run(const WideSpan<NW32>& A, const Wid
             if (CHECK && !ok[t]) { w[t].c0 = w[t].c1 = w[t].h0 = w[t].h1 = ~0ull; }
         }
         const uint64_t slot = slot0 + j2;
-        if ((uint32_t)j2 + 1 < nwin && o.vec_ok) {
+        if ((uint32_t)j2 + 1 < nwin && o.vec_ok && (slot & 1ull) == 0ull) {
             if (o.canon) st_stream_v4u64(o.canon + 2 * slot, w[0].c0, w[0].c1, w[1].c0, w[1].c1);
             if (o.hash) st_stream_v4u64(o.hash + 2 * slot, w[0].h0, w[0].h1, w[1].h0, w[1].h1);
         } else {
@@ -217,113 +207,29 @@ __device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][kExtrac
     }
 }
 
-__device__ __forceinline__ uint32_t wide_div_w(uint32_t u, const WideParams& p, uint32_t slots_per_cta) {
-    if (p.W32 >= slots_per_cta) return (u >= p.W32) ? 1u : 0u;
-    if (p.W32 == 1) return u;
-    return __umulhi(u, p.w_magic);
-}
-
+// The two-word engine plugged into the geometry of kmb_geometry.cuh (kernels: fixed_kernel / csr_kernel).
 template <int NW32, bool VALIDATE, bool DIGEST>
-__global__ void __launch_bounds__(kExtractThreads) extract_wide_fixed_kernel(const WideParams p) {
-    extern __shared__ uint2 tile[];
-    __shared__ unsigned long long red[3][kExtractThreads / 32];
-    const uint32_t slots_per_cta = p.items_per_cta * kRun;
-    const uint64_t slot_base = (uint64_t)blockIdx.x * slots_per_cta;
-    const uint32_t n_slots = (uint32_t)min((uint64_t)slots_per_cta, p.total_slots - slot_base);
-    uint64_t r_first;
-    if (p.W == 1) r_first = slot_base;
-    else if (p.w_magic64) r_first = div_magic64(slot_base, p.w_magic64);
-    else r_first = slot_base / p.W;
-    const uint32_t p_first = (uint32_t)(slot_base - r_first * p.W);
-    const uint64_t g_start = r_first * p.L + p_first;
-    const uint32_t u_last = p_first + n_slots - 1;
-    const uint32_t q_last = wide_div_w(u_last, p, slots_per_cta);
-    const uint32_t span = q_last * p.L32 + (u_last - q_last * p.W32) - p_first + p.wc.K;
-    const uint8_t* first = p.bases + g_start;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = ((span + mis + 15) >> 4) + NW32 + 1;  // a span reads NW32 + 2 entries
-    stage_tile<VALIDATE>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
-    __syncthreads();
-
+struct WideEng {
+    using Params = WideParams;
+    using Span = WideSpan<NW32>;
+    static constexpr bool kValidate = VALIDATE;
+    static constexpr int kSpanEntries = NW32 + 2;  // tile entries one span reads
+    const WideParams& p;
     WideAcc acc;
-    const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-    for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
-        const uint32_t u = p_first + li * kRun;
-        const uint32_t q = wide_div_w(u, p, slots_per_cta);
-        const uint32_t pos = u - q * p.W32;
-        const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
-        const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
-        const uint32_t rel = q * p.L32 + pos - p_first + mis;
-        const uint32_t left = p.W32 - pos;
-        if (left >= (uint32_t)kRun || left >= nwin) {
-            const WideSpan<NW32> s = load_wide_span<NW32, VALIDATE>(tile, rel, p.wc);
-            if (VALIDATE && (s.inv_lo | s.inv_hi) != 0ull) emit_wide_run<NW32, false, true, DIGEST>(s, s, kRun, p.wc, p.out, slot0, nwin, acc);
-            else emit_wide_run<NW32, false, false, DIGEST>(s, s, kRun, p.wc, p.out, slot0, nwin, acc);
-        } else if (p.W32 >= (uint32_t)kRun) {
-            const WideSpan<NW32> a = load_wide_span<NW32, VALIDATE>(tile, rel, p.wc);
-            const WideSpan<NW32> b = load_wide_span<NW32, VALIDATE>(tile, (q + 1) * p.L32 - p_first + mis - left, p.wc);
-            if (VALIDATE && (a.inv_lo | a.inv_hi | b.inv_lo | b.inv_hi) != 0ull)
-                emit_wide_run<NW32, true, true, DIGEST>(a, b, left, p.wc, p.out, slot0, nwin, acc);
-            else emit_wide_run<NW32, true, false, DIGEST>(a, b, left, p.wc, p.out, slot0, nwin, acc);
-        } else {
-            for (uint32_t j = 0; j < nwin; ++j) {
-                const uint32_t uj = u + j, qj = wide_div_w(uj, p, slots_per_cta);
-                emit_wide_single<NW32, VALIDATE, DIGEST>(tile, qj * p.L32 + (uj - qj * p.W32) - p_first + mis, p.wc, p.out,
-                                                         slot0 + j, acc);
-            }
-        }
+    __device__ explicit WideEng(const WideParams& params) : p(params) {}
+    __device__ __forceinline__ uint32_t K() const { return p.wc.K; }
+    __device__ __forceinline__ Span load(const uint2* tile, uint32_t rel) const { return load_wide_span<NW32, VALIDATE>(tile, rel, p.wc); }
+    __device__ __forceinline__ bool dirty(const Span& s) const { return (s.inv_lo | (uint64_t)s.inv_hi) != 0ull; }
+    template <bool TWO, bool CHECK>
+    __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin) {
+        emit_wide_run<NW32, TWO, CHECK, DIGEST>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
     }
-    wide_reduce<DIGEST>(red, p.out.digest, acc);
-}
-
-// ragged batches: fixed stretches of the flat stream, every window checks its own read
-template <int NW32, bool VALIDATE, bool DIGEST>
-__global__ void __launch_bounds__(kExtractThreads) extract_wide_csr_kernel(const WideParams p) {
-    extern __shared__ uint2 tile[];
-    __shared__ unsigned long long red[3][kExtractThreads / 32];
-    __shared__ uint64_t s_rlo, s_rhi;
-    const uint64_t g_start = (uint64_t)blockIdx.x * kCsrTileBases;
-    const uint64_t g_stop = min(g_start + (uint64_t)kCsrTileBases, p.n_bytes);
-    const uint64_t g_end = min(g_stop + p.wc.K - 1, p.n_bytes);
-    const uint8_t* first = p.bases + g_start;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = (uint32_t)((g_end - g_start + mis + 15) >> 4) + NW32 + 1;
-    stage_tile<VALIDATE>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
-    if (threadIdx.x == 0) {
-        s_rlo = find_read(p.offsets, 0, p.n_reads - 1, g_start);
-        s_rhi = find_read(p.offsets, s_rlo, p.n_reads - 1, g_stop - 1);
+    __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot) {
+        emit_wide_single<NW32, VALIDATE, DIGEST>(tile, rel, p.wc, p.out, slot, acc);
     }
-    __syncthreads();
-
-    WideAcc acc;
-    const uint32_t n_items = (uint32_t)((g_stop - g_start + kRun - 1) / kRun);
-    for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
-        const uint64_t g0 = g_start + (uint64_t)li * kRun;
-        const WideSpan<NW32> s = load_wide_span<NW32, VALIDATE>(tile, li * kRun + mis, p.wc);
-        uint64_t r = find_read(p.offsets, s_rlo, s_rhi, g0);
-        uint64_t r_beg = __ldg(p.offsets + r), r_end = __ldg(p.offsets + r + 1);
-        uint64_t w_off = __ldg(p.win_offsets + r);
-#pragma unroll
-        for (int j = 0; j < kRun; ++j) {
-            const uint64_t g = g0 + j;
-            if (g >= g_stop) break;
-            while (g >= r_end) {
-                ++r;
-                r_beg = r_end;
-                r_end = __ldg(p.offsets + r + 1);
-                w_off = __ldg(p.win_offsets + r);
-            }
-            if (g + p.wc.K > r_end) continue;
-            WideWindow w = wide_window<NW32>(s, j, p.wc);
-            const bool ok = !VALIDATE || wide_ok<NW32>(s, j, p.wc);
-            if (DIGEST && ok) { acc.canon += w.c0 + w.c1; acc.hash += w.h0 + w.h1; acc.valid += 1; }
-            if (!ok) { w.c0 = w.c1 = w.h0 = w.h1 = ~0ull; }
-            const uint64_t slot = w_off + (g - r_beg);
-            if (p.out.canon) st_stream_v2u64(p.out.canon + 2 * slot, w.c0, w.c1);
-            if (p.out.hash) st_stream_v2u64(p.out.hash + 2 * slot, w.h0, w.h1);
-        }
+    __device__ __forceinline__ void finish(unsigned long long (&red)[3][kExtractThreads / 32]) {
+        wide_reduce<DIGEST>(red, p.out.digest, acc);
     }
-    wide_reduce<DIGEST>(red, p.out.digest, acc);
-}
+};
 
 }  // namespace kmb

@@ -1,0 +1,277 @@
+// kmb_geometry.cuh -- how a batch of reads is cut into CTA tiles and per-thread work items,
+// shared by the K <= 32 engine (kmb_extract.cuh) and the two-word engine (kmb_extract_wide.cuh).
+//
+// Work is cut in OUTPUT-slot space: item i = slots [8i, 8i+8) of the dense result arrays
+// (SURVEY.md 8d layout), so an item's stores are 64-byte (128-byte for two-word k-mers) aligned
+// whatever the read lengths are.  A slot maps back to (read, window position):
+//   fixed-length reads : read = slot / W, pos = slot % W          (W = L - K + 1)
+//   ragged (CSR) reads : read = last r with win_offsets[r] <= slot, pos = slot - win_offsets[r]
+// An item lies inside one read (one span), straddles one read boundary (two spans), or -- only for
+// reads with fewer than 8 windows -- covers several reads (window-by-window path).
+//
+// A CTA first stages the stretch of the flat read stream its windows cover into shared memory
+// (2 bits/base + 1 invalid bit/base, kmb_device.cuh), then runs its items from that tile.
+#pragma once
+#include "kmb_device.cuh"
+
+namespace kmb {
+
+#ifndef KMB_EXTRACT_THREADS
+#define KMB_EXTRACT_THREADS 256
+#endif
+#ifndef KMB_ITEMS_PER_CTA
+#define KMB_ITEMS_PER_CTA 1024
+#endif
+constexpr int kExtractThreads = KMB_EXTRACT_THREADS;
+constexpr int kItemsPerCta = KMB_ITEMS_PER_CTA;  // default 1024 items = 8192 slots per CTA
+constexpr int kStageBatch = 3;                   // 16-byte loads a thread keeps in flight while staging
+
+// ---------------------------------------------------------------------------
+// phase 1: stage a stretch of the read stream into shared memory as
+// {packed bits, invalid mask} entries, 16 bases each.  Entry 0 starts at
+// first_al (16-byte aligned, at or below the first base needed).
+// ---------------------------------------------------------------------------
+template <bool VALIDATE>
+__device__ __forceinline__ void stage_tile(const uint8_t* bases, uint64_t n_bytes, const uint8_t* first_al,
+                                           uint32_t n_entries, const EncDesc& enc, uint2* tile) {
+    // CTA-uniform: does the whole stretch lie inside the batch?  (all but the edge CTAs)
+    const bool inside = first_al >= bases && first_al + (size_t)n_entries * 16 <= bases + n_bytes;
+    if (inside) {
+        const uint4* src = reinterpret_cast<const uint4*>(first_al);
+        for (uint32_t v0 = threadIdx.x; v0 < n_entries; v0 += kStageBatch * blockDim.x) {
+            uint4 raw[kStageBatch];
+#pragma unroll
+            for (int b = 0; b < kStageBatch; ++b) {  // all loads first: kStageBatch requests in flight per thread
+                const uint32_t v = v0 + b * blockDim.x;
+                if (v < n_entries) raw[b] = ld_stream_v4(src + v);
+            }
+#pragma unroll
+            for (int b = 0; b < kStageBatch; ++b) {
+                const uint32_t v = v0 + b * blockDim.x;
+                if (v < n_entries) {
+                    PackedWord pw = pack16<VALIDATE>(raw[b]);
+                    tile[v] = make_uint2(apply_encoding(pw.bits, enc), pw.inv);
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t v = threadIdx.x; v < n_entries; v += blockDim.x) {
+            PackedWord pw = pack16<VALIDATE>(load16_guarded(bases, n_bytes, first_al + (size_t)v * 16));
+            tile[v] = make_uint2(apply_encoding(pw.bits, enc), pw.inv);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fixed-length reads
+// ---------------------------------------------------------------------------
+struct FixedGeom {
+    const uint8_t* bases;   // flat read stream
+    uint64_t n_bytes;       // n_reads * L
+    uint64_t L;             // read length
+    uint64_t W;             // windows (= output slots) per read = L - K + 1
+    uint64_t total_slots;   // n_reads * W
+    uint64_t w_magic64;     // floor(2^64 / W) + 1 (W >= 2), 0 = divide
+    uint32_t L32;           // L mod 2^32 (only differences inside a tile are formed)
+    uint32_t W32;           // W (< 2^32, checked on the host)
+    uint32_t w_magic;       // floor(2^32 / W) + 1
+    uint32_t items_per_cta; // host-chosen so the staged stretch fits shared memory
+};
+
+// u / W for a small u (u < W + slots per CTA): 0/1 when W is large, else multiply-high
+__device__ __forceinline__ uint32_t div_w(uint32_t u, const FixedGeom& g, uint32_t slots_per_cta) {
+    if (g.W32 >= slots_per_cta) return (u >= g.W32) ? 1u : 0u;  // u < W + slots_per_cta <= 2W
+    if (g.W32 == 1) return u;
+    return __umulhi(u, g.w_magic);
+}
+
+template <class Eng>
+__device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& enc, Eng& eng, uint2* tile) {
+    const uint32_t K = eng.K();
+    const uint32_t slots_per_cta = g.items_per_cta * kRun;
+    const uint64_t slot_base = (uint64_t)blockIdx.x * slots_per_cta;
+    const uint32_t n_slots = (uint32_t)min((uint64_t)slots_per_cta, g.total_slots - slot_base);
+    uint64_t r_first;
+    if (g.W == 1) r_first = slot_base;
+    else if (g.w_magic64) r_first = div_magic64(slot_base, g.w_magic64);
+    else r_first = slot_base / g.W;
+    const uint32_t p_first = (uint32_t)(slot_base - r_first * g.W);  // position of the CTA's first window in its read
+
+    // ---- phase 1: pack the stretch of the flat stream that holds the CTA's windows
+    const uint64_t g_start = r_first * g.L + p_first;
+    const uint32_t u_last = p_first + n_slots - 1;
+    const uint32_t q_last = div_w(u_last, g, slots_per_cta);
+    // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
+    const uint32_t span = q_last * g.L32 + (u_last - q_last * g.W32) - p_first + K;
+    const uint8_t* first = g.bases + g_start;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
+    const uint32_t n_entries = ((span + mis + 15) >> 4) + Eng::kSpanEntries - 1;
+    stage_tile<Eng::kValidate>(g.bases, g.n_bytes, first - mis, n_entries, enc, tile);
+    __syncthreads();
+
+    // ---- phase 2
+    const uint32_t n_items = (n_slots + kRun - 1) / kRun;
+    for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
+        const uint32_t u = p_first + li * kRun;           // first slot, counted from window 0 of read r_first
+        const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
+        const uint32_t pos = u - q * g.W32;                 // window position inside its read
+        const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
+        const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+        const uint32_t rel = q * g.L32 + pos - p_first + mis;  // first base, relative to tile entry 0
+        const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
+        if (left >= (uint32_t)kRun || left >= nwin) {
+            const typename Eng::Span s = eng.load(tile, rel);
+            if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kRun, slot0, nwin);
+            else eng.template run<false, false>(s, s, kRun, slot0, nwin);
+        } else if (g.W32 >= (uint32_t)kRun) {
+            // straddles exactly one boundary: windows j >= left start read q+1 at position j - left
+            const typename Eng::Span a = eng.load(tile, rel);
+            const typename Eng::Span b = eng.load(tile, (q + 1) * g.L32 - p_first + mis - left);
+            if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin);
+            else eng.template run<true, false>(a, b, left, slot0, nwin);
+        } else {
+            // reads with fewer than kRun windows: window by window
+            for (uint32_t j = 0; j < nwin; ++j) {
+                const uint32_t uj = u + j, qj = div_w(uj, g, slots_per_cta);
+                eng.single(tile, qj * g.L32 + (uj - qj * g.W32) - p_first + mis, slot0 + j);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ragged reads (CSR offsets)
+// ---------------------------------------------------------------------------
+constexpr int kCsrCache = 1024;  // reads whose offsets a CTA keeps in shared memory per pass
+
+struct CsrGeom {
+    const uint8_t* bases;
+    uint64_t n_bytes;
+    const uint64_t* offsets;      // n_reads + 1
+    const uint64_t* win_offsets;  // n_reads + 1, exclusive prefix of per-read window counts
+    const uint64_t* first_read;   // grid + 1: read owning each CTA's first slot (csr_index_kernel)
+    uint64_t n_reads;
+    uint64_t total_slots;
+    uint32_t items_per_cta;
+    uint32_t tile_entries;        // shared-memory capacity of the staged tile, in 16-base entries
+};
+
+// largest r in [lo, hi] with a[r] <= v   (a[lo] <= v guaranteed)
+__device__ __forceinline__ uint64_t last_le(const uint64_t* a, uint64_t lo, uint64_t hi, uint64_t v) {
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo + 1) >> 1);
+        if (a[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// first_read[b] = read owning slot b * slots_per_cta (b < grid); first_read[grid] = read owning the last slot.
+// One thread per CTA of the extraction grid: the log2(n_reads)-deep searches all run concurrently here
+// instead of serially at the head of every extraction CTA.
+__global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_slots,
+                                                        uint64_t slots_per_cta, uint64_t grid, uint64_t* first_read) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > grid) return;
+    const uint64_t slot = b < grid ? b * slots_per_cta : total_slots - 1;
+    first_read[b] = last_le(win_offsets, 0, n_reads - 1, slot);  // skips window-less reads: takes the last equal entry
+}
+
+struct CsrPass {  // one staged stretch: slots [slot_lo, slot_hi) of reads [r_lo, r_hi]
+    uint64_t slot_lo, slot_hi, r_lo, r_hi, g0;
+    uint32_t span;
+};
+
+template <class Eng>
+__device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint64_t* c_off,
+                                         uint64_t* c_win, CsrPass* pass) {
+    const uint32_t K = eng.K();
+    const uint64_t slots_per_cta = (uint64_t)g.items_per_cta * kRun;
+    const uint64_t slot_begin = (uint64_t)blockIdx.x * slots_per_cta;
+    const uint64_t slot_end = min(g.total_slots, slot_begin + slots_per_cta);
+    const uint32_t tile_bases = (g.tile_entries - Eng::kSpanEntries - 1) * 16;  // bases one pass can stage
+
+    // reads this CTA can touch; their offsets go to shared memory when they fit (the common case)
+    const uint64_t R_lo = g.first_read[blockIdx.x], R_hi = g.first_read[blockIdx.x + 1];
+    const uint64_t* off = g.offsets;  // tables indexed by absolute read number
+    const uint64_t* win = g.win_offsets;
+    if (R_hi - R_lo + 2 <= (uint64_t)kCsrCache + 2) {
+        const uint32_t n = (uint32_t)(R_hi - R_lo + 2);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            c_off[i] = g.offsets[R_lo + i];
+            c_win[i] = g.win_offsets[R_lo + i];
+        }
+        off = c_off - R_lo;
+        win = c_win - R_lo;
+    }
+    __syncthreads();
+
+    uint64_t cur = slot_begin, r_cur = R_lo;
+    while (cur < slot_end) {  // CTA-uniform; one pass unless a stretch of very short reads overflows the tile
+        if (threadIdx.x == 0) {
+            CsrPass ps;
+            ps.slot_lo = cur;
+            ps.r_lo = last_le(win, r_cur, R_hi, cur);  // owner of slot `cur`
+            ps.g0 = off[ps.r_lo] + (cur - win[ps.r_lo]);
+            // windows starting before g_lim fit wholly in a tile that starts at g0
+            const uint64_t g_lim = ps.g0 + tile_bases - K + 1;
+            uint64_t lim = slot_end;
+            if (g_lim < g.n_bytes) {
+                const uint64_t r = last_le(off, ps.r_lo, R_hi, g_lim);
+                const uint64_t w_r = win[r + 1] - win[r];
+                lim = min(lim, win[r] + min(g_lim - off[r], w_r));  // slots whose window starts before g_lim
+            }
+            if (lim < slot_end && lim - cur >= (uint64_t)kRun) lim = cur + ((lim - cur) / kRun) * kRun;  // keep items aligned
+            ps.slot_hi = lim;
+            ps.r_hi = last_le(win, ps.r_lo, R_hi, lim - 1);
+            const uint64_t g_end = off[ps.r_hi] + (lim - 1 - win[ps.r_hi]) + K;
+            ps.span = (uint32_t)(g_end - ps.g0);
+            *pass = ps;
+        }
+        __syncthreads();
+        const CsrPass ps = *pass;
+        const uint8_t* first = g.bases + ps.g0;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
+        const uint32_t n_entries = ((ps.span + mis + 15) >> 4) + Eng::kSpanEntries - 1;
+        stage_tile<Eng::kValidate>(g.bases, g.n_bytes, first - mis, n_entries, enc, tile);
+        __syncthreads();
+
+        const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
+        const uint32_t n_items = (n_slots + kRun - 1) / kRun;
+        for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
+            const uint64_t slot0 = ps.slot_lo + (uint64_t)li * kRun;
+            const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+            uint64_t r = last_le(win, ps.r_lo, ps.r_hi, slot0);
+            const uint64_t pos = slot0 - win[r];
+            const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
+            const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
+            if (left >= nwin) {
+                const typename Eng::Span s = eng.load(tile, rel);
+                if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kRun, slot0, nwin);
+                else eng.template run<false, false>(s, s, kRun, slot0, nwin);
+                continue;
+            }
+            uint64_t r2 = r + 1;
+            while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+            if (left + (win[r2 + 1] - win[r2]) >= nwin) {
+                const typename Eng::Span a = eng.load(tile, rel);
+                const typename Eng::Span b = eng.load(tile, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left);
+                if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, (uint32_t)left, slot0, nwin);
+                else eng.template run<true, false>(a, b, (uint32_t)left, slot0, nwin);
+                continue;
+            }
+            // several short reads inside one item: window by window
+            uint64_t p = pos, w_r = win[r + 1] - win[r];
+            for (uint32_t j = 0; j < nwin; ++j) {
+                while (p >= w_r) { ++r; p = 0; w_r = win[r + 1] - win[r]; }
+                eng.single(tile, (uint32_t)(off[r] + p - ps.g0) + mis, slot0 + j);
+                ++p;
+            }
+        }
+        __syncthreads();  // the next pass overwrites the tile
+        cur = ps.slot_hi;
+        r_cur = ps.r_hi;
+    }
+}
+
+}  // namespace kmb

@@ -43,6 +43,9 @@ struct kmb_ctx {
     uint64_t win_total = 0;
     bool win_valid = false;
 
+    uint64_t* d_first_read = nullptr;  // per-CTA first read of the CSR kernels
+    size_t first_read_cap = 0;
+
     // scratch
     unsigned long long* d_digest = nullptr;  // 3 words
     unsigned long long* h_digest = nullptr;  // pinned, 4 words
@@ -162,6 +165,7 @@ extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
     cudaFree(ctx->own_bases);
     cudaFree(ctx->own_offsets);
     cudaFree(ctx->d_win_offsets);
+    cudaFree(ctx->d_first_read);
     cudaFree(ctx->d_digest);
     cudaFreeHost(ctx->h_digest);
     for (auto& s : ctx->d_scratch) cudaFree(s);
@@ -491,54 +495,18 @@ static int32_t digest_end(kmb_ctx* ctx, kmb_digest* digest) {
     return KMB_OK;
 }
 
-// ======================================================================= extract (K <= 32)
+// ======================================================================= geometry (shared by both engines)
 static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
 
-// Template dispatch: VALIDATE x DIGEST x FWRC x KHI for one MODE.
-template <int MODE, class Params, class Launch>
-static cudaError_t dispatch5(bool validate, bool digest, bool fwrc, bool khi, const Launch& launch) {
-#define KMB_CASE(V, D, F, H) if (validate == V && digest == D && fwrc == F && khi == H) { launch(std::integral_constant<bool, V>{}, std::integral_constant<bool, D>{}, std::integral_constant<bool, F>{}, std::integral_constant<bool, H>{}); return cudaGetLastError(); }
-    KMB_CASE(true, false, false, true) KMB_CASE(true, false, false, false)
-    KMB_CASE(true, true, false, true) KMB_CASE(true, true, false, false)
-    KMB_CASE(false, false, false, true) KMB_CASE(false, false, false, false)
-    KMB_CASE(false, true, false, true) KMB_CASE(false, true, false, false)
-    if (MODE == 0) {
-        KMB_CASE(true, false, true, true) KMB_CASE(true, false, true, false)
-        KMB_CASE(true, true, true, true) KMB_CASE(true, true, true, false)
-        KMB_CASE(false, false, true, true) KMB_CASE(false, false, true, false)
-        KMB_CASE(false, true, true, true) KMB_CASE(false, true, true, false)
-    }
-#undef KMB_CASE
-    return cudaErrorInvalidValue;
-}
-
-template <int MODE>
-static cudaError_t launch_fixed(bool validate, bool digest, bool fwrc, bool khi, unsigned grid, size_t smem,
-                                cudaStream_t st, const ExtractParams& p) {
-    return dispatch5<MODE, ExtractParams>(validate, digest, fwrc, khi, [&](auto V, auto D, auto F, auto H) {
-        extract_fixed_kernel<decltype(V)::value, decltype(D)::value, (MODE == 0) && decltype(F)::value, MODE, decltype(H)::value>
-            <<<grid, kExtractThreads, smem, st>>>(p);
-    });
-}
-
-template <int MODE>
-static cudaError_t launch_csr(bool validate, bool digest, bool fwrc, bool khi, unsigned grid, size_t smem,
-                              cudaStream_t st, const CsrParams& p) {
-    return dispatch5<MODE, CsrParams>(validate, digest, fwrc, khi, [&](auto V, auto D, auto F, auto H) {
-        extract_csr_kernel<decltype(V)::value, decltype(D)::value, (MODE == 0) && decltype(F)::value, MODE, decltype(H)::value>
-            <<<grid, kExtractThreads, smem, st>>>(p);
-    });
-}
-
-// slot-space geometry of extract_fixed_kernel
-struct SlotGeom {
-    uint64_t W, total_slots, w_magic64;
-    uint32_t W32, w_magic, items_per_cta;
-    unsigned grid;
-    size_t smem;
+struct Launch {
+    unsigned grid = 0;
+    size_t smem = 0;
 };
 
-static bool slot_geom(uint64_t n_reads, uint64_t L, uint32_t k, SlotGeom* g, uint32_t span_entries = 4) {
+// fixed-length reads: slot-space geometry of fixed_kernel
+static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
+                            uint32_t span_entries, FixedGeom* g, Launch* l) {
+    g->bases = d_bases; g->n_bytes = n_bytes; g->L = L; g->L32 = (uint32_t)L;
     g->W = L - k + 1;
     if (g->W > 0xFFFF0000ull) return false;  // one read of > 4.29 Gbases: split it (window positions are 32-bit inside a CTA)
     g->W32 = (uint32_t)g->W;
@@ -553,16 +521,68 @@ static bool slot_geom(uint64_t n_reads, uint64_t L, uint32_t k, SlotGeom* g, uin
         const uint64_t slots = (uint64_t)ipc * kRun;
         const uint64_t crossings = slots / g->W + 2;
         const uint64_t span = slots + crossings * (k - 1) + k + 32;
-        g->smem = (size_t)((span + 15) / 16 + span_entries + 2) * sizeof(uint2);
-        if (g->smem <= 44 * 1024 || ipc <= 64) break;
+        l->smem = (size_t)((span + 15) / 16 + span_entries + 2) * sizeof(uint2);
+        if (l->smem <= 44 * 1024 || ipc <= 64) break;
         ipc /= 2;
     }
     g->items_per_cta = ipc;
     const uint64_t items = (g->total_slots + kRun - 1) / kRun;
     const uint64_t ctas = (items + ipc - 1) / ipc;
     if (ctas > 0x7FFFFFFFull) return false;
-    g->grid = (unsigned)ctas;
+    l->grid = (unsigned)ctas;
     return true;
+}
+
+// ragged reads: window offsets (cached per k), per-CTA first-read index, shared-memory layout of csr_kernel
+static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, CsrGeom* g, Launch* l) {
+    int32_t rc = ensure_win_offsets(ctx, k);
+    if (rc) return rc;
+    g->bases = ctx->d_bases; g->n_bytes = ctx->n_bytes; g->offsets = ctx->d_offsets; g->win_offsets = ctx->d_win_offsets;
+    g->n_reads = ctx->n_reads; g->total_slots = ctx->win_total; g->items_per_cta = kItemsPerCta;
+    g->tile_entries = 2304 + span_entries;  // ~36.8 K bases per pass
+    const uint64_t slots_per_cta = (uint64_t)kItemsPerCta * kRun;
+    const uint64_t ctas = (g->total_slots + slots_per_cta - 1) / slots_per_cta;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    l->grid = (unsigned)ctas;
+    l->smem = (size_t)g->tile_entries * sizeof(uint2) + 2 * (size_t)(kCsrCache + 2) * sizeof(uint64_t);
+    if ((rc = grow(ctx, (void**)&ctx->d_first_read, &ctx->first_read_cap, (ctas + 1) * 8))) return rc;
+    g->first_read = ctx->d_first_read;
+    if (ctas) {
+        csr_index_kernel<<<(unsigned)((ctas + 1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_win_offsets, ctx->n_reads, g->total_slots,
+                                                                                   slots_per_cta, ctas, ctx->d_first_read);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return KMB_OK;
+}
+
+template <class Eng>
+static cudaError_t launch_eng(const FixedGeom* fg, const CsrGeom* cg, const Launch& l, cudaStream_t st, const EncDesc& enc,
+                              const typename Eng::Params& ep) {
+    if (fg) fixed_kernel<Eng><<<l.grid, kExtractThreads, l.smem, st>>>(*fg, enc, ep);
+    else csr_kernel<Eng><<<l.grid, kExtractThreads, l.smem, st>>>(*cg, enc, ep);
+    return cudaGetLastError();
+}
+
+// ======================================================================= extract (K <= 32)
+// Template dispatch: VALIDATE x DIGEST x FWRC x KHI for one MODE.
+template <int MODE>
+static cudaError_t launch_narrow(bool validate, bool digest, bool fwrc, bool khi, const FixedGeom* fg, const CsrGeom* cg,
+                                 const Launch& l, cudaStream_t st, const EncDesc& enc, const NarrowParams& ep) {
+#define KMB_CASE(V, D, F, H) \
+    if (validate == V && digest == D && fwrc == F && khi == H) return launch_eng<NarrowEng<V, D, F, MODE, H>>(fg, cg, l, st, enc, ep);
+    KMB_CASE(true, false, false, true) KMB_CASE(true, false, false, false)
+    KMB_CASE(true, true, false, true) KMB_CASE(true, true, false, false)
+    KMB_CASE(false, false, false, true) KMB_CASE(false, false, false, false)
+    KMB_CASE(false, true, false, true) KMB_CASE(false, true, false, false)
+    if (MODE == 0) {
+        KMB_CASE(true, false, (MODE == 0), true) KMB_CASE(true, false, (MODE == 0), false)
+        KMB_CASE(true, true, (MODE == 0), true) KMB_CASE(true, true, (MODE == 0), false)
+        KMB_CASE(false, false, (MODE == 0), true) KMB_CASE(false, false, (MODE == 0), false)
+        KMB_CASE(false, true, (MODE == 0), true) KMB_CASE(false, true, (MODE == 0), false)
+    }
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
 }
 
 static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
@@ -578,46 +598,37 @@ static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
     return wc;
 }
 
-static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint64_t n_bytes,
-                           uint64_t n_reads, uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* canon,
-                           uint64_t* hash, uint64_t* fw, uint64_t* rc, bool want_digest, unsigned long long* hist,
-                           uint32_t hist_bits, cudaStream_t st) {
+// One extraction launch over (d_bases, fixed_len) -- or over the ctx's resident CSR batch when fixed_len == 0.
+static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint64_t n_bytes, uint64_t n_reads,
+                           uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* canon, uint64_t* hash, uint64_t* fw,
+                           uint64_t* rc, bool want_digest, unsigned long long* hist, uint32_t hist_bits, cudaStream_t st) {
     EncDesc enc;
     make_enc(KMB_ENC_ACGT, &enc, nullptr);
     const bool validate = !(flags & KMB_F_NO_VALIDATE);
     const bool fwrc = fw || rc;
     const bool khi = k > 16;
-    OutPtrs out{};
-    out.canon = canon; out.hash = hash; out.fw = fw; out.rc = rc;
-    out.digest = ctx->d_digest; out.hist = hist; out.hist_shift = 2 * k - hist_bits;
-    out.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
-    if (!d_offsets) {
+    NarrowParams ep{};
+    ep.wc = make_winconst(k, enc);
+    ep.out.canon = canon; ep.out.hash = hash; ep.out.fw = fw; ep.out.rc = rc;
+    ep.out.digest = ctx->d_digest; ep.out.hist = hist; ep.out.hist_shift = 2 * k - hist_bits;
+    ep.out.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
+    FixedGeom fg{};
+    CsrGeom cg{};
+    Launch l;
+    if (!csr) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
-        SlotGeom g;
-        if (!slot_geom(n_reads, fixed_len, k, &g)) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
-        ExtractParams p{};
-        p.bases = d_bases; p.n_bytes = n_bytes; p.L = fixed_len; p.L32 = (uint32_t)fixed_len; p.W = g.W; p.W32 = g.W32;
-        p.total_slots = g.total_slots; p.w_magic64 = g.w_magic64; p.w_magic = g.w_magic; p.items_per_cta = g.items_per_cta;
-        p.wc = make_winconst(k, enc); p.out = out; p.enc = enc;
-        cudaError_t e = hist ? launch_fixed<1>(validate, want_digest, false, khi, g.grid, g.smem, st, p)
-                             : launch_fixed<0>(validate, want_digest, fwrc, khi, g.grid, g.smem, st, p);
-        CK(ctx, e);
-        ctx->launches++;
+        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l))
+            return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else {
         if (n_bytes == 0 || n_reads == 0) return KMB_OK;
-        int32_t r = ensure_win_offsets(ctx, k);
+        int32_t r = make_csr_geom(ctx, k, 4, &cg, &l);
         if (r) return r;
-        CsrParams p{};
-        p.bases = d_bases; p.n_bytes = n_bytes; p.offsets = d_offsets; p.win_offsets = ctx->d_win_offsets;
-        p.n_reads = n_reads; p.wc = make_winconst(k, enc); p.out = out; p.enc = enc;
-        const uint64_t ctas = (n_bytes + kCsrTileBases - 1) / kCsrTileBases;
-        if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
-        const size_t smem = (size_t)((kCsrTileBases + k + 32) / 16 + 6) * sizeof(uint2);
-        cudaError_t e = hist ? launch_csr<1>(validate, want_digest, false, khi, (unsigned)ctas, smem, st, p)
-                             : launch_csr<0>(validate, want_digest, fwrc, khi, (unsigned)ctas, smem, st, p);
-        CK(ctx, e);
-        ctx->launches++;
+        if (cg.total_slots == 0) return KMB_OK;
     }
+    cudaError_t e = hist ? launch_narrow<1>(validate, want_digest, false, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
+                         : launch_narrow<0>(validate, want_digest, fwrc, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
+    CK(ctx, e);
+    ctx->launches++;
     return KMB_OK;
 }
 
@@ -637,7 +648,7 @@ extern "C" int32_t kmb_extract_canonical(kmb_ctx* ctx, uint32_t k, uint32_t flag
         if ((rc = out_prepare(ctx, i, user[i], n_slots * 8, &ob[i]))) return rc;
     if (digest && (rc = digest_begin(ctx))) return rc;
     if (n_slots) {
-        rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags,
+        rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags,
                          (uint64_t*)ob[0].dev, (uint64_t*)ob[1].dev, (uint64_t*)ob[2].dev, (uint64_t*)ob[3].dev,
                          digest != nullptr, nullptr, 0, ctx->stream);
         if (rc) return rc;
@@ -664,7 +675,7 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
     if (ob.host && accumulate) CK(ctx, cudaMemcpyAsync(ob.dev, hist_out, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (!accumulate) CK(ctx, cudaMemsetAsync(ob.dev, 0, bytes, ctx->stream));
     if (digest && (rc = digest_begin(ctx))) return rc;
-    rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags, nullptr,
+    rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags, nullptr,
                      nullptr, nullptr, nullptr, digest != nullptr, (unsigned long long*)ob.dev, hist_bits, ctx->stream);
     if (rc) return rc;
     if ((rc = out_finish(ctx, ob))) return rc;
@@ -675,18 +686,12 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
 
 // ======================================================================= extract wide (extension, K <= 64)
 template <int NW32>
-static cudaError_t launch_wide(bool fixed, bool validate, bool digest, unsigned grid, size_t smem, cudaStream_t st,
-                               const WideParams& p) {
-#define KMB_WIDE(KERNEL)                                                                                   \
-    do {                                                                                                   \
-        if (validate) { if (digest) KERNEL<NW32, true, true><<<grid, kExtractThreads, smem, st>>>(p);       \
-                        else KERNEL<NW32, true, false><<<grid, kExtractThreads, smem, st>>>(p); }           \
-        else { if (digest) KERNEL<NW32, false, true><<<grid, kExtractThreads, smem, st>>>(p);               \
-               else KERNEL<NW32, false, false><<<grid, kExtractThreads, smem, st>>>(p); }                   \
-    } while (0)
-    if (fixed) KMB_WIDE(extract_wide_fixed_kernel); else KMB_WIDE(extract_wide_csr_kernel);
-#undef KMB_WIDE
-    return cudaGetLastError();
+static cudaError_t launch_wide(bool validate, bool digest, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
+                               cudaStream_t st, const EncDesc& enc, const WideParams& ep) {
+    if (validate) return digest ? launch_eng<WideEng<NW32, true, true>>(fg, cg, l, st, enc, ep)
+                                : launch_eng<WideEng<NW32, true, false>>(fg, cg, l, st, enc, ep);
+    return digest ? launch_eng<WideEng<NW32, false, true>>(fg, cg, l, st, enc, ep)
+                  : launch_eng<WideEng<NW32, false, false>>(fg, cg, l, st, enc, ep);
 }
 
 extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t enc_id, uint32_t flags,
@@ -695,8 +700,8 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
     BIND(ctx);
     NEED_BATCH(ctx);
     if (k < 1 || k > 64) return fail(ctx, KMB_ERR_INVALID_ARG, "k = %u: the two-word path supports 1 <= k <= 64", k);
-    WideParams p{};
-    if (!make_enc(enc_id, &p.enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
+    EncDesc enc;
+    if (!make_enc(enc_id, &enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
     uint64_t n_slots = 0;
     int32_t rc = num_slots(ctx, k, &n_slots);
     if (rc) return rc;
@@ -709,35 +714,29 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         const int nw32 = k <= 32 ? 2 : (k <= 48 ? 3 : 4);  // live 32-bit words of a k-mer
         uint32_t mask[4];
         for (int i = 0; i < 4; ++i) mask[i] = 2 * k > 32u * i ? mask32(2 * k - 32 * i) : 0u;
-        p.bases = ctx->d_bases; p.n_bytes = ctx->n_bytes;
-        p.wc.K = k;
-        p.wc.shiftD = 2 * (16 * (nw32 + 1) - (kRun + k - 1));
-        p.wc.mask_a = mask[nw32 - 2]; p.wc.mask_b = mask[nw32 - 1];
-        p.wc.cmask = p.enc.cmask; p.wc.cm_a = p.enc.cmask & p.wc.mask_a; p.wc.cm_b = p.enc.cmask & p.wc.mask_b;
-        p.wc.kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
-        p.out.canon = (uint64_t*)oc.dev; p.out.hash = (uint64_t*)oh.dev; p.out.digest = ctx->d_digest;
-        p.out.vec_ok = ((((uintptr_t)oc.dev | (uintptr_t)oh.dev) & 31u) == 0) ? 1u : 0u;
-        unsigned grid;
-        size_t smem;
-        const bool fixed = ctx->d_offsets == nullptr;
-        if (fixed) {
-            SlotGeom g;
-            if (!slot_geom(ctx->n_reads, ctx->fixed_len, k, &g, nw32 + 2))
+        WideParams ep{};
+        ep.wc.K = k;
+        ep.wc.shiftD = 2 * (16 * (nw32 + 1) - (kRun + k - 1));
+        ep.wc.mask_a = mask[nw32 - 2]; ep.wc.mask_b = mask[nw32 - 1];
+        ep.wc.cmask = enc.cmask; ep.wc.cm_a = enc.cmask & ep.wc.mask_a; ep.wc.cm_b = enc.cmask & ep.wc.mask_b;
+        ep.wc.kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+        ep.out.canon = (uint64_t*)oc.dev; ep.out.hash = (uint64_t*)oh.dev; ep.out.digest = ctx->d_digest;
+        ep.out.vec_ok = ((((uintptr_t)oc.dev | (uintptr_t)oh.dev) & 31u) == 0) ? 1u : 0u;
+        FixedGeom fg{};
+        CsrGeom cg{};
+        Launch l;
+        const bool csr = ctx->d_offsets != nullptr;
+        if (!csr) {
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, nw32 + 2, &fg, &l))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
-            p.L = ctx->fixed_len; p.L32 = (uint32_t)ctx->fixed_len; p.W = g.W; p.W32 = g.W32; p.total_slots = g.total_slots;
-            p.w_magic64 = g.w_magic64; p.w_magic = g.w_magic; p.items_per_cta = g.items_per_cta;
-            grid = g.grid; smem = g.smem;
-        } else {
-            if ((rc = ensure_win_offsets(ctx, k))) return rc;
-            p.offsets = ctx->d_offsets; p.win_offsets = ctx->d_win_offsets; p.n_reads = ctx->n_reads;
-            const uint64_t ctas = (ctx->n_bytes + kCsrTileBases - 1) / kCsrTileBases;
-            if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
-            grid = (unsigned)ctas;
-            smem = (size_t)((kCsrTileBases + k + 32) / 16 + nw32 + 4) * sizeof(uint2);
+        } else if ((rc = make_csr_geom(ctx, k, nw32 + 2, &cg, &l))) {
+            return rc;
         }
-        cudaError_t e = nw32 == 2 ? launch_wide<2>(fixed, validate, digest != nullptr, grid, smem, ctx->stream, p)
-                      : nw32 == 3 ? launch_wide<3>(fixed, validate, digest != nullptr, grid, smem, ctx->stream, p)
-                                  : launch_wide<4>(fixed, validate, digest != nullptr, grid, smem, ctx->stream, p);
+        const FixedGeom* pf = csr ? nullptr : &fg;
+        const CsrGeom* pc = csr ? &cg : nullptr;
+        cudaError_t e = nw32 == 2 ? launch_wide<2>(validate, digest != nullptr, pf, pc, l, ctx->stream, enc, ep)
+                      : nw32 == 3 ? launch_wide<3>(validate, digest != nullptr, pf, pc, l, ctx->stream, enc, ep)
+                                  : launch_wide<4>(validate, digest != nullptr, pf, pc, l, ctx->stream, enc, ep);
         CK(ctx, e);
         ctx->launches++;
     }
@@ -806,7 +805,7 @@ extern "C" int32_t kmb_extract_canonical_host(kmb_ctx* ctx, const uint8_t* host_
             CK(ctx, cudaEventRecord(ctx->ev_in[buf], ctx->copy_stream));
             CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
             if (chunk_idx >= 2 && want_out) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[buf], 0));
-            rc = run_extract(ctx, ctx->pipe_in[buf], nullptr, in_bytes, nr, fixed_len, k, flags, ctx->pipe_canon[buf],
+            rc = run_extract(ctx, ctx->pipe_in[buf], false, in_bytes, nr, fixed_len, k, flags, ctx->pipe_canon[buf],
                              ctx->pipe_hash[buf], nullptr, nullptr, digest != nullptr, nullptr, 0, ctx->stream);
             if (rc) return rc;
             CK(ctx, cudaEventRecord(ctx->ev_k[buf], ctx->stream));
@@ -875,7 +874,21 @@ extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, vo
     if (total && words_out) {
         p.bases = ctx->d_bases; p.offsets = ctx->d_offsets; p.word_offsets = d_woff; p.n_reads = ctx->n_reads;
         p.L = ctx->fixed_len; p.word_bytes = word_bytes; p.bases_per_word = bpw; p.out = (uint8_t*)ob.dev;
-        if (!ctx->d_offsets) {
+        if (!ctx->d_offsets && ((((ctx->fixed_len + bpw - 1) / bpw) * word_bytes) % 4 == 0) && ((uintptr_t)ob.dev & 3u) == 0 &&
+            ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes / 4 <= 0xFFFFFFFFull) {
+            // regions are whole 32-bit groups: tiled kernel (aligned loads, coalesced stores)
+            PackTileParams t{};
+            t.bases = ctx->d_bases; t.n_bytes = ctx->n_bytes; t.L = ctx->fixed_len; t.L32 = (uint32_t)ctx->fixed_len;
+            t.gpr = (uint32_t)(((ctx->fixed_len + bpw - 1) / bpw) * word_bytes / 4);
+            t.total_groups = ctx->n_reads * t.gpr;
+            t.gpr_magic = t.gpr > 1 ? (uint32_t)((1ull << 32) / t.gpr + 1) : 0;
+            t.gpr_magic64 = (t.gpr > 1 && (double)t.total_groups * (double)t.gpr < 9.0e18) ? (~0ull / t.gpr + 1) : 0;
+            t.out = (uint32_t*)ob.dev; t.enc = p.enc;
+            const uint64_t ctas = (t.total_groups + kPackGroups - 1) / kPackGroups;
+            if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+            const size_t smem = (size_t)(kPackGroups + 8) * sizeof(uint2);
+            pack_tile_kernel<<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
+        } else if (!ctx->d_offsets) {
             p.out_bytes_per_read = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;
             const uint64_t gpr = (p.out_bytes_per_read + 3) / 4;
             const uint64_t threads = ctx->n_reads * gpr;
