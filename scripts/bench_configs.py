@@ -157,8 +157,61 @@ def main():
     row("config5 1 Gbp, fused histogram 2^16 bins + digest", g - K + 1, "kmers", g + 8 * 65536, avg, best,
         "ALU/atomic-bound by construction")
 
+    # ---------------- config 1: the reference's own bench sizes (benches/simple_benchmark.rs:58-102), GPU vs CPU port
+    import time
+    import oracle as ko
+    cpu_rows = []
+    cores = os.cpu_count() or 1
+    for logn in (8, 12, 15, 24):
+        nb = 1 << logn
+        host = ko.generate_bases(1, 0, nb)
+        t0 = time.perf_counter(); reps = max(1, (1 << 22) // nb)
+        for _ in range(reps):
+            r = ko.bench_windows(host, K, n_reads=1, fixed_len=nb, materialize=False)
+        cpu_faithful = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r2 = ko.extract_canonical(host, K, n_reads=1, fixed_len=nb, materialize=False)
+        cpu_iter = (time.perf_counter() - t0) / reps
+        b = ctx.upload(host, fixed_len=nb)
+        o = kb.CanonicalKmers(k=K, n_slots=nb - K + 1, canon=i64(nb - K + 1), hash=i64(nb - K + 1))
+        avg, best = time_ms(stream, lambda: b.extract_canonical(K, out=o), reps=20)
+        d = b.extract_canonical(K, out=o, digest=True).digest
+        assert d == (r2["n_valid"], r2["checksum_canon"], r2["checksum_hash"]) and r["checksum_canon"] == r2["checksum_canon"]
+        cpu_rows.append({"config": f"config1 2^{logn} random ACGT bytes, K=31", "kmers": nb - K + 1,
+                         "cpu_bench_faithful_1thread_ms": cpu_faithful * 1e3, "cpu_iterator_1thread_ms": cpu_iter * 1e3,
+                         "gpu_kernel_ms": avg, "note": "GPU time is launch-latency-bound below ~2^20 bytes"})
+        print(f"config1 2^{logn:<2d} B: cpu bench-faithful {cpu_faithful * 1e3:9.4f} ms, cpu iterator {cpu_iter * 1e3:9.4f} ms, gpu {avg:7.4f} ms", flush=True)
+    # CPU port on bounded samples of configs 2-5 (all cores), same synthetic bytes
+    def cpu_time(fn, reps=2):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+    ns = 2_000_000 // scale
+    hb = ko.generate_bases(42, 0, ns * 150)
+    c_out, h_out = np.zeros(ns * 120, dtype=np.uint64), np.zeros(ns * 120, dtype=np.uint64)
+    t = cpu_time(lambda: ko.extract_canonical(hb, 31, n_reads=ns, fixed_len=150, n_threads=cores, canon_out=c_out, hash_out=h_out))
+    cpu_rows.append({"config": "config2 sample (2M reads) iterator + canonical + LexHash, materialised", "cores": cores, "kmers_per_s": ns * 120 / t})
+    t = cpu_time(lambda: ko.bench_windows(hb, 31, n_reads=ns, fixed_len=150, n_threads=cores, materialize=False))
+    cpu_rows.append({"config": "config2 sample (2M reads) bench-faithful per-window O(K) re-encode", "cores": cores, "kmers_per_s": ns * 120 / t})
+    n3 = 20_000 // scale
+    t = cpu_time(lambda: ko.extract_canonical_wide(hb[:n3 * 150], 63, n_reads=n3, fixed_len=150, want_hash=False), reps=1)
+    cpu_rows.append({"config": "config3 sample (20k reads) K=63 encode + swap-loop rev_comp per window (1 thread)", "cores": 1, "kmers_per_s": n3 * 88 / t})
+    n4 = 20_000 // scale
+    hb4 = ko.generate_bases(43, 0, n4 * 10_000, 1049)
+    t = cpu_time(lambda: ko.extract_canonical(hb4, 31, n_reads=n4, fixed_len=10_000, n_threads=cores, materialize=False))
+    cpu_rows.append({"config": "config4 sample (20k x 10 kbp) iterator, digest only", "cores": cores, "kmers_per_s": n4 * 9970 / t})
+    g5 = 200_000_000 // scale
+    hb5 = ko.generate_bases(44, 0, g5, 105)
+    t = cpu_time(lambda: ko.extract_canonical(hb5, 31, n_reads=1000, fixed_len=g5 // 1000, n_threads=cores, materialize=False, hist_bits=16), reps=1)
+    cpu_rows.append({"config": "config5 sample (200 Mbp as 1000 chunks) iterator + 2^16-bin histogram", "cores": cores, "kmers_per_s": (g5 - 30 * 1000) / t})
+    for r in cpu_rows[4:]:
+        print(f"CPU {r['config']:90s} {r['kmers_per_s'] / 1e6:10.1f} M kmers/s on {r['cores']} core(s)", flush=True)
+
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump({"hbm_peak_gbs": pk, "rows": rows}, open(args.out, "w"), indent=1)
+    json.dump({"hbm_peak_gbs": pk, "host_cores": cores, "rows": rows, "cpu_rows": cpu_rows}, open(args.out, "w"), indent=1)
     ctx.close()
 
 

@@ -374,3 +374,71 @@ def test_word_ops_on_device_tensors(ctx, ko):
     assert rc.is_cuda
     back = ctx.reverse_complement_words(rc, 31)
     assert torch.equal(back, words)
+
+
+# ------------------------------------------------------------------ ragged-path corner cases (slot-space CSR geometry)
+def test_ragged_window_less_stretch_forces_multiple_passes(ctx, ko):
+    """A CTA's slots separated by > one tile (36.8 K bases) of reads too short to hold a window."""
+    rng = np.random.default_rng(2024)
+    k = 31
+    lens = np.concatenate([np.full(40, 200), np.full(4000, 20), np.full(40, 200), np.full(3000, 30), np.full(10, 77)])
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(offs[-1]))].copy()
+    bases[rng.integers(0, bases.size, size=200)] = ord("N")
+    res = ctx.upload(bases, offsets=offs).extract_canonical(k, want_fw_rc=True, digest=True)
+    _check_extract(res, ko.extract_canonical(bases, k, offsets=offs, want_fw_rc=True), fwrc=True)
+
+
+def test_ragged_many_tiny_reads_uncached_tables(ctx, ko):
+    """More reads per CTA than the shared-memory offset cache holds (1024): W_r in {0,1,2,3}."""
+    rng = np.random.default_rng(77)
+    k = 31
+    lens = rng.integers(29, 34, size=30000)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    bases = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, size=int(offs[-1]))].copy()
+    bases[rng.integers(0, bases.size, size=500)] = ord("N")
+    res = ctx.upload(bases, offsets=offs).extract_canonical(k, digest=True)
+    _check_extract(res, ko.extract_canonical(bases, k, offsets=offs))
+    w = ctx.upload(bases, offsets=offs).extract_canonical_wide(k, digest=True)
+    assert np.array_equal(w.host("canon")[:, 0], res.host("canon"))
+
+
+@pytest.mark.parametrize("L,k", [(32, 31), (33, 31), (37, 31), (9, 5), (70, 63), (66, 63)])
+def test_fixed_reads_with_fewer_than_eight_windows(ctx, ko, L, k):
+    """W < 8: one work item covers several reads (window-by-window path), narrow and wide engines."""
+    rng = np.random.default_rng(L * 7 + k)
+    n = 5000
+    bases, _ = random_reads(rng, n, L, L, p_bad=0.01)
+    if k <= 32:
+        res = ctx.upload(bases, fixed_len=L).extract_canonical(k, digest=True)
+        _check_extract(res, ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, n_threads=4))
+    w = ctx.upload(bases, fixed_len=L).extract_canonical_wide(k, digest=True)
+    ref = ko.extract_canonical_wide(bases[:300 * L], k, n_reads=300, fixed_len=L)
+    assert np.array_equal(w.host("canon")[:ref["canon"].shape[0]], ref["canon"])
+    assert np.array_equal(w.host("hash")[:ref["hash"].shape[0]], ref["hash"])
+
+
+def test_straddling_items_with_invalid_bases(ctx, ko):
+    """W = 130 (not a multiple of 8): every 16th item straddles a read boundary; N's at read edges."""
+    rng = np.random.default_rng(5)
+    n, L, k = 4000, 150, 21
+    bases, _ = random_reads(rng, n, L, L, p_bad=0.0)
+    b2 = bases.reshape(n, L)
+    b2[::3, :2] = ord("N")
+    b2[1::3, -3:] = ord("n")
+    b2[2::7, 70] = ord("-")
+    res = ctx.upload(bases, fixed_len=L).extract_canonical(k, want_fw_rc=True, digest=True)
+    _check_extract(res, ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, want_fw_rc=True, n_threads=4), fwrc=True)
+
+
+def test_pack_tiled_kernel_lengths(ctx, ko):
+    """Tiled pack kernel (regions that are whole 32-bit groups) across read lengths incl. L < 16 and padding-only groups."""
+    import kmers_b200 as kb
+    rng = np.random.default_rng(31)
+    for L, wb in [(150, 64), (31, 64), (1, 32), (16, 32), (17, 32), (100, 128), (5, 128), (1000, 64), (40000, 64)]:
+        n = max(2, 20000 // L)
+        bases, _ = random_reads(rng, n, L, L, p_bad=0.05)
+        img, _ = ctx.upload(bases, fixed_len=L).pack(int(kb.Naive.TGCA), wb)
+        nw = kb.word_for_k(wb, L)
+        want = np.concatenate([ko.encode(ko.NAIVE["TGCA"], bases[r * L:(r + 1) * L].tobytes(), wb, nw) for r in range(n)])
+        assert np.array_equal(img, want), (L, wb)
