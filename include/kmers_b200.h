@@ -140,6 +140,17 @@ int32_t kmb_extract_canonical(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t
                               uint64_t *hash_out, uint64_t *fw_out, uint64_t *rc_out,
                               kmb_digest *digest);
 
+/* Compacted, iterator-identical form: exactly the sequence of CanonicalKmerPos{km, pos}
+ * (canonical_kmer_iterator.rs:13-16) that `while !it.exhausted() { it.get(); it.inc(); }` yields for
+ * every read, reads back to back in batch order:
+ *   pos_out[i] = pos (i32, as the reference), canon_out[i], hash_out[i] as in kmb_extract_canonical,
+ *   emit_offsets_out[r] = index of read r's first entry (n_reads + 1 entries; [n_reads] = total).
+ * *n_emitted receives the number of emitted k-mers.  Call once with every output pointer NULL to
+ * size the arrays, then with arrays of `capacity` >= *n_emitted entries.  Outputs may be host or
+ * device memory; any of them may be NULL.  Synchronous. */
+int32_t kmb_extract_compact(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t *canon_out, uint64_t *hash_out,
+                            int32_t *pos_out, uint64_t *emit_offsets_out, uint64_t capacity, uint64_t *n_emitted);
+
 /* EXTENSION (not defined by the reference, parity unpinned): 1 <= k <= 64,
  * two u64 words per slot (canon_out[2*slot], [2*slot+1]; word 1 most
  * significant), any encoding.  Built from Encoding::encode + rev_comp::<K>

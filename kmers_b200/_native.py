@@ -64,6 +64,7 @@ SIGNATURES = {
     "kmb_batch_num_slots": (_i32, [_vp, _u32, _pu64]),
     "kmb_batch_window_offsets": (_i32, [_vp, _u32, _vp]),
     "kmb_extract_canonical": (_i32, [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _pd]),
+    "kmb_extract_compact": (_i32, [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _pu64]),
     "kmb_extract_canonical_wide": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _pd]),
     "kmb_histogram": (_i32, [_vp, _u32, _u32, _u32, _vp, _i32, _pd]),
     "kmb_extract_canonical_host": (_i32, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _pd]),

@@ -278,6 +278,26 @@ class ReadBatch:
         out.digest = d.astuple() if digest else None
         return out
 
+    def extract_compact(self, k: int, *, validate: bool = True, to: str = "host"):
+        """Iterator-identical output (kmb_extract_compact): only the k-mers CanonicalKmerIterator emits, in order.
+        Returns dict(pos int32, canon, hash, emit_offsets (n_reads + 1), n)."""
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        n = C.c_uint64()
+        self.ctx._ck(self.ctx._lib.kmb_extract_compact(self.ctx._h, k, flags, None, None, None, None, 0, C.byref(n)))
+        m = int(n.value)
+        if to == "device":
+            t = _torch()
+            canon, hsh = t.empty(m, dtype=t.int64, device="cuda"), t.empty(m, dtype=t.int64, device="cuda")
+            pos = t.empty(m, dtype=t.int32, device="cuda")
+            offs = t.empty(self.n_reads + 1, dtype=t.int64, device="cuda")
+        else:
+            canon, hsh = np.empty(m, dtype=np.uint64), np.empty(m, dtype=np.uint64)
+            pos = np.empty(m, dtype=np.int32)
+            offs = np.empty(self.n_reads + 1, dtype=np.uint64)
+        self.ctx._ck(self.ctx._lib.kmb_extract_compact(self.ctx._h, k, flags, _ptr(canon), _ptr(hsh), _ptr(pos), _ptr(offs), m,
+                                                       C.byref(n)))
+        return dict(pos=pos, canon=canon, hash=hsh, emit_offsets=offs, n=int(n.value))
+
     def extract_canonical_wide(self, k: int, enc: int = nv.ENC_ACGT, *, want_hash: bool = True, digest: bool = False,
                                validate: bool = True, to: str = "device") -> CanonicalKmers:
         """EXTENSION: 1 <= k <= 64, two u64 words per slot (kmb_extract_canonical_wide)."""

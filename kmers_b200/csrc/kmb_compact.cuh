@@ -1,0 +1,162 @@
+// kmb_compact.cuh -- iterator-identical (compacted) output for K <= 32.
+//
+// CanonicalKmerIterator yields CanonicalKmerPos{km, pos} only for the windows that hold no invalid
+// base, in increasing pos (naive_impl/canonical_kmer_iterator.rs:13-16, 42-70).  This engine writes
+// exactly that sequence for every read of the batch, back to back in read order:
+//   pos_out[i]   = pos (i32, as the reference)         canon_out[i] = get_canonical_word()
+//   hash_out[i]  = hash_one(LexHasherState(k), canon)  emit_offsets[r] = index of read r's first entry
+// Two launches of the same geometry: COUNT_ONLY counts the valid windows of every CTA (reads the bases
+// only); after an exclusive scan of the CTA counts the emit launch re-derives the per-item offsets with a
+// CTA-wide scan and stores each valid window at its final index.
+#pragma once
+#include "kmb_extract.cuh"
+
+namespace kmb {
+
+struct CompactOut {
+    uint64_t* canon;
+    uint64_t* hash;
+    int32_t* pos;
+    uint64_t* emit_offsets;              // n_reads + 1 (entry n_reads is written by the host)
+    unsigned long long* cta_counts;      // COUNT_ONLY: valid windows per CTA (out); emit: exclusive scan of them (in)
+};
+
+struct CompactParams {
+    WinConst wc;
+    CompactOut out;
+};
+
+template <bool VALIDATE, bool KHI, bool COUNT_ONLY>
+struct CompactEng {
+    using Params = CompactParams;
+    using Span = kmb::Span;
+    static constexpr bool kValidate = VALIDATE;
+    static constexpr bool kTwoPhase = true, kCountOnly = COUNT_ONLY;
+    static constexpr int kSpanEntries = 4;
+    const CompactParams& p;
+    uint32_t* cnt;           // shared: kItemsPerCta + 1 counts -> exclusive offsets after scan()
+    uint32_t* warp_tot;      // shared: per-warp totals of the scan
+    uint64_t pass_base = 0;      // valid windows of this CTA's passes so far
+    uint64_t cur_pass_base = 0;  // ... before the current pass
+    uint64_t cta_base = 0;       // valid windows of all earlier CTAs
+
+    __device__ CompactEng(const CompactParams& params, uint32_t* s_cnt, uint32_t* s_warp) : p(params), cnt(s_cnt), warp_tot(s_warp) {
+        if (!COUNT_ONLY) cta_base = p.out.cta_counts[blockIdx.x];
+    }
+    __device__ __forceinline__ uint32_t K() const { return p.wc.K; }
+    __device__ __forceinline__ Span load(const uint2* tile, uint32_t rel) const { return load_span<VALIDATE>(tile, rel, p.wc); }
+    __device__ __forceinline__ bool dirty(const Span& s) const { return s.inv != 0ull; }
+
+    __device__ __forceinline__ void begin_pass(uint32_t n_items) {
+        for (uint32_t i = threadIdx.x; i <= n_items; i += blockDim.x) cnt[i] = 0;
+    }
+    __device__ __forceinline__ void count(uint32_t li, uint32_t c) { cnt[li] += c; }  // one thread owns item li
+
+    // exclusive scan of cnt[0 .. n_items) in place; cnt[n_items] = total.  Called by all threads between barriers.
+    __device__ __forceinline__ void scan(uint32_t n_items) {
+        constexpr int PER = (kItemsPerCta + kExtractThreads - 1) / kExtractThreads;  // consecutive items per thread
+        const uint32_t base = threadIdx.x * PER;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { v[i] = (base + i < n_items) ? cnt[base + i] : 0u; sum += v[i]; }
+        uint32_t incl = sum;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < kExtractThreads / 32; ++w) { const uint32_t t = warp_tot[w]; if (w < warp) before += t; total += t; }
+        uint32_t run = before + incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { if (base + i < n_items) cnt[base + i] = run; run += v[i]; }
+        __syncthreads();  // warp_tot / cnt are re-used by the next pass
+        if (threadIdx.x == 0) cnt[n_items] = total;
+        const uint64_t prev = pass_base;
+        pass_base += total;
+        cur_pass_base = prev;
+    }
+    __device__ __forceinline__ void put(uint64_t o, const Window& w, uint64_t pos) const {
+        if (p.out.canon) p.out.canon[o] = w.canon;
+        if (p.out.hash) p.out.hash[o] = w.hash;
+        if (p.out.pos) p.out.pos[o] = (int32_t)pos;
+    }
+
+    template <bool TWO, bool CHECK>
+    __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+        uint64_t o = cta_base + cur_pass_base + cnt[ic.li];
+        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o;  // this item opens read r_a
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) {
+            if ((uint32_t)j < nwin) {
+                const bool second = TWO && (uint32_t)j >= n_first;
+                if (TWO && (uint32_t)j == n_first && p.out.emit_offsets) p.out.emit_offsets[ic.r_b] = o;  // opens read r_b
+                const Span s = second ? b : a;
+                const bool ok = !CHECK || (((uint32_t)(s.inv >> j)) & p.wc.kmask) == 0u;
+                if (ok) {
+                    put(o, make_window<KHI>(s, j, p.wc), second ? (uint64_t)(j - n_first) : ic.pos_a + j);
+                    ++o;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t, const ItemCtx& ic) {
+        // windows of one item arrive in order; the running index lives in cnt[li] (owned by this thread)
+        const uint64_t o = cta_base + cur_pass_base + cnt[ic.li];
+        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o;
+        const Span s = load_span<VALIDATE>(tile, rel, p.wc);
+        const bool ok = !VALIDATE || (((uint32_t)s.inv) & p.wc.kmask) == 0u;
+        if (ok) {
+            put(o, make_window<KHI>(s, 0, p.wc), ic.pos_a);
+            cnt[ic.li] += 1;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (COUNT_ONLY && threadIdx.x == 0) p.out.cta_counts[blockIdx.x] = pass_base;
+    }
+};
+
+template <class Eng>
+__global__ void __launch_bounds__(kExtractThreads) compact_fixed_kernel(const FixedGeom g, const EncDesc enc, const CompactParams ep) {
+    extern __shared__ uint2 tile[];
+    __shared__ uint32_t s_cnt[kItemsPerCta + 1];
+    __shared__ uint32_t s_warp[kExtractThreads / 32];
+    Eng eng(ep, s_cnt, s_warp);
+    fixed_body(g, enc, eng, tile);
+    eng.finish();
+}
+
+template <class Eng>
+__global__ void __launch_bounds__(kExtractThreads) compact_csr_kernel(const CsrGeom g, const EncDesc enc, const CompactParams ep) {
+    extern __shared__ uint2 tile[];
+    __shared__ uint32_t s_cnt[kItemsPerCta + 1];
+    __shared__ uint32_t s_warp[kExtractThreads / 32];
+    __shared__ CsrPass pass;
+    uint64_t* c_off = reinterpret_cast<uint64_t*>(tile + g.tile_entries);
+    uint64_t* c_win = c_off + (kCsrCache + 2);
+    Eng eng(ep, s_cnt, s_warp);
+    csr_body(g, enc, eng, tile, c_off, c_win, &pass);
+    eng.finish();
+}
+
+// Reads without a window (shorter than k) open no entry: their emit offset is that of the next read that has
+// windows (or the total).  win_offsets[r + 1] == win_offsets[r] identifies them.
+__global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_emitted,
+                                                               uint64_t* emit_offsets) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    if (win_offsets[r + 1] != win_offsets[r]) return;
+    // first read after r whose window offset exceeds win_offsets[r] - 1 ... i.e. first r' > r with windows
+    uint64_t lo = r + 1, hi = n_reads;  // answer in [lo, hi]; n_reads = none
+    const uint64_t v = win_offsets[r];
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (win_offsets[mid + 1] > v) hi = mid; else lo = mid + 1;
+    }
+    emit_offsets[r] = lo < n_reads ? emit_offsets[lo] : total_emitted;
+}
+
+}  // namespace kmb

@@ -222,6 +222,7 @@ struct NarrowEng {
     using Params = NarrowParams;
     using Span = kmb::Span;
     static constexpr bool kValidate = VALIDATE;
+    static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;  // tile entries one span reads
     const NarrowParams& p;
     Acc acc;
@@ -230,10 +231,10 @@ struct NarrowEng {
     __device__ __forceinline__ Span load(const uint2* tile, uint32_t rel) const { return load_span<VALIDATE>(tile, rel, p.wc); }
     __device__ __forceinline__ bool dirty(const Span& s) const { return s.inv != 0ull; }
     template <bool TWO, bool CHECK>
-    __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin) {
+    __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin, const ItemCtx&) {
         emit_run<TWO, CHECK, DIGEST, FWRC, MODE, KHI>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
     }
-    __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot) {
+    __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
         emit_single<VALIDATE, DIGEST, FWRC, MODE, KHI>(tile, rel, p.wc, p.out, slot, acc);
     }
     __device__ __forceinline__ void finish(unsigned long long (&red)[3][kExtractThreads / 32]) {

@@ -213,6 +213,7 @@ struct WideEng {
     using Params = WideParams;
     using Span = WideSpan<NW32>;
     static constexpr bool kValidate = VALIDATE;
+    static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = NW32 + 2;  // tile entries one span reads
     const WideParams& p;
     WideAcc acc;
@@ -221,10 +222,10 @@ struct WideEng {
     __device__ __forceinline__ Span load(const uint2* tile, uint32_t rel) const { return load_wide_span<NW32, VALIDATE>(tile, rel, p.wc); }
     __device__ __forceinline__ bool dirty(const Span& s) const { return (s.inv_lo | (uint64_t)s.inv_hi) != 0ull; }
     template <bool TWO, bool CHECK>
-    __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin) {
+    __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin, const ItemCtx&) {
         emit_wide_run<NW32, TWO, CHECK, DIGEST>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
     }
-    __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot) {
+    __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
         emit_wide_single<NW32, VALIDATE, DIGEST>(tile, rel, p.wc, p.out, slot, acc);
     }
     __device__ __forceinline__ void finish(unsigned long long (&red)[3][kExtractThreads / 32]) {

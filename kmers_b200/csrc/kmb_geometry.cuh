@@ -63,6 +63,38 @@ __device__ __forceinline__ void stage_tile(const uint8_t* bases, uint64_t n_byte
     }
 }
 
+// Where an item (or a single window) sits in the batch: handed to the engine with every call so that
+// engines producing per-read or position-bearing output (kmb_compact.cuh) know what they are emitting.
+struct ItemCtx {
+    uint32_t li;     // item index inside the CTA's current pass
+    uint64_t r_a;    // read of span A's windows
+    uint64_t pos_a;  // position inside read r_a of span A's window 0
+    uint64_t r_b;    // read of span B's windows (two-span items; they start at position 0 of r_b)
+};
+
+// Number of windows j in [j0, j1) starting at tile base rel + j whose K bases are all valid
+// (K <= 64, j1 <= kRun).  NE = tile entries that may be read (the engine's span size).
+template <int NE>
+__device__ __forceinline__ uint32_t count_valid_windows(const uint2* tile, uint32_t rel, uint32_t K, uint32_t j0, uint32_t j1) {
+    const uint32_t e = rel >> 4, o = rel & 15u;
+    uint32_t y[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < NE && i < 6; ++i) { y[i] = tile[e + i].y; any |= y[i]; }
+    if (any == 0u) return j1 - j0;
+    const uint64_t m0 = (uint64_t)y[0] | ((uint64_t)y[1] << 16) | ((uint64_t)y[2] << 32) | ((uint64_t)y[3] << 48);
+    const uint64_t m1 = (uint64_t)y[4] | ((uint64_t)y[5] << 16);
+    const uint64_t lo = o ? ((m0 >> o) | (m1 << (64 - o))) : m0;
+    const uint64_t hi = m1 >> o;
+    const uint64_t kmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
+    uint32_t n = 0;
+    for (uint32_t j = j0; j < j1; ++j) {
+        const uint64_t x = j ? ((lo >> j) | (hi << (64 - j))) : lo;
+        n += (x & kmask) == 0ull;
+    }
+    return n;
+}
+
 // ---------------------------------------------------------------------------
 // fixed-length reads
 // ---------------------------------------------------------------------------
@@ -84,6 +116,37 @@ __device__ __forceinline__ uint32_t div_w(uint32_t u, const FixedGeom& g, uint32
     if (g.W32 >= slots_per_cta) return (u >= g.W32) ? 1u : 0u;  // u < W + slots_per_cta <= 2W
     if (g.W32 == 1) return u;
     return __umulhi(u, g.w_magic);
+}
+
+// One pass over the items of a staged tile.  Two-phase engines (compaction) first count the valid
+// windows of every item, scan the counts CTA-wide, then emit at the scanned offsets.
+template <class Eng, class Visit>
+__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Visit&& visit) {
+    if constexpr (Eng::kTwoPhase) {
+        eng.begin_pass(n_items);
+        __syncthreads();
+        visit([&](uint32_t rel, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, nwin)); },
+              [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
+                                       count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin)); },
+              [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
+                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1)); });
+        __syncthreads();
+        eng.scan(n_items);
+        __syncthreads();
+        if (Eng::kCountOnly) return;
+    }
+    visit([&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+              const typename Eng::Span s = eng.load(tile, rel);
+              if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kRun, slot0, nwin, ic);
+              else eng.template run<false, false>(s, s, kRun, slot0, nwin, ic); },
+          [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+              const typename Eng::Span a = eng.load(tile, rel_a);
+              const typename Eng::Span b = eng.load(tile, rel_b);
+              if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
+              else eng.template run<true, false>(a, b, left, slot0, nwin, ic); },
+          [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); });
 }
 
 template <class Eng>
@@ -110,34 +173,33 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     stage_tile<Eng::kValidate>(g.bases, g.n_bytes, first - mis, n_entries, enc, tile);
     __syncthreads();
 
-    // ---- phase 2
+    // ---- phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than
+    //      kRun windows, a run of single windows
     const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-    for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
-        const uint32_t u = p_first + li * kRun;           // first slot, counted from window 0 of read r_first
-        const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
-        const uint32_t pos = u - q * g.W32;                 // window position inside its read
-        const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
-        const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
-        const uint32_t rel = q * g.L32 + pos - p_first + mis;  // first base, relative to tile entry 0
-        const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
-        if (left >= (uint32_t)kRun || left >= nwin) {
-            const typename Eng::Span s = eng.load(tile, rel);
-            if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kRun, slot0, nwin);
-            else eng.template run<false, false>(s, s, kRun, slot0, nwin);
-        } else if (g.W32 >= (uint32_t)kRun) {
-            // straddles exactly one boundary: windows j >= left start read q+1 at position j - left
-            const typename Eng::Span a = eng.load(tile, rel);
-            const typename Eng::Span b = eng.load(tile, (q + 1) * g.L32 - p_first + mis - left);
-            if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin);
-            else eng.template run<true, false>(a, b, left, slot0, nwin);
-        } else {
-            // reads with fewer than kRun windows: window by window
-            for (uint32_t j = 0; j < nwin; ++j) {
-                const uint32_t uj = u + j, qj = div_w(uj, g, slots_per_cta);
-                eng.single(tile, qj * g.L32 + (uj - qj * g.W32) - p_first + mis, slot0 + j);
+    auto visit = [&](auto&& one, auto&& two, auto&& single) {
+        for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
+            const uint32_t u = p_first + li * kRun;           // first slot, counted from window 0 of read r_first
+            const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
+            const uint32_t pos = u - q * g.W32;                 // window position inside its read
+            const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
+            const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+            const uint32_t rel = q * g.L32 + pos - p_first + mis;  // first base, relative to tile entry 0
+            const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
+            const ItemCtx ic{li, r_first + q, pos, r_first + q + 1};
+            if (left >= (uint32_t)kRun || left >= nwin) {
+                one(rel, slot0, nwin, ic);
+            } else if (g.W32 >= (uint32_t)kRun) {
+                // straddles exactly one boundary: windows j >= left start read q+1 at position j - left
+                two(rel, (q + 1) * g.L32 - p_first + mis - left, left, slot0, nwin, ic);
+            } else {
+                for (uint32_t j = 0; j < nwin; ++j) {
+                    const uint32_t uj = u + j, qj = div_w(uj, g, slots_per_cta), pj = uj - qj * g.W32;
+                    single(qj * g.L32 + pj - p_first + mis, slot0 + j, ItemCtx{li, r_first + qj, pj, 0});
+                }
             }
         }
-    }
+    };
+    run_pass(eng, tile, K, n_items, visit);
 }
 
 // ---------------------------------------------------------------------------
@@ -238,36 +300,34 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
 
         const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
         const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-        for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
-            const uint64_t slot0 = ps.slot_lo + (uint64_t)li * kRun;
-            const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
-            uint64_t r = last_le(win, ps.r_lo, ps.r_hi, slot0);
-            const uint64_t pos = slot0 - win[r];
-            const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
-            const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
-            if (left >= nwin) {
-                const typename Eng::Span s = eng.load(tile, rel);
-                if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kRun, slot0, nwin);
-                else eng.template run<false, false>(s, s, kRun, slot0, nwin);
-                continue;
+        auto visit = [&](auto&& one, auto&& two, auto&& single) {
+            for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
+                const uint64_t slot0 = ps.slot_lo + (uint64_t)li * kRun;
+                const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+                uint64_t r = last_le(win, ps.r_lo, ps.r_hi, slot0);
+                const uint64_t pos = slot0 - win[r];
+                const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
+                const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
+                if (left >= nwin) {
+                    one(rel, slot0, nwin, ItemCtx{li, r, pos, 0});
+                    continue;
+                }
+                uint64_t r2 = r + 1;
+                while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+                if (left + (win[r2 + 1] - win[r2]) >= nwin) {
+                    two(rel, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left, (uint32_t)left, slot0, nwin, ItemCtx{li, r, pos, r2});
+                    continue;
+                }
+                // several short reads inside one item: window by window
+                uint64_t p = pos, w_r = win[r + 1] - win[r];
+                for (uint32_t j = 0; j < nwin; ++j) {
+                    while (p >= w_r) { ++r; p = 0; w_r = win[r + 1] - win[r]; }
+                    single((uint32_t)(off[r] + p - ps.g0) + mis, slot0 + j, ItemCtx{li, r, p, 0});
+                    ++p;
+                }
             }
-            uint64_t r2 = r + 1;
-            while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
-            if (left + (win[r2 + 1] - win[r2]) >= nwin) {
-                const typename Eng::Span a = eng.load(tile, rel);
-                const typename Eng::Span b = eng.load(tile, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left);
-                if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, (uint32_t)left, slot0, nwin);
-                else eng.template run<true, false>(a, b, (uint32_t)left, slot0, nwin);
-                continue;
-            }
-            // several short reads inside one item: window by window
-            uint64_t p = pos, w_r = win[r + 1] - win[r];
-            for (uint32_t j = 0; j < nwin; ++j) {
-                while (p >= w_r) { ++r; p = 0; w_r = win[r + 1] - win[r]; }
-                eng.single(tile, (uint32_t)(off[r] + p - ps.g0) + mis, slot0 + j);
-                ++p;
-            }
-        }
+        };
+        run_pass(eng, tile, K, n_items, visit);
         __syncthreads();  // the next pass overwrites the tile
         cur = ps.slot_hi;
         r_cur = ps.r_hi;

@@ -14,6 +14,7 @@
 #include "kmb_encoding.cuh"
 #include "kmb_extract.cuh"
 #include "kmb_extract_wide.cuh"
+#include "kmb_compact.cuh"
 
 using namespace kmb;
 
@@ -45,6 +46,8 @@ struct kmb_ctx {
 
     uint64_t* d_first_read = nullptr;  // per-CTA first read of the CSR kernels
     size_t first_read_cap = 0;
+    unsigned long long* d_cta_counts = nullptr;  // compaction: valid windows per CTA / their scan
+    size_t cta_counts_cap = 0;
 
     // scratch
     unsigned long long* d_digest = nullptr;  // 3 words
@@ -166,6 +169,7 @@ extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
     cudaFree(ctx->own_offsets);
     cudaFree(ctx->d_win_offsets);
     cudaFree(ctx->d_first_read);
+    cudaFree(ctx->d_cta_counts);
     cudaFree(ctx->d_digest);
     cudaFreeHost(ctx->h_digest);
     for (auto& s : ctx->d_scratch) cudaFree(s);
@@ -681,6 +685,99 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
     if ((rc = out_finish(ctx, ob))) return rc;
     if (digest) return digest_end(ctx, digest);
     if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= compacted (iterator-identical) output
+template <bool COUNT_ONLY>
+static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
+                                  cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
+#define KMB_CASE(V, H)                                                                                                  \
+    if (validate == V && khi == H) {                                                                                    \
+        if (fg) compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, l.smem, st>>>(*fg, enc, ep); \
+        else compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, l.smem, st>>>(*cg, enc, ep);     \
+        return cudaGetLastError();                                                                                      \
+    }
+    KMB_CASE(true, true) KMB_CASE(true, false) KMB_CASE(false, true) KMB_CASE(false, false)
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
+}
+
+extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint64_t* canon_out, uint64_t* hash_out,
+                                       int32_t* pos_out, uint64_t* emit_offsets_out, uint64_t capacity, uint64_t* n_emitted) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    if (!n_emitted) return fail(ctx, KMB_ERR_INVALID_ARG, "n_emitted is NULL");
+    // the reference's pos is i32 (canonical_kmer_iterator.rs:15); longer reads cannot be represented
+    if (!ctx->d_offsets && ctx->fixed_len > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "reads above 2^31-1 bases: pos is i32");
+    *n_emitted = 0;
+    EncDesc enc;
+    make_enc(KMB_ENC_ACGT, &enc, nullptr);
+    const bool validate = !(flags & KMB_F_NO_VALIDATE), khi = k > 16, csr = ctx->d_offsets != nullptr;
+    uint64_t n_slots = 0;
+    int32_t rc = num_slots(ctx, k, &n_slots);
+    if (rc) return rc;
+    OutBuf oe;
+    if ((rc = out_prepare(ctx, 3, emit_offsets_out, (ctx->n_reads + 1) * 8, &oe))) return rc;
+    if (n_slots == 0) {
+        if (oe.dev) CK(ctx, cudaMemsetAsync(oe.dev, 0, (ctx->n_reads + 1) * 8, ctx->stream));
+        if ((rc = out_finish(ctx, oe))) return rc;
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        return KMB_OK;
+    }
+    FixedGeom fg{};
+    CsrGeom cg{};
+    Launch l;
+    if (!csr) {
+        if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l))
+            return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
+    } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
+        return rc;
+    }
+    const FixedGeom* pf = csr ? nullptr : &fg;
+    const CsrGeom* pc = csr ? &cg : nullptr;
+    if ((rc = grow(ctx, (void**)&ctx->d_cta_counts, &ctx->cta_counts_cap, ((size_t)l.grid + 1) * 8))) return rc;
+    CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 1) * 8, ctx->stream));
+    CompactParams ep{};
+    ep.wc = make_winconst(k, enc);
+    ep.out.cta_counts = ctx->d_cta_counts;
+    // launch 1: valid windows per CTA, then their exclusive scan (entry [grid] becomes the total)
+    CK(ctx, launch_compact<true>(validate, khi, pf, pc, l, ctx->stream, enc, ep));
+    ctx->launches++;
+    size_t need = 0;
+    CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
+    if ((rc = grow(ctx, &ctx->d_cub, &ctx->cub_cap, need))) return rc;
+    CK(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t total = ctx->h_digest[3];
+    *n_emitted = total;
+    if (!canon_out && !hash_out && !pos_out && !emit_offsets_out) return KMB_OK;  // counting call
+    if (total > capacity) return fail(ctx, KMB_ERR_INVALID_ARG, "capacity %llu < %llu emitted k-mers", (unsigned long long)capacity,
+                                      (unsigned long long)total);
+    OutBuf oc, oh, op;
+    if ((rc = out_prepare(ctx, 0, canon_out, total * 8, &oc))) return rc;
+    if ((rc = out_prepare(ctx, 1, hash_out, total * 8, &oh))) return rc;
+    if ((rc = out_prepare(ctx, 2, pos_out, total * 4, &op))) return rc;
+    ep.out.canon = (uint64_t*)oc.dev; ep.out.hash = (uint64_t*)oh.dev; ep.out.pos = (int32_t*)op.dev;
+    ep.out.emit_offsets = (uint64_t*)oe.dev;
+    // launch 2: emit at the scanned offsets
+    CK(ctx, launch_compact<false>(validate, khi, pf, pc, l, ctx->stream, enc, ep));
+    ctx->launches++;
+    if (oe.dev) {
+        CK(ctx, cudaMemcpyAsync((uint64_t*)oe.dev + ctx->n_reads, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (csr) {
+            compact_backfill_kernel<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_win_offsets, ctx->n_reads,
+                                                                                                   total, (uint64_t*)oe.dev);
+            CK(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+    if ((rc = out_finish(ctx, oc)) || (rc = out_finish(ctx, oh)) || (rc = out_finish(ctx, op)) || (rc = out_finish(ctx, oe))) return rc;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return KMB_OK;
 }
 

@@ -1,0 +1,127 @@
+"""Iterator-identical output (kmb_extract_compact): the exact (pos, canonical word, LexHash) sequence
+CanonicalKmerIterator yields (naive_impl/canonical_kmer_iterator.rs:13-16, 42-101), read after read."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from golden_util import load_goldens, random_reads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import kmers_b200 as kb
+    c = kb.Context(0)
+    yield c
+    c.close()
+
+
+def _reference_sequence(ko, bases, offs, k):
+    """while !it.exhausted() { it.get(); it.inc(); } over every read, with the restated iterator."""
+    L = ko.lib()
+    pos, canon, hsh, starts = [], [], [], [0]
+    for r in range(len(offs) - 1):
+        it = ko.Iter(bases[int(offs[r]):int(offs[r + 1])].tobytes(), k)
+        while not it.exhausted():
+            km = it.km
+            c = L.ko_ck_get_canonical_word(C.byref(km))
+            pos.append(it.pos)
+            canon.append(c)
+            hsh.append(L.ko_lexhash_word(c, k))
+            it.inc()
+        starts.append(len(pos))
+    return (np.array(pos, dtype=np.int32), np.array(canon, dtype=np.uint64), np.array(hsh, dtype=np.uint64),
+            np.array(starts, dtype=np.uint64))
+
+
+def _from_dense(ko, bases, k, offsets=None, n_reads=None, fixed_len=0):
+    ref = ko.extract_canonical(bases, k, offsets=offsets, n_reads=n_reads, fixed_len=fixed_len, n_threads=4)
+    if offsets is None:
+        w = max(0, fixed_len - k + 1)
+        woff = np.arange(n_reads + 1, dtype=np.int64) * w
+    else:
+        lens = np.diff(np.asarray(offsets).astype(np.int64))
+        woff = np.concatenate([[0], np.cumsum(np.maximum(0, lens - k + 1))])
+    ok = ref["canon"] != ko.SENTINEL
+    slots = np.flatnonzero(ok)
+    read_of = np.searchsorted(woff, slots, side="right") - 1
+    pos = (slots - woff[read_of]).astype(np.int32)
+    emit = np.concatenate([[0], np.cumsum(ok)])[woff].astype(np.uint64)
+    return pos, ref["canon"][ok], ref["hash"][ok], emit
+
+
+def _check(got, want):
+    pos, canon, hsh, emit = want
+    assert got["n"] == pos.size
+    assert np.array_equal(got["pos"], pos)
+    assert np.array_equal(got["canon"], canon)
+    assert np.array_equal(got["hash"], hsh)
+    assert np.array_equal(got["emit_offsets"], emit)
+
+
+def test_compact_reference_reads(ctx):
+    """The reference's own iterator test reads (canonical_kmer_iterator.rs:123-206), incl. the N cases."""
+    import oracle as ko
+    reads = [c["read"].encode() for c in load_goldens()["iterator"]["cases"]] + [b"ACGT" * 5, b"", b"N" * 40]
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    bases = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    got = ctx.upload(bases, offsets=offs).extract_compact(31)
+    _check(got, _reference_sequence(ko, bases, offs, 31))
+    # N at index 35 of the 5th read: positions 0..4 then 36.. (canonical_kmer_iterator.rs:178-189)
+    s, e = int(got["emit_offsets"][4]), int(got["emit_offsets"][5])
+    assert got["pos"][s:e].tolist() == [0, 1, 2, 3, 4] + list(range(36, 121 - 31 + 1))
+
+
+@pytest.mark.parametrize("k", [1, 5, 16, 17, 31, 32])
+def test_compact_ragged_vs_iterator(ctx, k):
+    import oracle as ko
+    rng = np.random.default_rng(40 + k)
+    bases, offs = random_reads(rng, 300, 0, 130, p_bad=0.03)
+    got = ctx.upload(bases, offsets=offs).extract_compact(k)
+    _check(got, _reference_sequence(ko, bases, offs, k))
+
+
+@pytest.mark.parametrize("L,k,p_bad", [(150, 31, 0.01), (150, 21, 0.02), (33, 31, 0.01), (31, 31, 0.0), (10007, 31, 0.002), (60, 31, 0.5)])
+def test_compact_fixed_vs_dense(ctx, L, k, p_bad):
+    import oracle as ko
+    rng = np.random.default_rng(L + k)
+    n = max(4, 300000 // L)
+    bases, _ = random_reads(rng, n, L, L, p_bad=p_bad)
+    got = ctx.upload(bases, fixed_len=L).extract_compact(k)
+    _check(got, _from_dense(ko, bases, k, n_reads=n, fixed_len=L))
+
+
+def test_compact_ragged_large_and_device_outputs(ctx):
+    import oracle as ko
+    rng = np.random.default_rng(99)
+    b1, o1 = random_reads(rng, 20000, 20, 300, p_bad=0.004)
+    b2, o2 = random_reads(rng, 3000, 0, 40, p_bad=0.0)       # a stretch of reads mostly too short for a window
+    b3, o3 = random_reads(rng, 5, 20000, 50000, p_bad=0.001)
+    bases = np.concatenate([b1, b2, b3])
+    offs = np.concatenate([o1, o2[1:] + o1[-1], o3[1:] + o1[-1] + o2[-1]])
+    want = _from_dense(ko, bases, 31, offsets=offs)
+    host = ctx.upload(bases, offsets=offs).extract_compact(31, to="host")
+    _check(host, want)
+    dev = ctx.upload(bases, offsets=offs).extract_compact(31, to="device")
+    assert np.array_equal(dev["canon"].cpu().numpy().view(np.uint64), want[1])
+    assert np.array_equal(dev["pos"].cpu().numpy(), want[0])
+    assert np.array_equal(dev["emit_offsets"].cpu().numpy().view(np.uint64), want[3])
+
+
+def test_compact_capacity_and_empty(ctx):
+    import kmers_b200 as kb
+    n = C.c_uint64()
+    b = ctx.upload(b"ACGTACGTAC" * 10, fixed_len=100)
+    lib, h = ctx._lib, ctx._h
+    assert lib.kmb_extract_compact(h, 31, 0, None, None, None, None, 0, C.byref(n)) == 0 and n.value == 70
+    buf = np.zeros(10, dtype=np.uint64)
+    assert lib.kmb_extract_compact(h, 31, 0, buf.ctypes.data, None, None, None, 10, C.byref(n)) == kb._native.ERR_INVALID_ARG
+    assert n.value == 70  # the count is still reported so the caller can re-allocate
+    got = ctx.upload(b"NNNN" * 20, fixed_len=80).extract_compact(31)
+    assert got["n"] == 0 and got["emit_offsets"].tolist() == [0, 0]
+    got = ctx.upload(b"ACGT" * 5, fixed_len=20).extract_compact(31)  # reads shorter than k
+    assert got["n"] == 0 and got["emit_offsets"].tolist() == [0, 0]
+    with pytest.raises(kb.KmbPanic):
+        b.extract_compact(33)
