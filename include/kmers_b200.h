@@ -175,6 +175,20 @@ int32_t kmb_extract_canonical_host(kmb_ctx *ctx, const uint8_t *host_bases, uint
                                    uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t *host_canon,
                                    uint64_t *host_hash, kmb_digest *digest);
 
+/* ---- "next" row N1: minimizers ------------------------------------------ */
+/* One (lmer, pos) per k-mer window of every read, dense slots as kmb_extract_canonical: the LEFTMOST w-mer of
+ * minimum hash_one(&LexHasherState::new(hash_k), lmer) inside the k-mer -- the sequence SeqVecMinimizerIter yields
+ * (naive_impl/seq_vector/minimizers.rs:38-142; ties keep the older entry, :72-78).  mmer_out[slot] = the lmer word
+ * (forward strand, SeqVector::get_kmer_u64, seq_vector.rs:96-99), pos_out[slot] = its position inside the read.
+ * EXTENSION: a SeqVector cannot hold non-ACGT bases; windows holding one get KMB_SENTINEL / UINT32_MAX.
+ * 1 <= w <= k <= 32, 1 <= hash_k <= 32. */
+int32_t kmb_minimizers(kmb_ctx *ctx, uint32_t k, uint32_t w, uint32_t hash_k, uint32_t flags, uint64_t *mmer_out,
+                       uint32_t *pos_out);
+/* Kmer::minimizer_word (naive_impl/kmer.rs:170-191) with LexHasherState(hash_k) on n k-mer words:
+ * mmer_out[i] = leftmost width-mer of minimum hash, offset_out[i] = its offset inside the k-mer. */
+int32_t kmb_minimizer_words(kmb_ctx *ctx, uint32_t k, uint32_t w, uint32_t hash_k, const uint64_t *words, uint64_t n,
+                            uint64_t *mmer_out, uint32_t *offset_out);
+
 /* ---- batched Encoding<P,B> (encoding/mod.rs:14-23) --------------------- */
 /* Encoding::encode of every read of the batch (encoding/naive.rs:116-124,
  * xor10.rs:52-60): read r becomes ceil(L_r / (word_bits/2)) words of

@@ -68,6 +68,8 @@ SIGNATURES = {
     "kmb_extract_canonical_wide": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _pd]),
     "kmb_histogram": (_i32, [_vp, _u32, _u32, _u32, _vp, _i32, _pd]),
     "kmb_extract_canonical_host": (_i32, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _pd]),
+    "kmb_minimizers": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "kmb_minimizer_words": (_i32, [_vp, _u32, _u32, _u32, _vp, _u64, _vp, _vp]),
     "kmb_pack": (_i32, [_vp, _i32, _u32, _vp, _vp]),
     "kmb_pack_num_words": (_i32, [_vp, _u32, _pu64]),
     "kmb_unpack": (_i32, [_vp, _i32, _u32, _vp, _u64, _u32, _u32, _vp]),

@@ -205,6 +205,20 @@ class Context:
         self.sync()
         return out
 
+    def minimizer_words(self, words, k: int, w: int, hash_k=None, to=None):
+        """Kmer::minimizer_word (naive_impl/kmer.rs:170-191) with LexHasherState(hash_k) on every word -> (mmer, offset)."""
+        hash_k = w if hash_k is None else hash_k
+        n, wd, to = self._words_in(words, to)
+        mm = self._alloc(n, to, np.uint64)
+        if to == "device":
+            t = _torch()
+            off = t.empty(n, dtype=t.int32, device="cuda")
+        else:
+            off = np.empty(n, dtype=np.uint32)
+        self._ck(self._lib.kmb_minimizer_words(self._h, k, w, hash_k, _ptr(wd), n, _ptr(mm), _ptr(off)))
+        self.sync()
+        return mm, off
+
     # ---- batched Encoding::decode / rev_comp on arrays [P; B]
     def unpack(self, enc: int, word_bits: int, words: np.ndarray, n_items: int, words_per_item: int,
                bases_per_item: Optional[int] = None) -> np.ndarray:
@@ -277,6 +291,21 @@ class ReadBatch:
                                                          _ptr(out.fw), _ptr(out.rc), C.byref(d) if digest else None))
         out.digest = d.astuple() if digest else None
         return out
+
+    def minimizers(self, k: int, w: int, hash_k=None, *, validate: bool = True, to: str = "host"):
+        """SeqVecMinimizerIter in batch (kmb_minimizers): (lmer word, position in read) of the leftmost minimum-LexHash
+        w-mer of every k-mer window; dense slots.  Returns (mmer u64, pos u32)."""
+        hash_k = w if hash_k is None else hash_k
+        n = self.num_slots(k)
+        if to == "device":
+            t = _torch()
+            mm, pos = t.empty(n, dtype=t.int64, device="cuda"), t.empty(n, dtype=t.int32, device="cuda")
+        else:
+            mm, pos = np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.uint32)
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._ck(self.ctx._lib.kmb_minimizers(self.ctx._h, k, w, hash_k, flags, _ptr(mm), _ptr(pos)))
+        self.ctx.sync()
+        return mm, pos
 
     def extract_compact(self, k: int, *, validate: bool = True, to: str = "host"):
         """Iterator-identical output (kmb_extract_compact): only the k-mers CanonicalKmerIterator emits, in order.

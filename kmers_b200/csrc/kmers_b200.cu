@@ -15,6 +15,7 @@
 #include "kmb_extract.cuh"
 #include "kmb_extract_wide.cuh"
 #include "kmb_compact.cuh"
+#include "kmb_minimizer.cuh"
 
 using namespace kmb;
 
@@ -778,6 +779,82 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     }
     if ((rc = out_finish(ctx, oc)) || (rc = out_finish(ctx, oh)) || (rc = out_finish(ctx, op)) || (rc = out_finish(ctx, oe))) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+static int32_t in_prepare(kmb_ctx* ctx, int slot, const void* user, size_t bytes, const void** dev);
+
+// ======================================================================= minimizers ("next" row N1)
+extern "C" int32_t kmb_minimizers(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t hash_k, uint32_t flags, uint64_t* mmer_out,
+                                  uint32_t* pos_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    // get_kmer_u64 reads at most 64 bits (seq_vector.rs:96-99); k - w underflows for w > k (minimizers.rs:104); LexHasher
+    // shifts by (32 - hash_k) * 2 (hash.rs:69)
+    if (k < 1 || k > 32 || w < 1 || w > k || hash_k < 1 || hash_k > 32)
+        return fail(ctx, KMB_ERR_PANIC, "need 1 <= w <= k <= 32 and 1 <= hash_k <= 32 (k=%u w=%u hash_k=%u)", k, w, hash_k);
+    EncDesc enc;
+    make_enc(KMB_ENC_ACGT, &enc, nullptr);
+    uint64_t n_slots = 0;
+    int32_t rc = num_slots(ctx, k, &n_slots);
+    if (rc) return rc;
+    OutBuf om, op;
+    if ((rc = out_prepare(ctx, 0, mmer_out, n_slots * 8, &om))) return rc;
+    if ((rc = out_prepare(ctx, 1, pos_out, n_slots * 4, &op))) return rc;
+    if (n_slots) {
+        MinParams ep{};
+        ep.mc.wc = make_winconst(k, enc);
+        ep.mc.w = w; ep.mc.m = k - w + 1; ep.mc.hshift = hash_k < w ? 2 * (w - hash_k) : 0;
+        ep.mc.wmask = w >= 32 ? ~0ull : ((1ull << (2 * w)) - 1ull);
+        const unsigned __int128 c96 = ((unsigned __int128)enc.cmask) | ((unsigned __int128)enc.cmask << 32) | ((unsigned __int128)enc.cmask << 64);
+        const unsigned __int128 vm = c96 >> ep.mc.wc.shiftD;
+        ep.mc.vm0 = (uint32_t)vm; ep.mc.vm1 = (uint32_t)(vm >> 32); ep.mc.vm2 = (uint32_t)(vm >> 64);
+        ep.out.mmer = (uint64_t*)om.dev; ep.out.pos = (uint32_t*)op.dev;
+        ep.out.vec_ok = ((((uintptr_t)om.dev | (uintptr_t)op.dev) & 31u) == 0) ? 1u : 0u;
+        FixedGeom fg{};
+        CsrGeom cg{};
+        Launch l;
+        const bool csr = ctx->d_offsets != nullptr, validate = !(flags & KMB_F_NO_VALIDATE);
+        if (!csr) {
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l))
+                return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
+        } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
+            return rc;
+        }
+        cudaError_t e = validate ? launch_eng<MinimizerEng<true>>(csr ? nullptr : &fg, csr ? &cg : nullptr, l, ctx->stream, enc, ep)
+                                 : launch_eng<MinimizerEng<false>>(csr ? nullptr : &fg, csr ? &cg : nullptr, l, ctx->stream, enc, ep);
+        CK(ctx, e);
+        ctx->launches++;
+    }
+    if ((rc = out_finish(ctx, om)) || (rc = out_finish(ctx, op))) return rc;
+    if (om.host || op.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_minimizer_words(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t hash_k, const uint64_t* words, uint64_t n,
+                                       uint64_t* mmer_out, uint32_t* offset_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    // sub_kmer_word asserts pos + width <= k (kmer.rs:155-157); LexHasher shift (hash.rs:69)
+    if (k < 1 || k > 32 || w < 1 || w > k || hash_k < 1 || hash_k > 32)
+        return fail(ctx, KMB_ERR_PANIC, "need 1 <= w <= k <= 32 and 1 <= hash_k <= 32 (k=%u w=%u hash_k=%u)", k, w, hash_k);
+    if (n == 0) return KMB_OK;
+    if (!words) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL input");
+    const void* d_in;
+    int32_t rc = in_prepare(ctx, 2, words, n * 8, &d_in);
+    if (rc) return rc;
+    OutBuf om, oo;
+    if ((rc = out_prepare(ctx, 0, mmer_out, n * 8, &om))) return rc;
+    if ((rc = out_prepare(ctx, 1, offset_out, n * 4, &oo))) return rc;
+    const uint64_t ctas = (n + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    minimizer_words_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint64_t*)d_in, n, k, w, hash_k, (uint64_t*)om.dev,
+                                                                   (uint32_t*)oo.dev);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, om)) || (rc = out_finish(ctx, oo))) return rc;
+    if (om.host || oo.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
     return KMB_OK;
 }
 

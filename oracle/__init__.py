@@ -137,6 +137,11 @@ def lib() -> C.CDLL:
     sig("ko_extract_canonical", i32, vp, vp, sz, u64, u32, i32, vp, vp, vp, vp, vp, u32, P(Digest), i32)
     sig("ko_bench_windows", i32, vp, vp, sz, u64, u32, vp, vp, P(Digest), i32)
     sig("ko_extract_canonical_wide", i32, vp, vp, sz, u64, u32, i32, i32, vp, vp, P(Digest))
+    sig("ko_minimizer_word", i32, u64, sz, sz, u32, i32, P(u64), P(sz))
+    sig("ko_sv_from_bytes", i32, vp, sz, vp)
+    sig("ko_sv_get_kmer_u64", i32, vp, sz, sz, sz, P(u64))
+    sig("ko_sv_minimizers", i32, vp, sz, sz, sz, u32, vp, vp)
+    sig("ko_minimizers_batch", i32, vp, vp, sz, u64, u32, u32, u32, vp, vp)
     _lib = L
     return L
 
@@ -318,3 +323,51 @@ def extract_canonical_wide(bases: np.ndarray, k: int, *, enc=NAIVE["ACGT"], vali
     return dict(canon=canon.reshape(-1, 2), hash=hsh.reshape(-1, 2) if want_hash else None,
                 n_valid=d.n_valid, checksum_canon=d.checksum_canon, checksum_hash=d.checksum_hash,
                 n_slots=n_slots)
+
+
+# ---- "next" rows: minimizers + SeqVector -------------------------------------------------------------
+def minimizer_word(word: int, k: int, width: int, hash_k: int, strict: bool = False):
+    """Kmer::minimizer_word with LexHasherState(hash_k) -> (mmer word, offset)."""
+    m, o = C.c_uint64(), C.c_size_t()
+    if lib().ko_minimizer_word(word, k, width, hash_k, int(strict), C.byref(m), C.byref(o)) != OK:
+        raise RuntimeError("panic: minimizer_word")
+    return int(m.value), int(o.value)
+
+
+def sv_from_bytes(seq: bytes) -> np.ndarray:
+    """SeqVector::from(&[u8]) -> its u64 words."""
+    out = np.zeros((len(seq) + 31) // 32, dtype=np.uint64)
+    if lib().ko_sv_from_bytes(_buf(seq), len(seq), out.ctypes.data) != OK:
+        raise RuntimeError("panic: SeqVector::from")
+    return out
+
+
+def sv_get_kmer_u64(words: np.ndarray, length: int, pos: int, k: int) -> int:
+    v = C.c_uint64()
+    if lib().ko_sv_get_kmer_u64(words.ctypes.data, length, pos, k, C.byref(v)) != OK:
+        raise RuntimeError("panic: get_kmer_u64")
+    return int(v.value)
+
+
+def sv_minimizers(seq: bytes, k: int, w: int, hash_k: int):
+    """SeqVecMinimizerIter over SeqVector::from(seq) -> list of (word, pos)."""
+    words = sv_from_bytes(seq)
+    n = len(seq) - k + 1
+    if n <= 0:
+        raise RuntimeError("panic: assert!(sv.len() >= k)")
+    mw, mp = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+    if lib().ko_sv_minimizers(words.ctypes.data, len(seq), k, w, hash_k, mw.ctypes.data, mp.ctypes.data) != OK:
+        raise RuntimeError("panic: SeqVecMinimizerIter")
+    return list(zip(mw.tolist(), mp.tolist()))
+
+
+def minimizers_batch(bases: np.ndarray, k: int, w: int, hash_k: int, *, offsets=None, n_reads=None, fixed_len=0):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    o, op = _offs_ptr(offsets)
+    if o is not None:
+        n_reads = o.size - 1
+    n_slots = count_slots(o, n_reads, fixed_len, k)
+    mm, pos = np.empty(n_slots, dtype=np.uint64), np.empty(n_slots, dtype=np.uint32)
+    if lib().ko_minimizers_batch(bases.ctypes.data, op, n_reads, fixed_len, k, w, hash_k, mm.ctypes.data, pos.ctypes.data) != OK:
+        raise RuntimeError("panic: minimizers_batch")
+    return mm, pos

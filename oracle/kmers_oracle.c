@@ -712,3 +712,135 @@ int ko_extract_canonical_wide(const uint8_t *bases, const uint64_t *offsets, siz
     if (digest) *digest = d;
     return KO_OK;
 }
+
+/* ======================================================================= */
+/* "next" rows: minimizers + SeqVector                                      */
+/* ======================================================================= */
+
+/* naive_impl/kmer.rs:170-191 */
+int ko_minimizer_word(uint64_t word, size_t k, size_t width, unsigned hash_k, int strict, uint64_t *mmer, size_t *offset) {
+    uint64_t min_mmer;
+    if (width > k) return KO_PANIC; /* k - width + 1 underflows / sub_kmer_word asserts */
+    if (ko_sub_kmer_word(word, k, 0, width, strict, &min_mmer) != KO_OK) return KO_PANIC; /* kmer.rs:176 */
+    uint64_t min_hash = UINT64_MAX;
+    size_t off = 0;
+    for (size_t pos = 0; pos < k - width + 1; ++pos) {
+        uint64_t m;
+        if (ko_sub_kmer_word(word, k, pos, width, strict, &m) != KO_OK) return KO_PANIC;
+        uint64_t h = ko_lexhash_word(m, hash_k); /* hash_one(state, mmer: u64) -> write_u64, hash.rs:10-20,60-71 */
+        if (h < min_hash) { /* strict: the leftmost minimum wins */
+            min_mmer = m;
+            min_hash = h;
+            off = pos;
+        }
+    }
+    *mmer = min_mmer;
+    *offset = off;
+    return KO_OK;
+}
+
+/* naive_impl/seq_vector.rs:230-242 */
+int ko_sv_from_bytes(const uint8_t *s, size_t len, uint64_t *words_out) {
+    size_t nw = 0;
+    for (size_t i = 0; i < len; i += 32) {
+        size_t n = len - i < 32 ? len - i : 32;
+        ko_kmer km;
+        if (ko_kmer_from_bytes(s + i, n, &km) != KO_OK) return KO_PANIC;
+        words_out[nw++] = km.data;
+    }
+    return KO_OK;
+}
+
+/* naive_impl/seq_vector.rs:96-99 ; simple-sds RawVector::int(bit_offset, bit_len) */
+int ko_sv_get_kmer_u64(const uint64_t *words, size_t len, size_t pos, size_t k, uint64_t *out) {
+    if (!(pos < len)) return KO_PANIC; /* seq_vector.rs:97 */
+    size_t bit = pos * 2, nbits = k * 2;
+    size_t wi = bit / 64, sh = bit % 64;
+    size_t n_words = (len * 2 + 63) / 64;
+    uint64_t v = words[wi] >> sh;
+    if (sh != 0 && sh + nbits > 64 && wi + 1 < n_words) v |= words[wi + 1] << (64 - sh);
+    if (nbits < 64) v &= (((uint64_t)1) << nbits) - 1;
+    *out = v;
+    return KO_OK;
+}
+
+typedef struct { uint64_t lmer, pos, hash; } dqmer_t; /* minimizers.rs:8-12 */
+
+/* naive_impl/seq_vector/minimizers.rs:38-142 */
+int ko_sv_minimizers(const uint64_t *words, size_t len, size_t k, size_t w, unsigned hash_k, uint64_t *mm_words,
+                     uint64_t *mm_pos) {
+    if (!(len >= k)) return KO_PANIC; /* minimizers.rs:102 */
+    if (w > k || w == 0) return KO_PANIC;
+    size_t cap = k - w + 3;
+    dqmer_t *dq = (dqmer_t *)malloc(cap * sizeof(dqmer_t));
+    size_t head = 0, n = 0; /* ring buffer: front at head */
+    size_t curr = 0;
+    int status = KO_OK;
+#define DQ(i) dq[(head + (i)) % cap]
+    /* enqueue_dqmer, minimizers.rs:60-81 */
+#define ENQUEUE(m)                                                            \
+    do {                                                                      \
+        if (n > 0 && DQ(0).pos < curr) { head = (head + 1) % cap; n--; }      \
+        while (n > 0) {                                                       \
+            if (DQ(n - 1).hash <= (m).hash) break;                            \
+            n--;                                                              \
+        }                                                                     \
+        DQ(n) = (m);                                                          \
+        n++;                                                                  \
+    } while (0)
+    for (size_t i = 0; i < k - w; ++i) { /* minimizers.rs:114-121 : lmers of the k-1 prefix */
+        dqmer_t m;
+        if (ko_sv_get_kmer_u64(words, len, i, w, &m.lmer) != KO_OK) { status = KO_PANIC; goto done; }
+        m.pos = i;
+        m.hash = ko_lexhash_word(m.lmer, hash_k);
+        ENQUEUE(m);
+    }
+    for (; curr < len - k + 1; ++curr) { /* Iterator::next, minimizers.rs:127-142 */
+        dqmer_t m; /* next_dqmer :84-90 */
+        m.pos = curr + k - w;
+        if (ko_sv_get_kmer_u64(words, len, m.pos, w, &m.lmer) != KO_OK) { status = KO_PANIC; goto done; }
+        m.hash = ko_lexhash_word(m.lmer, hash_k);
+        ENQUEUE(m);
+        mm_words[curr] = DQ(0).lmer;
+        mm_pos[curr] = DQ(0).pos;
+    }
+#undef ENQUEUE
+#undef DQ
+done:
+    free(dq);
+    return status;
+}
+
+int ko_minimizers_batch(const uint8_t *bases, const uint64_t *offsets, size_t n_reads, uint64_t fixed_len, unsigned k,
+                        unsigned w, unsigned hash_k, uint64_t *mm_out, uint32_t *pos_out) {
+    if (k < 1 || k > 32 || w < 1 || w > k) return KO_PANIC;
+    uint64_t slot = 0;
+    for (size_t r = 0; r < n_reads; ++r) {
+        uint64_t b = read_begin(offsets, fixed_len, r), e = read_begin(offsets, fixed_len, r + 1);
+        uint64_t len = e - b, nwin = n_windows(len, k);
+        for (uint64_t p = 0; p < nwin; ++p) { mm_out[slot + p] = KO_SENTINEL; pos_out[slot + p] = UINT32_MAX; }
+        uint64_t i = 0;
+        while (i < len) { /* maximal runs of valid bases */
+            if (ko_encode_binary_u8(bases[b + i]) == KO_INVALID_BASE) { ++i; continue; }
+            uint64_t j = i;
+            while (j < len && ko_encode_binary_u8(bases[b + j]) != KO_INVALID_BASE) ++j;
+            uint64_t seg = j - i;
+            if (seg >= k) {
+                uint64_t *words = (uint64_t *)malloc(((seg + 31) / 32) * 8);
+                uint64_t *mw = (uint64_t *)malloc((seg - k + 1) * 8), *mp = (uint64_t *)malloc((seg - k + 1) * 8);
+                int st = ko_sv_from_bytes(bases + b + i, seg, words);
+                if (st == KO_OK) st = ko_sv_minimizers(words, seg, k, w, hash_k, mw, mp);
+                if (st == KO_OK)
+                    for (uint64_t q = 0; q < seg - k + 1; ++q) {
+                        mm_out[slot + i + q] = mw[q];
+                        pos_out[slot + i + q] = (uint32_t)(mp[q] + i);
+                    }
+                free(words); free(mw); free(mp);
+                if (st != KO_OK) return st;
+            }
+            i = j;
+        }
+        slot += nwin;
+    }
+    return KO_OK;
+}

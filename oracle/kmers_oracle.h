@@ -230,6 +230,32 @@ int ko_extract_canonical_wide(const uint8_t *bases, const uint64_t *offsets, siz
                               uint64_t *hash_out /* 2 words per slot, may be NULL */,
                               ko_digest *digest);
 
+/* ---------------- "next" rows: minimizers + packed sequence store ---------------- */
+
+/* Kmer::minimizer_word (naive_impl/kmer.rs:170-191) with state = LexHasherState::new(hash_k):
+ * the first (leftmost) width-mer of minimum hash_one(state, mmer: u64).  KO_PANIC on the
+ * sub_kmer_word asserts (pos < k, pos + width <= k) or width > k. */
+int ko_minimizer_word(uint64_t word, size_t k, size_t width, unsigned hash_k, int strict, uint64_t *mmer, size_t *offset);
+
+/* SeqVector::from(&[u8]) (naive_impl/seq_vector.rs:230-242): 32 bases per u64 through Kmer::from
+ * (panics on non-ACGT -> KO_PANIC).  words_out has ceil(len / 32) entries. */
+int ko_sv_from_bytes(const uint8_t *s, size_t len, uint64_t *words_out);
+/* SeqVector::get_kmer_u64 (seq_vector.rs:96-99) = RawVector::int(2*pos, 2*k) of simple-sds (un-vendored git
+ * dependency; semantics pinned by seq_vector.rs:304-321 and minimizers.rs:221-290): 2k bits from bit 2*pos,
+ * LSB first across the u64 words.  KO_PANIC on assert!(pos < len). */
+int ko_sv_get_kmer_u64(const uint64_t *words, size_t len, size_t pos, size_t k, uint64_t *out);
+/* SeqVecMinimizerIter (naive_impl/seq_vector/minimizers.rs:38-142), the monotone-deque algorithm restated
+ * literally, hash = hash_one(LexHasherState(hash_k), lmer: u64).  Writes len - k + 1 (word, pos) pairs.
+ * KO_PANIC on assert!(sv.len() >= k). */
+int ko_sv_minimizers(const uint64_t *words, size_t len, size_t k, size_t w, unsigned hash_k, uint64_t *mm_words,
+                     uint64_t *mm_pos);
+/* Batch driver, dense slots like ko_extract_canonical: slot of window `pos` of read r holds the minimizer
+ * (lmer word, position inside the read) of that k-mer.  EXTENSION: a SeqVector cannot hold non-ACGT bases;
+ * here every maximal run of valid bases is one SeqVector, and windows holding an invalid base get
+ * KO_SENTINEL / UINT32_MAX. */
+int ko_minimizers_batch(const uint8_t *bases, const uint64_t *offsets, size_t n_reads, uint64_t fixed_len, unsigned k,
+                        unsigned w, unsigned hash_k, uint64_t *mm_out, uint32_t *pos_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -629,3 +629,81 @@ def test_generator_is_counter_based():
         return z ^ (z >> 31)
     assert all(L.ko_splitmix64(x) == sm(x) for x in (0, 1, 42, 2**63, 2**64 - 1))
     assert a[:8].tobytes() == bytes(b"ACGT"[sm(42 + i) >> 62] for i in range(8))
+
+
+# ---------------------------------------------------------------- "next" rows: minimizers + SeqVector
+def test_seq_vector_slice():  # naive_impl/seq_vector.rs:304-321 seq_slice_test
+    words = np.array([1, 2, 3], dtype=np.uint64)
+    assert ko.sv_get_kmer_u64(words, 96, 0, 32) == 1
+    # slice(1, 96).get_kmer_u64(0, 32) == sv.get_kmer_u64(1, 32): bits 2..66 -> (1 >> 2) | (2 << 62)
+    assert ko.sv_get_kmer_u64(words, 96, 1, 32) == ((1 >> 2) | (2 << 62)) % 2**64
+    assert ko.sv_get_kmer_u64(words, 96, 75, 7) == (3 >> 22) & ((1 << 14) - 1)
+    with pytest.raises(RuntimeError):
+        ko.sv_get_kmer_u64(words, 96, 96, 1)  # assert!(pos < self.len())
+
+
+def test_seq_vector_iter_kmers():  # seq_vector.rs:342-358 iter_kmers
+    s = b"ACTTGAT"
+    words = ko.sv_from_bytes(s)
+    mers = ["act", "ctt", "ttg", "tga", "gat"]
+    got = [ko.kmer_str(ko.Kmer(3, ko.sv_get_kmer_u64(words, 7, i, 3))) for i in range(5)]
+    assert got == mers
+    assert words.tolist() == [ko.kmer_from(s).data]
+    long = b"A" * 30 + b"C" * 40  # seq_vector.rs:328-339 push_chars: 30 A then 40 C
+    w2 = ko.sv_from_bytes(long)
+    assert "".join("acgt"[ko.sv_get_kmer_u64(w2, 70, i, 1)] for i in range(70)).upper().encode() == long
+
+
+def test_minimizer_leftmost():  # minimizers.rs:221-236 leftmost_mmer (any hasher: all lmers equal)
+    assert ko.sv_minimizers(b"AAAAAAA", 5, 3, 3) == [(0, 0), (0, 1), (0, 2)]
+
+
+def test_minimizer_mmers0():  # minimizers.rs:238-249 : LexHasherState::new(6), k=6, w=3
+    assert ko.sv_minimizers(b"AAACAAA", 6, 3, 6) == [(0, 0), (0, 4)]
+
+
+def test_minimizer_mmers1():  # minimizers.rs:251-270 : LexHasherState::new(5), k=5, w=3
+    aac, acc, aaa = 0b010000, 0b010100, 0b000000
+    assert ko.sv_minimizers(b"AACCAAA", 5, 3, 5) == [(aac, 0), (acc, 1), (aaa, 4)]
+
+
+def test_minimizer_mmers2():  # minimizers.rs:272-290 : LexHasherState::new(3), k=7, w=3
+    aca = 0b000100
+    assert ko.sv_minimizers(b"CACACACCAC", 7, 3, 3) == [(aca, 1), (aca, 1), (aca, 3), (aca, 3)]
+
+
+def test_minimizer_word_matches_definition():  # naive_impl/kmer.rs:560-579 test_minimizer, with the pinned hasher
+    s = "ACTTGAT"
+    km = ko.kmer_from(s)
+    for w in range(1, len(s)):
+        mm, o = ko.minimizer_word(km.data, km.k, w, w)
+        h_min = L.ko_lexhash_word(mm, w)
+        for i in range(len(s) - w + 1):
+            out = C.c_uint64()
+            assert L.ko_sub_kmer_word(km.data, km.k, i, w, 0, C.byref(out)) == ko.OK
+            assert h_min <= L.ko_lexhash_word(out.value, w)
+        assert ko.kmer_from(s[o:o + w]).data == mm
+    with pytest.raises(RuntimeError):
+        ko.minimizer_word(km.data, 7, 8, 3)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.text(alphabet="ACGT", min_size=12, max_size=80), st.integers(5, 12), st.data())
+def test_minimizer_deque_equals_bruteforce(seq, k, data):
+    """The restated deque iterator == leftmost argmin of the lmer hashes over every k-mer (what it computes)."""
+    w = data.draw(st.integers(1, k))
+    hk = data.draw(st.integers(w, 32))
+    got = ko.sv_minimizers(seq.encode(), k, w, hk)
+    words = ko.sv_from_bytes(seq.encode())
+    for i, (word, pos) in enumerate(got):
+        cands = [(L.ko_lexhash_word(ko.sv_get_kmer_u64(words, len(seq), p, w), hk), p) for p in range(i, i + k - w + 1)]
+        best = min(cands)  # ties -> smallest p
+        assert pos == best[1] and word == ko.sv_get_kmer_u64(words, len(seq), pos, w)
+
+
+def test_minimizers_batch_with_invalid_bases():
+    seq = np.frombuffer(b"AACCAAANAACCAAAACGTNNACGTTTT", dtype=np.uint8)
+    mm, pos = ko.minimizers_batch(seq, 5, 3, 5, n_reads=1, fixed_len=seq.size)
+    assert mm[:3].tolist() == [0b010000, 0b010100, 0] and pos[:3].tolist() == [0, 1, 4]
+    assert (mm[3:8] == ko.SENTINEL).all() and (pos[3:8] == 2**32 - 1).all()
+    assert pos[8] == 8 and mm[8] == 0b010000
