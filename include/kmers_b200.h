@@ -189,6 +189,25 @@ int32_t kmb_minimizers(kmb_ctx *ctx, uint32_t k, uint32_t w, uint32_t hash_k, ui
 int32_t kmb_minimizer_words(kmb_ctx *ctx, uint32_t k, uint32_t w, uint32_t hash_k, const uint64_t *words, uint64_t n,
                             uint64_t *mmer_out, uint32_t *offset_out);
 
+/* ---- "next" row N2: the batch as a 2-bit packed sequence store ------------- */
+/* SeqVector twin (naive_impl/seq_vector.rs:18-258): 32 bases per u64 word, base i of a read at bits 2i+1:2i of its
+ * region, A0 C1 G2 T3 -- the layout SeqVector::from(&[u8]) builds (:230-242) and kmb_pack(KMB_ENC_ACGT, 64) writes;
+ * every read starts on a word boundary.  Once the batch is packed, kmb_extract_canonical (fw_out = iter_kmers,
+ * :117-124), kmb_extract_compact, kmb_histogram and kmb_minimizers (= iter_minimizers, :126-139) read 0.25 B/base
+ * instead of 1 B/base.  A packed store holds no invalid base, so every window is emitted. */
+/* pack the resident ASCII batch on the device and switch the batch to the packed copy.  strict != 0: fail with
+ * KMB_ERR_PANIC if any byte is outside ACGTacgt, as SeqVector::from would panic; strict == 0: such bytes encode
+ * by (c >> 1) & 3 like Encoding::encode. */
+int32_t kmb_batch_repack(kmb_ctx *ctx, int32_t strict);
+/* borrow caller-owned packed DEVICE memory.  Fixed-length: dev_offsets == dev_word_offsets == NULL and
+ * n_words == n_reads * ceil(fixed_len / 32).  Ragged: dev_offsets = base offsets (n_reads + 1), dev_word_offsets =
+ * u64-word offsets (n_reads + 1), both as kmb_pack reports them. */
+int32_t kmb_batch_attach_packed(kmb_ctx *ctx, const uint64_t *dev_words, uint64_t n_words, const uint64_t *dev_offsets,
+                                const uint64_t *dev_word_offsets, uint64_t n_reads, uint64_t fixed_len);
+/* SeqVector::get_kmer_u64 (seq_vector.rs:96-99) for n (read, pos) pairs (reads == NULL: read 0): out[i] = the k bases
+ * at pos[i] of read reads[i], or KMB_SENTINEL where the reference's assert!(pos < len) / the read's end is violated. */
+int32_t kmb_packed_get_kmers(kmb_ctx *ctx, uint32_t k, const uint64_t *reads, const uint64_t *pos, uint64_t n, uint64_t *out);
+
 /* ---- batched Encoding<P,B> (encoding/mod.rs:14-23) --------------------- */
 /* Encoding::encode of every read of the batch (encoding/naive.rs:116-124,
  * xor10.rs:52-60): read r becomes ceil(L_r / (word_bits/2)) words of

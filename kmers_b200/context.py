@@ -249,6 +249,7 @@ class ReadBatch:
     def __init__(self, ctx: Context, n_bytes: int, n_reads: int, fixed_len: int, ragged: bool):
         self.ctx = ctx
         self.n_bytes, self.n_reads, self.fixed_len, self.ragged = n_bytes, n_reads, fixed_len, ragged
+        self.packed = False
 
     def num_slots(self, k: int) -> int:
         n = C.c_uint64()
@@ -290,6 +291,21 @@ class ReadBatch:
         self.ctx._ck(self.ctx._lib.kmb_extract_canonical(self.ctx._h, k, flags, _ptr(out.canon), _ptr(out.hash),
                                                          _ptr(out.fw), _ptr(out.rc), C.byref(d) if digest else None))
         out.digest = d.astuple() if digest else None
+        return out
+
+    def to_packed(self, strict: bool = True) -> "ReadBatch":
+        """Switch the resident batch to a 2-bit packed store (SeqVector layout; kmb_batch_repack).  strict: raise
+        KmbPanic on a byte outside ACGTacgt, as SeqVector::from would panic."""
+        self.ctx._ck(self.ctx._lib.kmb_batch_repack(self.ctx._h, int(strict)))
+        self.packed = True
+        return self
+
+    def get_kmers(self, k: int, pos, reads=None) -> np.ndarray:
+        """SeqVector::get_kmer_u64 at (read, pos) pairs of a packed batch (kmb_packed_get_kmers)."""
+        pos = np.ascontiguousarray(pos, dtype=np.uint64)
+        rd = None if reads is None else np.ascontiguousarray(reads, dtype=np.uint64)
+        out = np.empty(pos.size, dtype=np.uint64)
+        self.ctx._ck(self.ctx._lib.kmb_packed_get_kmers(self.ctx._h, k, _ptr(rd), _ptr(pos), pos.size, _ptr(out)))
         return out
 
     def minimizers(self, k: int, w: int, hash_k=None, *, validate: bool = True, to: str = "host"):

@@ -95,13 +95,39 @@ __device__ __forceinline__ uint32_t count_valid_windows(const uint2* tile, uint3
     return n;
 }
 
+// 2-bit packed input (the layout kmb_pack writes with Naive::ACGT and u64 words = SeqVector's words,
+// naive_impl/seq_vector.rs:230-242): the tile entries are the packed 32-bit words themselves.
+// A packed store cannot hold an invalid base, so the invalid masks are zero.
+__device__ __forceinline__ void stage_packed(const uint32_t* words, uint64_t n_words32, uint64_t first_word,
+                                             uint32_t n_entries, uint2* tile) {
+    for (uint32_t v = threadIdx.x; v < n_entries; v += blockDim.x) {
+        const uint64_t i = first_word + v;
+        tile[v] = make_uint2(i < n_words32 ? __ldg(words + i) : 0u, 0u);
+    }
+}
+
+// Stage the stretch that starts at flat base index g_start; returns the offset of that base inside tile entry 0.
+template <bool VALIDATE>
+__device__ __forceinline__ uint32_t stage_stretch(const uint8_t* bases, uint64_t n_bytes, uint32_t packed, uint64_t g_start,
+                                                  uint32_t span, uint32_t span_entries, const EncDesc& enc, uint2* tile) {
+    if (packed) {
+        const uint32_t mis = (uint32_t)(g_start & 15u);
+        stage_packed(reinterpret_cast<const uint32_t*>(bases), n_bytes >> 2, g_start >> 4, ((span + mis + 15) >> 4) + span_entries - 1, tile);
+        return mis;
+    }
+    const uint8_t* first = bases + g_start;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
+    stage_tile<VALIDATE>(bases, n_bytes, first - mis, ((span + mis + 15) >> 4) + span_entries - 1, enc, tile);
+    return mis;
+}
+
 // ---------------------------------------------------------------------------
 // fixed-length reads
 // ---------------------------------------------------------------------------
 struct FixedGeom {
     const uint8_t* bases;   // flat read stream
-    uint64_t n_bytes;       // n_reads * L
-    uint64_t L;             // read length
+    uint64_t n_bytes;       // bytes of the buffer behind `bases`
+    uint64_t L;             // distance between read starts, in bases (= read length; packed: padded to 32)
     uint64_t W;             // windows (= output slots) per read = L - K + 1
     uint64_t total_slots;   // n_reads * W
     uint64_t w_magic64;     // floor(2^64 / W) + 1 (W >= 2), 0 = divide
@@ -109,6 +135,7 @@ struct FixedGeom {
     uint32_t W32;           // W (< 2^32, checked on the host)
     uint32_t w_magic;       // floor(2^32 / W) + 1
     uint32_t items_per_cta; // host-chosen so the staged stretch fits shared memory
+    uint32_t packed;        // bases = 2-bit packed words (SeqVector layout) instead of ASCII
 };
 
 // u / W for a small u (u < W + slots per CTA): 0/1 when W is large, else multiply-high
@@ -167,10 +194,7 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     const uint32_t q_last = div_w(u_last, g, slots_per_cta);
     // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
     const uint32_t span = q_last * g.L32 + (u_last - q_last * g.W32) - p_first + K;
-    const uint8_t* first = g.bases + g_start;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = ((span + mis + 15) >> 4) + Eng::kSpanEntries - 1;
-    stage_tile<Eng::kValidate>(g.bases, g.n_bytes, first - mis, n_entries, enc, tile);
+    const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile);
     __syncthreads();
 
     // ---- phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than
@@ -209,14 +233,16 @@ constexpr int kCsrCache = 1024;  // reads whose offsets a CTA keeps in shared me
 
 struct CsrGeom {
     const uint8_t* bases;
-    uint64_t n_bytes;
-    const uint64_t* offsets;      // n_reads + 1
+    uint64_t n_bytes;             // bytes of the buffer behind `bases`
+    uint64_t n_bases;             // length of the flat base index space (ASCII: n_bytes; packed: 4 * n_bytes)
+    const uint64_t* offsets;      // n_reads + 1: flat base index of every read's first base
     const uint64_t* win_offsets;  // n_reads + 1, exclusive prefix of per-read window counts
     const uint64_t* first_read;   // grid + 1: read owning each CTA's first slot (csr_index_kernel)
     uint64_t n_reads;
     uint64_t total_slots;
     uint32_t items_per_cta;
     uint32_t tile_entries;        // shared-memory capacity of the staged tile, in 16-base entries
+    uint32_t packed;              // as FixedGeom::packed (offsets then index the padded, packed space)
 };
 
 // largest r in [lo, hi] with a[r] <= v   (a[lo] <= v guaranteed)
@@ -278,7 +304,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
             // windows starting before g_lim fit wholly in a tile that starts at g0
             const uint64_t g_lim = ps.g0 + tile_bases - K + 1;
             uint64_t lim = slot_end;
-            if (g_lim < g.n_bytes) {
+            if (g_lim < g.n_bases) {
                 const uint64_t r = last_le(off, ps.r_lo, R_hi, g_lim);
                 const uint64_t w_r = win[r + 1] - win[r];
                 lim = min(lim, win[r] + min(g_lim - off[r], w_r));  // slots whose window starts before g_lim
@@ -292,10 +318,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         }
         __syncthreads();
         const CsrPass ps = *pass;
-        const uint8_t* first = g.bases + ps.g0;
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-        const uint32_t n_entries = ((ps.span + mis + 15) >> 4) + Eng::kSpanEntries - 1;
-        stage_tile<Eng::kValidate>(g.bases, g.n_bytes, first - mis, n_entries, enc, tile);
+        const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, ps.g0, ps.span, Eng::kSpanEntries, enc, tile);
         __syncthreads();
 
         const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);

@@ -37,6 +37,15 @@ struct kmb_ctx {
     size_t own_offsets_cap = 0;
     uint64_t n_bytes = 0, n_reads = 0, fixed_len = 0;
     bool have_batch = false;
+    // 2-bit packed batch (SeqVector layout): d_bases points at u64 words; reads start on word boundaries
+    bool packed = false;
+    uint64_t stride_len = 0;                  // fixed-length: bases between read starts (fixed_len padded to 32)
+    const uint64_t* d_base_starts = nullptr;  // ragged: flat (padded) base index of every read's first base, n_reads + 1
+    uint64_t n_bases_flat = 0;                // size of the flat base index space
+    uint64_t* own_packed = nullptr;
+    size_t own_packed_cap = 0;
+    uint64_t* own_base_starts = nullptr;
+    size_t own_base_starts_cap = 0;
 
     // CSR window-offset cache (per k)
     uint64_t* d_win_offsets = nullptr;
@@ -168,6 +177,8 @@ extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     cudaFree(ctx->own_bases);
     cudaFree(ctx->own_offsets);
+    cudaFree(ctx->own_packed);
+    cudaFree(ctx->own_base_starts);
     cudaFree(ctx->d_win_offsets);
     cudaFree(ctx->d_first_read);
     cudaFree(ctx->d_cta_counts);
@@ -272,6 +283,8 @@ static void drop_batch(kmb_ctx* ctx) {
     ctx->win_valid = false;
     ctx->d_bases = nullptr;
     ctx->d_offsets = nullptr;
+    ctx->packed = false;
+    ctx->d_base_starts = nullptr;
 }
 
 static int32_t check_shape(kmb_ctx* ctx, uint64_t n_bytes, bool has_offsets, uint64_t n_reads, uint64_t fixed_len) {
@@ -330,6 +343,7 @@ extern "C" int32_t kmb_batch_upload(kmb_ctx* ctx, const uint8_t* bases, uint64_t
         ctx->d_offsets = ctx->own_offsets;
     }
     ctx->n_bytes = n_bytes; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->stride_len = ctx->fixed_len; ctx->n_bases_flat = ctx->n_bytes;
     ctx->have_batch = true;
     return KMB_OK;
 }
@@ -345,6 +359,7 @@ extern "C" int32_t kmb_batch_attach(kmb_ctx* ctx, const uint8_t* dev_bases, uint
     drop_batch(ctx);
     ctx->d_bases = dev_bases; ctx->d_offsets = dev_offsets;
     ctx->n_bytes = n_bytes; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->stride_len = ctx->fixed_len; ctx->n_bases_flat = ctx->n_bytes;
     ctx->have_batch = true;
     return KMB_OK;
 }
@@ -367,6 +382,7 @@ extern "C" int32_t kmb_batch_generate(kmb_ctx* ctx, uint64_t seed, uint64_t firs
     }
     ctx->d_bases = ctx->own_bases; ctx->d_offsets = nullptr;
     ctx->n_bytes = n; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->stride_len = ctx->fixed_len; ctx->n_bases_flat = ctx->n_bytes;
     ctx->have_batch = true;
     return KMB_OK;
 }
@@ -378,7 +394,7 @@ extern "C" int32_t kmb_batch_download(kmb_ctx* ctx, uint8_t* dst, uint64_t n_byt
     NEED_CTX(ctx);
     BIND(ctx);
     NEED_BATCH(ctx);
-    if (n_bytes > ctx->n_bytes) return fail(ctx, KMB_ERR_INVALID_ARG, "n_bytes exceeds the batch");
+    if (n_bytes > ctx->n_bytes) return fail(ctx, KMB_ERR_INVALID_ARG, "n_bytes exceeds the batch");  // packed: the packed bytes
     if (n_bytes == 0) return KMB_OK;
     CK(ctx, cudaMemcpyAsync(dst, ctx->d_bases, n_bytes, cudaMemcpyDefault, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -510,8 +526,9 @@ struct Launch {
 
 // fixed-length reads: slot-space geometry of fixed_kernel
 static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
-                            uint32_t span_entries, FixedGeom* g, Launch* l) {
-    g->bases = d_bases; g->n_bytes = n_bytes; g->L = L; g->L32 = (uint32_t)L;
+                            uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, bool packed = false) {
+    if (stride == 0) stride = L;
+    g->bases = d_bases; g->n_bytes = n_bytes; g->L = stride; g->L32 = (uint32_t)stride; g->packed = packed ? 1u : 0u;
     g->W = L - k + 1;
     if (g->W > 0xFFFF0000ull) return false;  // one read of > 4.29 Gbases: split it (window positions are 32-bit inside a CTA)
     g->W32 = (uint32_t)g->W;
@@ -525,7 +542,7 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
     for (;;) {
         const uint64_t slots = (uint64_t)ipc * kRun;
         const uint64_t crossings = slots / g->W + 2;
-        const uint64_t span = slots + crossings * (k - 1) + k + 32;
+        const uint64_t span = slots + crossings * (k - 1 + (stride - L)) + k + 32;
         l->smem = (size_t)((span + 15) / 16 + span_entries + 2) * sizeof(uint2);
         if (l->smem <= 44 * 1024 || ipc <= 64) break;
         ipc /= 2;
@@ -542,7 +559,8 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
 static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, CsrGeom* g, Launch* l) {
     int32_t rc = ensure_win_offsets(ctx, k);
     if (rc) return rc;
-    g->bases = ctx->d_bases; g->n_bytes = ctx->n_bytes; g->offsets = ctx->d_offsets; g->win_offsets = ctx->d_win_offsets;
+    g->bases = ctx->d_bases; g->n_bytes = ctx->n_bytes; g->n_bases = ctx->n_bases_flat; g->packed = ctx->packed ? 1u : 0u;
+    g->offsets = ctx->packed ? ctx->d_base_starts : ctx->d_offsets; g->win_offsets = ctx->d_win_offsets;
     g->n_reads = ctx->n_reads; g->total_slots = ctx->win_total; g->items_per_cta = kItemsPerCta;
     g->tile_entries = 2304 + span_entries;  // ~36.8 K bases per pass
     const uint64_t slots_per_cta = (uint64_t)kItemsPerCta * kRun;
@@ -606,10 +624,11 @@ static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
 // One extraction launch over (d_bases, fixed_len) -- or over the ctx's resident CSR batch when fixed_len == 0.
 static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint64_t n_bytes, uint64_t n_reads,
                            uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* canon, uint64_t* hash, uint64_t* fw,
-                           uint64_t* rc, bool want_digest, unsigned long long* hist, uint32_t hist_bits, cudaStream_t st) {
+                           uint64_t* rc, bool want_digest, unsigned long long* hist, uint32_t hist_bits, cudaStream_t st,
+                           uint64_t stride = 0, bool packed = false) {
     EncDesc enc;
     make_enc(KMB_ENC_ACGT, &enc, nullptr);
-    const bool validate = !(flags & KMB_F_NO_VALIDATE);
+    const bool validate = !(flags & KMB_F_NO_VALIDATE) && !packed;  // a packed store holds no invalid base
     const bool fwrc = fw || rc;
     const bool khi = k > 16;
     NarrowParams ep{};
@@ -622,7 +641,7 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
     Launch l;
     if (!csr) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
-        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l))
+        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l, stride, packed))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else {
         if (n_bytes == 0 || n_reads == 0) return KMB_OK;
@@ -655,7 +674,7 @@ extern "C" int32_t kmb_extract_canonical(kmb_ctx* ctx, uint32_t k, uint32_t flag
     if (n_slots) {
         rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags,
                          (uint64_t*)ob[0].dev, (uint64_t*)ob[1].dev, (uint64_t*)ob[2].dev, (uint64_t*)ob[3].dev,
-                         digest != nullptr, nullptr, 0, ctx->stream);
+                         digest != nullptr, nullptr, 0, ctx->stream, ctx->stride_len, ctx->packed);
         if (rc) return rc;
     }
     bool any_host = false;
@@ -681,7 +700,7 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
     if (!accumulate) CK(ctx, cudaMemsetAsync(ob.dev, 0, bytes, ctx->stream));
     if (digest && (rc = digest_begin(ctx))) return rc;
     rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags, nullptr,
-                     nullptr, nullptr, nullptr, digest != nullptr, (unsigned long long*)ob.dev, hist_bits, ctx->stream);
+                     nullptr, nullptr, nullptr, digest != nullptr, (unsigned long long*)ob.dev, hist_bits, ctx->stream, ctx->stride_len, ctx->packed);
     if (rc) return rc;
     if ((rc = out_finish(ctx, ob))) return rc;
     if (digest) return digest_end(ctx, digest);
@@ -716,7 +735,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     *n_emitted = 0;
     EncDesc enc;
     make_enc(KMB_ENC_ACGT, &enc, nullptr);
-    const bool validate = !(flags & KMB_F_NO_VALIDATE), khi = k > 16, csr = ctx->d_offsets != nullptr;
+    const bool validate = !(flags & KMB_F_NO_VALIDATE) && !ctx->packed, khi = k > 16, csr = ctx->d_offsets != nullptr;
     uint64_t n_slots = 0;
     int32_t rc = num_slots(ctx, k, &n_slots);
     if (rc) return rc;
@@ -732,7 +751,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     CsrGeom cg{};
     Launch l;
     if (!csr) {
-        if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l))
+        if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
         return rc;
@@ -815,9 +834,9 @@ extern "C" int32_t kmb_minimizers(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t
         FixedGeom fg{};
         CsrGeom cg{};
         Launch l;
-        const bool csr = ctx->d_offsets != nullptr, validate = !(flags & KMB_F_NO_VALIDATE);
+        const bool csr = ctx->d_offsets != nullptr, validate = !(flags & KMB_F_NO_VALIDATE) && !ctx->packed;
         if (!csr) {
-            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l))
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
         } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
             return rc;
@@ -874,6 +893,7 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
     BIND(ctx);
     NEED_BATCH(ctx);
     if (k < 1 || k > 64) return fail(ctx, KMB_ERR_INVALID_ARG, "k = %u: the two-word path supports 1 <= k <= 64", k);
+    if (ctx->packed) return fail(ctx, KMB_ERR_STATE, "the two-word path reads ASCII batches, not packed ones");
     EncDesc enc;
     if (!make_enc(enc_id, &enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
     uint64_t n_slots = 0;
@@ -1002,6 +1022,116 @@ extern "C" int32_t kmb_extract_canonical_host(kmb_ctx* ctx, const uint8_t* host_
     return KMB_OK;
 }
 
+// ======================================================================= packed sequence store ("next" row N2)
+__global__ void __launch_bounds__(256) base_starts_kernel(const uint64_t* word_offsets, uint64_t n, uint64_t* base_starts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) base_starts[i] = word_offsets[i] * 32;  // 32 bases per u64 word
+}
+
+// SeqVector::get_kmer_u64 (naive_impl/seq_vector.rs:96-99) on (read, pos) pairs of a packed batch
+__global__ void __launch_bounds__(256) packed_get_kmers_kernel(const uint64_t* words, uint64_t n_words, const uint64_t* offsets,
+                                                               const uint64_t* base_starts, uint64_t fixed_len, uint64_t stride,
+                                                               uint64_t n_reads, uint32_t k, const uint64_t* reads,
+                                                               const uint64_t* pos, uint64_t n, uint64_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r = reads ? reads[i] : 0, p = pos[i];
+    uint64_t v = ~0ull;
+    if (r < n_reads) {
+        const uint64_t len = offsets ? offsets[r + 1] - offsets[r] : fixed_len;
+        if (p + k <= len) {
+            const uint64_t bit = ((base_starts ? base_starts[r] : r * stride) + p) * 2;
+            const uint64_t wi = bit >> 6, sh = bit & 63;
+            v = words[wi] >> sh;
+            if (sh != 0 && wi + 1 < n_words) v |= words[wi + 1] << (64 - sh);
+            if (k < 32) v &= (1ull << (2 * k)) - 1ull;
+        }
+    }
+    out[i] = v;
+}
+
+static int32_t set_packed(kmb_ctx* ctx, const uint64_t* d_words, uint64_t n_words, const uint64_t* d_word_offsets) {
+    if (ctx->d_offsets) {  // ragged: flat index of every read's first base in the padded space
+        int32_t rc = grow(ctx, (void**)&ctx->own_base_starts, &ctx->own_base_starts_cap, (ctx->n_reads + 1) * 8);
+        if (rc) return rc;
+        base_starts_kernel<<<(unsigned)((ctx->n_reads + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_word_offsets, ctx->n_reads + 1,
+                                                                                             ctx->own_base_starts);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+        ctx->d_base_starts = ctx->own_base_starts;
+    }
+    ctx->d_bases = (const uint8_t*)d_words;
+    ctx->n_bytes = n_words * 8;
+    ctx->n_bases_flat = n_words * 32;
+    ctx->stride_len = (ctx->fixed_len + 31) / 32 * 32;
+    ctx->packed = true;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_repack(kmb_ctx* ctx, int32_t strict) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (ctx->packed) return KMB_OK;
+    if (strict && ctx->n_bytes) {
+        // SeqVector::from goes through Kmer::from, which panics on a non-ACGT byte (seq_vector.rs:236, naive_impl/mod.rs:35)
+        uint64_t n_valid = 0;
+        int32_t rc = kmb_extract_compact(ctx, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, &n_valid);
+        if (rc) return rc;
+        if (n_valid != ctx->n_bytes) return fail(ctx, KMB_ERR_PANIC, "%llu bases are not ACGTacgt: SeqVector::from would panic",
+                                                 (unsigned long long)(ctx->n_bytes - n_valid));
+    }
+    uint64_t n_words = 0;
+    int32_t rc = kmb_pack_num_words(ctx, 64, &n_words);
+    if (rc) return rc;
+    if ((rc = grow(ctx, (void**)&ctx->own_packed, &ctx->own_packed_cap, n_words * 8 + 64))) return rc;
+    uint64_t* d_woff = nullptr;
+    if (ctx->d_offsets) {
+        if ((rc = grow(ctx, &ctx->d_scratch[2], &ctx->scratch_cap[2], (ctx->n_reads + 1) * 8))) return rc;
+        d_woff = (uint64_t*)ctx->d_scratch[2];
+    }
+    if ((rc = kmb_pack(ctx, KMB_ENC_ACGT, 64, ctx->own_packed, d_woff))) return rc;
+    return set_packed(ctx, ctx->own_packed, n_words, d_woff);
+}
+
+extern "C" int32_t kmb_batch_attach_packed(kmb_ctx* ctx, const uint64_t* dev_words, uint64_t n_words, const uint64_t* dev_offsets,
+                                           const uint64_t* dev_word_offsets, uint64_t n_reads, uint64_t fixed_len) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if ((dev_offsets != nullptr) == (fixed_len > 0) && n_reads) return fail(ctx, KMB_ERR_INVALID_ARG, "give either offsets or fixed_len > 0");
+    if ((dev_offsets != nullptr) != (dev_word_offsets != nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "ragged packed batches need offsets and word_offsets");
+    if (n_words && !is_device_ptr(dev_words)) return fail(ctx, KMB_ERR_INVALID_ARG, "dev_words is not device memory");
+    if (!dev_offsets && n_reads * ((fixed_len + 31) / 32) != n_words) return fail(ctx, KMB_ERR_INVALID_ARG, "n_words != n_reads * ceil(fixed_len / 32)");
+    drop_batch(ctx);
+    ctx->d_offsets = dev_offsets; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
+    ctx->have_batch = true;
+    return set_packed(ctx, dev_words, n_words, dev_word_offsets);
+}
+
+extern "C" int32_t kmb_packed_get_kmers(kmb_ctx* ctx, uint32_t k, const uint64_t* reads, const uint64_t* pos, uint64_t n, uint64_t* out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (!ctx->packed) return fail(ctx, KMB_ERR_STATE, "the resident batch is not packed (kmb_batch_repack first)");
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: get_kmer_u64 reads at most 32 bases", k);
+    if (n == 0) return KMB_OK;
+    if (!pos || !out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    const void *d_reads = nullptr, *d_pos;
+    int32_t rc;
+    if (reads && (rc = in_prepare(ctx, 2, reads, n * 8, &d_reads))) return rc;
+    if ((rc = in_prepare(ctx, 3, pos, n * 8, &d_pos))) return rc;
+    OutBuf ob;
+    if ((rc = out_prepare(ctx, 0, out, n * 8, &ob))) return rc;
+    packed_get_kmers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        (const uint64_t*)ctx->d_bases, ctx->n_bytes / 8, ctx->d_offsets, ctx->d_base_starts, ctx->fixed_len, ctx->stride_len, ctx->n_reads,
+        k, (const uint64_t*)d_reads, (const uint64_t*)d_pos, n, (uint64_t*)ob.dev);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
 // ======================================================================= batched Encoding<P,B>
 static bool word_bits_ok(uint32_t wb) { return wb == 8 || wb == 16 || wb == 32 || wb == 64 || wb == 128; }
 
@@ -1036,6 +1166,7 @@ extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, vo
     BIND(ctx);
     NEED_BATCH(ctx);
     if (!word_bits_ok(word_bits)) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128");
+    if (ctx->packed) return fail(ctx, KMB_ERR_STATE, "the resident batch is already packed");
     PackParams p{};
     if (!make_enc(enc_id, &p.enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
     uint64_t total = 0;
