@@ -73,6 +73,12 @@ struct CanonicalKmers {
     Digest digest;
 };
 
+// Compacted iterator output: entry i is the i-th emitted k-mer; emit_offsets[r] = first entry of read r.
+struct CompactKmers {
+    std::vector<int32_t> pos;
+    std::vector<uint64_t> canon, hash, emit_offsets;
+};
+
 class Context;
 
 // The device-resident read batch of a Context (stand-in for the &[u8] handed to
@@ -89,6 +95,19 @@ class ReadBatch {
     std::vector<std::array<uint64_t, 2>> canonical_kmers_wide(uint32_t k, Enc enc, Digest* digest = nullptr) const;
     // fused histogram by the top hist_bits of the LexHash + digest
     std::vector<uint64_t> histogram(uint32_t k, uint32_t hist_bits, Digest* digest = nullptr) const;
+    // exactly what `while !it.exhausted() { it.get(); it.inc(); }` yields, read after read
+    // (CanonicalKmerPos{km, pos}, canonical_kmer_iterator.rs:13-16)
+    CompactKmers canonical_kmer_positions(uint32_t k) const;
+    // SeqVecMinimizerIter in batch (seq_vector/minimizers.rs:38-142): (lmer word, pos) per k-mer window
+    std::pair<std::vector<uint64_t>, std::vector<uint32_t>> minimizers(uint32_t k, uint32_t w, uint32_t hash_k) const;
+    // switch the batch to the 2-bit packed store (SeqVector layout, seq_vector.rs:230-242)
+    void to_packed(bool strict = true) const { detail::check(ctx_, kmb_batch_repack(ctx_, strict ? 1 : 0)); }
+    // SeqVector::get_kmer_u64 (seq_vector.rs:96-99) at (read, pos) pairs of a packed batch
+    std::vector<uint64_t> get_kmers_u64(uint32_t k, const std::vector<uint64_t>& reads, const std::vector<uint64_t>& pos) const {
+        std::vector<uint64_t> out(pos.size());
+        detail::check(ctx_, kmb_packed_get_kmers(ctx_, k, reads.empty() ? nullptr : reads.data(), pos.data(), pos.size(), out.data()));
+        return out;
+    }
     // Encoding::encode of every read -> byte image
     template <class Enc>
     std::vector<uint8_t> pack(Enc enc, uint32_t word_bits) const;
@@ -149,6 +168,15 @@ class Context {
         std::vector<MatchType> out(words.size());
         detail::check(ctx_, kmb_match_words(ctx_, k, words.data(), others.data(), reinterpret_cast<uint8_t*>(out.data()), words.size()));
         return out;
+    }
+
+    // Kmer::minimizer_word with LexHasherState(hash_k) (naive_impl/kmer.rs:170-191) -> (mmer, offset) per word
+    std::pair<std::vector<uint64_t>, std::vector<uint32_t>> minimizer_word(const std::vector<uint64_t>& words, uint32_t k, uint32_t width,
+                                                                          uint32_t hash_k) {
+        std::vector<uint64_t> mm(words.size());
+        std::vector<uint32_t> off(words.size());
+        detail::check(ctx_, kmb_minimizer_words(ctx_, k, width, hash_k, words.data(), words.size(), mm.data(), off.data()));
+        return {std::move(mm), std::move(off)};
     }
 
     // ---- batched Encoding<P,B> on arrays [P;B]
@@ -227,6 +255,24 @@ inline std::vector<uint64_t> ReadBatch::histogram(uint32_t k, uint32_t hist_bits
     detail::check(ctx_, kmb_histogram(ctx_, k, 0, hist_bits, out.data(), 0, digest ? &d : nullptr));
     if (digest) *digest = {d.n_valid, d.checksum_canon, d.checksum_hash};
     return out;
+}
+
+inline CompactKmers ReadBatch::canonical_kmer_positions(uint32_t k) const {
+    CompactKmers r;
+    uint64_t n = 0, nb = 0, nr = 0, fl = 0;
+    detail::check(ctx_, kmb_extract_compact(ctx_, k, 0, nullptr, nullptr, nullptr, nullptr, 0, &n));
+    kmb_batch_info(ctx_, &nb, &nr, &fl);
+    r.pos.resize(n); r.canon.resize(n); r.hash.resize(n); r.emit_offsets.resize(nr + 1);
+    detail::check(ctx_, kmb_extract_compact(ctx_, k, 0, r.canon.data(), r.hash.data(), r.pos.data(), r.emit_offsets.data(), n, &n));
+    return r;
+}
+
+inline std::pair<std::vector<uint64_t>, std::vector<uint32_t>> ReadBatch::minimizers(uint32_t k, uint32_t w, uint32_t hash_k) const {
+    const uint64_t n = num_slots(k);
+    std::vector<uint64_t> mm(n);
+    std::vector<uint32_t> pos(n);
+    detail::check(ctx_, kmb_minimizers(ctx_, k, w, hash_k, 0, mm.data(), pos.data()));
+    return {std::move(mm), std::move(pos)};
 }
 
 template <class Enc>

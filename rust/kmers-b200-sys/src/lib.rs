@@ -48,6 +48,12 @@ extern "C" {
     pub fn kmb_batch_num_slots(ctx: *mut kmb_ctx, k: u32, n_slots: *mut u64) -> i32;
     pub fn kmb_batch_window_offsets(ctx: *mut kmb_ctx, k: u32, win_offsets_out: *mut u64) -> i32;
     pub fn kmb_extract_canonical(ctx: *mut kmb_ctx, k: u32, flags: u32, canon_out: *mut u64, hash_out: *mut u64, fw_out: *mut u64, rc_out: *mut u64, digest: *mut kmb_digest) -> i32;
+    pub fn kmb_extract_compact(ctx: *mut kmb_ctx, k: u32, flags: u32, canon_out: *mut u64, hash_out: *mut u64, pos_out: *mut i32, emit_offsets_out: *mut u64, capacity: u64, n_emitted: *mut u64) -> i32;
+    pub fn kmb_minimizers(ctx: *mut kmb_ctx, k: u32, w: u32, hash_k: u32, flags: u32, mmer_out: *mut u64, pos_out: *mut u32) -> i32;
+    pub fn kmb_minimizer_words(ctx: *mut kmb_ctx, k: u32, w: u32, hash_k: u32, words: *const u64, n: u64, mmer_out: *mut u64, offset_out: *mut u32) -> i32;
+    pub fn kmb_batch_repack(ctx: *mut kmb_ctx, strict: i32) -> i32;
+    pub fn kmb_batch_attach_packed(ctx: *mut kmb_ctx, dev_words: *const u64, n_words: u64, dev_offsets: *const u64, dev_word_offsets: *const u64, n_reads: u64, fixed_len: u64) -> i32;
+    pub fn kmb_packed_get_kmers(ctx: *mut kmb_ctx, k: u32, reads: *const u64, pos: *const u64, n: u64, out: *mut u64) -> i32;
     pub fn kmb_extract_canonical_wide(ctx: *mut kmb_ctx, k: u32, enc: i32, flags: u32, canon_out: *mut u64, hash_out: *mut u64, digest: *mut kmb_digest) -> i32;
     pub fn kmb_histogram(ctx: *mut kmb_ctx, k: u32, flags: u32, hist_bits: u32, hist_out: *mut u64, accumulate: i32, digest: *mut kmb_digest) -> i32;
     pub fn kmb_extract_canonical_host(ctx: *mut kmb_ctx, host_bases: *const u8, n_reads: u64, fixed_len: u64, k: u32, flags: u32, host_canon: *mut u64, host_hash: *mut u64, digest: *mut kmb_digest) -> i32;

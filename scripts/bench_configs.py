@@ -140,6 +140,29 @@ def main():
     row("Encoding::rev_comp::<63> on [u64;2]", nk // 2, "kmers", nk * 16, avg, best)
     del words, dst, out, out1, bases_dev, offs
 
+    # ---------------- "next" rows: compacted output, minimizers, packed store (config-2 reads)
+    import ctypes as C
+    batch = ctx.generate(42, n, L, n_thresh20=1049)  # 0.1 % N so that compaction has something to drop
+    cnt = C.c_uint64()
+    ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, K, 0, None, None, None, None, 0, C.byref(cnt)))
+    m = int(cnt.value)
+    cc, ch, cp = i64(m), i64(m), torch.empty(m, dtype=torch.int32, device="cuda")
+    ce = i64(n + 1)
+    avg, best = time_ms(stream, lambda: ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, K, 0, _ptr(cc), _ptr(ch), _ptr(cp), _ptr(ce), m, C.byref(cnt))))
+    row("config2 reads + 0.1% N, compacted (pos,canon,hash) output, 2 launches + scan", m, "kmers", 2 * n * L + m * 20 + (n + 1) * 8, avg, best,
+        "iterator-identical output; the count launch re-reads the bases")
+    del cc, ch, cp, ce
+    batch = ctx.generate(42, n, L)
+    mm, mp = i64(n * W), torch.empty(n * W, dtype=torch.int32, device="cuda")
+    avg, best = time_ms(stream, lambda: ctx._ck(ctx._lib.kmb_minimizers(ctx._h, 31, 15, 15, 0, _ptr(mm), _ptr(mp))))
+    row("config2 reads, minimizers (k=31, w=15): lmer word + pos per k-mer", n * W, "kmers", n * (L + W * 12), avg, best, "next row N1")
+    del mm, mp
+    out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=i64(n * W))
+    pb = batch.to_packed()
+    avg, best = time_ms(stream, lambda: pb.extract_canonical(K, out=out))
+    row("config2 reads from the 2-bit packed store (0.27 B/base in)", n * W, "kmers", n * (40 + W * 16), avg, best, "next row N2")
+    del out
+
     # ---------------- config 4: long reads with N
     n4, L4 = 100_000 // scale, 10_000
     w4 = L4 - K + 1

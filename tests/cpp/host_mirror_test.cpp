@@ -108,6 +108,29 @@ int main() {
         for (auto v : hist) total += v;
         CHECK(total == d.n_valid && total == 100 * 120);
     }
+    {  // canonical_kmer_iterator.rs:178-189 : N at index 35 -> the iterator's positions are 0..4, 36..
+        std::string r = read.substr(0, 35) + "N" + read.substr(35);
+        auto c = ctx.upload({r, std::string("ACGT")}).canonical_kmer_positions(31);
+        CHECK(c.pos.size() == 60 && c.pos[4] == 4 && c.pos[5] == 36 && c.emit_offsets[1] == 60 && c.emit_offsets[2] == 60);
+        CHECK(c.canon.size() == 60 && c.hash.size() == 60);
+    }
+    {  // seq_vector/minimizers.rs:251-290 mmers1 / mmers2 ; naive_impl/kmer.rs:560-579 via the pinned hasher
+        auto m1 = ctx.upload({std::string("AACCAAA")}).minimizers(5, 3, 5);
+        CHECK(m1.first.size() == 3 && m1.first[0] == 0b010000 && m1.first[1] == 0b010100 && m1.first[2] == 0);
+        CHECK(m1.second[0] == 0 && m1.second[1] == 1 && m1.second[2] == 4);
+        auto m2 = ctx.upload({std::string("CACACACCAC")}).minimizers(7, 3, 3);
+        CHECK(m2.second.size() == 4 && m2.second[0] == 1 && m2.second[1] == 1 && m2.second[2] == 3 && m2.second[3] == 3);
+        auto mw = ctx.minimizer_word({kmer_word("ACTTGAT")}, 7, 3, 3);
+        CHECK(mw.first[0] == kmer_word("ACT") && mw.second[0] == 0);
+    }
+    {  // seq_vector.rs:342-358 iter_kmers on the packed store
+        auto b = ctx.upload({std::string("ACTTGAT")});
+        b.to_packed();
+        auto res = b.canonical_kmers(3, true);
+        CHECK(res.fw.size() == 5 && res.fw[0] == kmer_word("act") && res.fw[4] == kmer_word("gat"));
+        auto km = b.get_kmers_u64(3, {}, {0, 2, 4, 5});
+        CHECK(km[0] == kmer_word("act") && km[1] == kmer_word("ttg") && km[2] == kmer_word("gat") && km[3] == KMB_SENTINEL);
+    }
     std::printf(failures ? "FAILED (%d)\n" : "OK\n", failures);
     return failures ? 1 : 0;
 }
