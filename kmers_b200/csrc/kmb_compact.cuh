@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kExtractThreads) compact_fixed_kernel(const Fi
     __shared__ uint32_t s_cnt[kItemsPerCta + 1];
     __shared__ uint32_t s_warp[kExtractThreads / 32];
     Eng eng(ep, s_cnt, s_warp);
-    fixed_body(g, enc, eng, tile);
+    fixed_body(g, enc, eng, tile, blockIdx.x);
     eng.finish();
 }
 
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kExtractThreads) compact_csr_kernel(const CsrG
     uint64_t* c_off = reinterpret_cast<uint64_t*>(tile + g.tile_entries);
     uint64_t* c_win = c_off + (kCsrCache + 2);
     Eng eng(ep, s_cnt, s_warp);
-    csr_body(g, enc, eng, tile, c_off, c_win, &pass);
+    csr_body(g, enc, eng, tile, c_off, c_win, &pass, blockIdx.x);
     eng.finish();
 }
 

@@ -39,7 +39,8 @@ struct OutPtrs {
     uint64_t* fw;
     uint64_t* rc;
     unsigned long long* digest;  // n_valid, checksum_canon, checksum_hash
-    unsigned long long* hist;    // fused histogram mode
+    unsigned long long* hist;    // fused histogram mode: global u64 bins
+    unsigned int* s_hist;        // MODE 2: this CTA's bins in shared memory, two 16-bit counters per word
     uint32_t hist_shift;         // 2K - hist_bits
     uint32_t vec_ok;             // output pointers are 32-byte aligned
 };
@@ -115,6 +116,18 @@ struct Acc {
     uint32_t valid = 0;
 };
 
+// MODE 2: one count into this CTA's shared-memory histogram.  Two 16-bit counters share a 32-bit word; when a
+// counter wraps (the returned old value shows 0xFFFF) the 65536 it stood for moves to the global bin at once, and a
+// carry out of the low half into the high half is taken back -- so the shared counts stay exact modulo 2^16.
+__device__ __forceinline__ void smem_hist_add(const OutPtrs& o, uint32_t bin) {
+    const uint32_t sh = (bin & 1u) * 16;
+    const uint32_t old = atomicAdd(o.s_hist + (bin >> 1), 1u << sh);
+    if (((old >> sh) & 0xFFFFu) == 0xFFFFu) {
+        if (sh == 0) atomicSub(o.s_hist + (bin >> 1), 1u << 16);  // undo the carry into the neighbouring counter
+        atomicAdd(o.hist + bin, 65536ull);
+    }
+}
+
 // The kRun windows of one work item = kRun consecutive, 64-byte-aligned output slots.
 // TWO: the item straddles a read boundary: windows j < n_first come from span A (the tail of
 //      one read), the rest from span B (the head of the next; B is loaded n_first bases early so
@@ -132,10 +145,11 @@ __device__ __forceinline__ void emit_run(const Span& A, const Span& B, uint32_t 
         Window w = make_window<KHI>(s, j, wc);
         bool ok = true;
         if (CHECK) ok = (((uint32_t)(s.inv >> j)) & wc.kmask) == 0u;
-        if (DIGEST || MODE == 1) {
+        if (DIGEST || MODE != 0) {
             const bool counted = ok && (uint32_t)j < nwin;
             if (DIGEST && counted) { acc.canon += w.canon; acc.hash += w.hash; acc.valid += 1; }
             if (MODE == 1 && counted) atomicAdd(o.hist + (w.hash >> o.hist_shift), 1ull);
+            if (MODE == 2 && counted) smem_hist_add(o, (uint32_t)(w.hash >> o.hist_shift));
         }
         if (MODE == 0) {
             oc[j] = (CHECK && !ok) ? ~0ull : w.canon;
@@ -190,6 +204,10 @@ __device__ __forceinline__ void emit_single(const uint2* tile, uint32_t rel, con
         if (ok) atomicAdd(o.hist + (w.hash >> o.hist_shift), 1ull);
         return;
     }
+    if (MODE == 2) {
+        if (ok) smem_hist_add(o, (uint32_t)(w.hash >> o.hist_shift));
+        return;
+    }
     if (o.canon) st_stream_u64(o.canon + slot, ok ? w.canon : ~0ull);
     if (o.hash) st_stream_u64(o.hash + slot, ok ? w.hash : ~0ull);
     if (FWRC) {
@@ -199,7 +217,7 @@ __device__ __forceinline__ void emit_single(const uint2* tile, uint32_t rel, con
 }
 
 template <bool DIGEST>
-__device__ __forceinline__ void reduce_digest(unsigned long long (&red)[3][kExtractThreads / 32],
+__device__ __forceinline__ void reduce_digest(unsigned long long (&red)[3][32],
                                               unsigned long long* digest, const Acc& acc) {
     if (!DIGEST) return;
     const uint64_t v = warp_sum64(acc.valid), c = warp_sum64(acc.canon), h = warp_sum64(acc.hash);
@@ -208,7 +226,7 @@ __device__ __forceinline__ void reduce_digest(unsigned long long (&red)[3][kExtr
     __syncthreads();
     if (threadIdx.x < 3) {
         unsigned long long s = 0;
-        for (int w = 0; w < kExtractThreads / 32; ++w) s += red[threadIdx.x][w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
         atomicAdd(digest + threadIdx.x, s);
     }
 }
@@ -237,7 +255,7 @@ struct NarrowEng {
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
         emit_single<VALIDATE, DIGEST, FWRC, MODE, KHI>(tile, rel, p.wc, p.out, slot, acc);
     }
-    __device__ __forceinline__ void finish(unsigned long long (&red)[3][kExtractThreads / 32]) {
+    __device__ __forceinline__ void finish(unsigned long long (&red)[3][32]) {
         reduce_digest<DIGEST>(red, p.out.digest, acc);
     }
 };
@@ -245,9 +263,9 @@ struct NarrowEng {
 template <class Eng>
 __global__ void __launch_bounds__(kExtractThreads) fixed_kernel(const FixedGeom g, const EncDesc enc, const typename Eng::Params ep) {
     extern __shared__ uint2 tile[];
-    __shared__ unsigned long long red[3][kExtractThreads / 32];
+    __shared__ unsigned long long red[3][32];
     Eng eng(ep);
-    fixed_body(g, enc, eng, tile);
+    fixed_body(g, enc, eng, tile, blockIdx.x);
     eng.finish(red);
 }
 
@@ -255,12 +273,68 @@ __global__ void __launch_bounds__(kExtractThreads) fixed_kernel(const FixedGeom 
 template <class Eng>
 __global__ void __launch_bounds__(kExtractThreads) csr_kernel(const CsrGeom g, const EncDesc enc, const typename Eng::Params ep) {
     extern __shared__ uint2 tile[];
-    __shared__ unsigned long long red[3][kExtractThreads / 32];
+    __shared__ unsigned long long red[3][32];
     __shared__ CsrPass pass;
     uint64_t* c_off = reinterpret_cast<uint64_t*>(tile + g.tile_entries);
     uint64_t* c_win = c_off + (kCsrCache + 2);
     Eng eng(ep);
-    csr_body(g, enc, eng, tile, c_off, c_win, &pass);
+    csr_body(g, enc, eng, tile, c_off, c_win, &pass, blockIdx.x);
+    eng.finish(red);
+}
+
+// ---------------------------------------------------------------------------
+// Fused histogram with shared-memory bins (hist_bits <= 16): a persistent grid (a few CTAs per SM) walks the
+// tiles; every CTA counts into its own 2^hist_bits x 16-bit shared histogram and adds it to the global u64 bins
+// once at the end -- global atomics drop from one per k-mer to bins per CTA.
+// dynamic shared memory: [tile (+ CSR tables)] then the histogram words.
+// ---------------------------------------------------------------------------
+constexpr int kHistThreads = 1024;  // one big CTA per SM shares the 128 KiB histogram: occupancy comes from its 32 warps
+
+template <class Eng>
+__device__ __forceinline__ void smem_hist_flush(unsigned int* s_hist, unsigned long long* hist, uint32_t n_bins) {
+    for (uint32_t w = threadIdx.x; w < (n_bins + 1) / 2; w += blockDim.x) {
+        const uint32_t v = s_hist[w];
+        if (v & 0xFFFFu) atomicAdd(hist + 2 * w, (unsigned long long)(v & 0xFFFFu));
+        if (v >> 16) atomicAdd(hist + 2 * w + 1, (unsigned long long)(v >> 16));
+    }
+}
+
+template <class Eng>
+__global__ void __launch_bounds__(kHistThreads) hist_fixed_kernel(const FixedGeom g, const EncDesc enc, typename Eng::Params ep,
+                                                                      uint32_t n_tiles, uint32_t tile_words, uint32_t n_bins) {
+    extern __shared__ uint2 tile[];
+    __shared__ unsigned long long red[3][32];
+    unsigned int* s_hist = reinterpret_cast<unsigned int*>(tile + tile_words);
+    for (uint32_t w = threadIdx.x; w < (n_bins + 1) / 2; w += blockDim.x) s_hist[w] = 0;
+    ep.out.s_hist = s_hist;
+    __syncthreads();
+    Eng eng(ep);
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        fixed_body(g, enc, eng, tile, t);
+        __syncthreads();  // the next tile overwrites the staged stretch
+    }
+    smem_hist_flush<Eng>(s_hist, ep.out.hist, n_bins);
+    eng.finish(red);
+}
+
+template <class Eng>
+__global__ void __launch_bounds__(kHistThreads) hist_csr_kernel(const CsrGeom g, const EncDesc enc, typename Eng::Params ep,
+                                                                    uint32_t n_tiles, uint32_t n_bins) {
+    extern __shared__ uint2 tile[];
+    __shared__ unsigned long long red[3][32];
+    __shared__ CsrPass pass;
+    uint64_t* c_off = reinterpret_cast<uint64_t*>(tile + g.tile_entries);
+    uint64_t* c_win = c_off + (kCsrCache + 2);
+    unsigned int* s_hist = reinterpret_cast<unsigned int*>(c_win + (kCsrCache + 2));
+    for (uint32_t w = threadIdx.x; w < (n_bins + 1) / 2; w += blockDim.x) s_hist[w] = 0;
+    ep.out.s_hist = s_hist;
+    __syncthreads();
+    Eng eng(ep);
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        csr_body(g, enc, eng, tile, c_off, c_win, &pass, t);
+        __syncthreads();
+    }
+    smem_hist_flush<Eng>(s_hist, ep.out.hist, n_bins);
     eng.finish(red);
 }
 

@@ -110,14 +110,10 @@ __device__ __forceinline__ WideWindow wide_window(const WideSpan<NW32>& s, int j
     }
     f[NW32 - 2] &= wc.mask_a; r[NW32 - 2] &= wc.mask_a;
     f[NW32 - 1] &= wc.mask_b; r[NW32 - 1] &= wc.mask_b;
-    // unsigned compare of the 2K-bit integers, top word first
-    bool fw_less = f[NW32 - 1] < r[NW32 - 1];
-    bool eq = f[NW32 - 1] == r[NW32 - 1];
-#pragma unroll
-    for (int i = NW32 - 2; i >= 0; --i) {
-        fw_less = fw_less || (eq && f[i] < r[i]);
-        eq = eq && f[i] == r[i];
-    }
+    // unsigned compare of the 2K-bit integers (strict '<', as canonical_kmer.rs:114): one carry-chained compare
+    const unsigned __int128 fw128 = ((unsigned __int128)mk64(f[2], f[3]) << 64) | mk64(f[0], f[1]);
+    const unsigned __int128 rc128 = ((unsigned __int128)mk64(r[2], r[3]) << 64) | mk64(r[0], r[1]);
+    const bool fw_less = fw128 < rc128;
     uint32_t c[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < NW32; ++i) {
@@ -193,7 +189,7 @@ __device__ __forceinline__ void emit_wide_single(const uint2* tile, uint32_t rel
 }
 
 template <bool DIGEST>
-__device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][kExtractThreads / 32], unsigned long long* digest,
+__device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][32], unsigned long long* digest,
                                             const WideAcc& acc) {
     if (!DIGEST) return;
     const uint64_t v = warp_sum64(acc.valid), c = warp_sum64(acc.canon), h = warp_sum64(acc.hash);
@@ -202,7 +198,7 @@ __device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][kExtrac
     __syncthreads();
     if (threadIdx.x < 3) {
         unsigned long long s = 0;
-        for (int w = 0; w < kExtractThreads / 32; ++w) s += red[threadIdx.x][w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
         atomicAdd(digest + threadIdx.x, s);
     }
 }
@@ -228,7 +224,7 @@ struct WideEng {
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
         emit_wide_single<NW32, VALIDATE, DIGEST>(tile, rel, p.wc, p.out, slot, acc);
     }
-    __device__ __forceinline__ void finish(unsigned long long (&red)[3][kExtractThreads / 32]) {
+    __device__ __forceinline__ void finish(unsigned long long (&red)[3][32]) {
         wide_reduce<DIGEST>(red, p.out.digest, acc);
     }
 };

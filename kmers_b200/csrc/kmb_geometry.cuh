@@ -177,10 +177,10 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
 }
 
 template <class Eng>
-__device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& enc, Eng& eng, uint2* tile) {
+__device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint32_t tile_idx) {
     const uint32_t K = eng.K();
     const uint32_t slots_per_cta = g.items_per_cta * kRun;
-    const uint64_t slot_base = (uint64_t)blockIdx.x * slots_per_cta;
+    const uint64_t slot_base = (uint64_t)tile_idx * slots_per_cta;
     const uint32_t n_slots = (uint32_t)min((uint64_t)slots_per_cta, g.total_slots - slot_base);
     uint64_t r_first;
     if (g.W == 1) r_first = slot_base;
@@ -201,7 +201,7 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     //      kRun windows, a run of single windows
     const uint32_t n_items = (n_slots + kRun - 1) / kRun;
     auto visit = [&](auto&& one, auto&& two, auto&& single) {
-        for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
+        for (uint32_t li = threadIdx.x; li < n_items; li += blockDim.x) {
             const uint32_t u = p_first + li * kRun;           // first slot, counted from window 0 of read r_first
             const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
             const uint32_t pos = u - q * g.W32;                 // window position inside its read
@@ -272,15 +272,15 @@ struct CsrPass {  // one staged stretch: slots [slot_lo, slot_hi) of reads [r_lo
 
 template <class Eng>
 __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint64_t* c_off,
-                                         uint64_t* c_win, CsrPass* pass) {
+                                         uint64_t* c_win, CsrPass* pass, uint32_t tile_idx) {
     const uint32_t K = eng.K();
     const uint64_t slots_per_cta = (uint64_t)g.items_per_cta * kRun;
-    const uint64_t slot_begin = (uint64_t)blockIdx.x * slots_per_cta;
+    const uint64_t slot_begin = (uint64_t)tile_idx * slots_per_cta;
     const uint64_t slot_end = min(g.total_slots, slot_begin + slots_per_cta);
     const uint32_t tile_bases = (g.tile_entries - Eng::kSpanEntries - 1) * 16;  // bases one pass can stage
 
     // reads this CTA can touch; their offsets go to shared memory when they fit (the common case)
-    const uint64_t R_lo = g.first_read[blockIdx.x], R_hi = g.first_read[blockIdx.x + 1];
+    const uint64_t R_lo = g.first_read[tile_idx], R_hi = g.first_read[tile_idx + 1];
     const uint64_t* off = g.offsets;  // tables indexed by absolute read number
     const uint64_t* win = g.win_offsets;
     if (R_hi - R_lo + 2 <= (uint64_t)kCsrCache + 2) {
@@ -324,7 +324,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
         const uint32_t n_items = (n_slots + kRun - 1) / kRun;
         auto visit = [&](auto&& one, auto&& two, auto&& single) {
-            for (uint32_t li = threadIdx.x; li < n_items; li += kExtractThreads) {
+            for (uint32_t li = threadIdx.x; li < n_items; li += blockDim.x) {
                 const uint64_t slot0 = ps.slot_lo + (uint64_t)li * kRun;
                 const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
                 uint64_t r = last_le(win, ps.r_lo, ps.r_hi, slot0);

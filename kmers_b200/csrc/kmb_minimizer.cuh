@@ -161,7 +161,7 @@ struct MinimizerEng {
         if (p.out.mmer) st_stream_u64(p.out.mmer + slot, ok ? (bits96(s.a0, s.a1, s.a2, 2 * best[0]) & p.mc.wmask) : ~0ull);
         if (p.out.pos) p.out.pos[slot] = ok ? (uint32_t)ic.pos_a + best[0] : 0xFFFFFFFFu;
     }
-    __device__ __forceinline__ void finish(unsigned long long (&)[3][kExtractThreads / 32]) {}
+    __device__ __forceinline__ void finish(unsigned long long (&)[3][32]) {}
 };
 
 // Kmer::minimizer_word (naive_impl/kmer.rs:170-191) on every word: leftmost width-mer of minimum LexHash.

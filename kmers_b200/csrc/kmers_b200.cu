@@ -4,6 +4,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -608,6 +610,34 @@ static cudaError_t launch_narrow(bool validate, bool digest, bool fwrc, bool khi
     return cudaErrorInvalidValue;
 }
 
+// MODE 2 (shared-memory bins): persistent grid, opt-in dynamic shared memory above 48 KiB
+template <class Eng>
+static cudaError_t launch_hist_eng(const FixedGeom* fg, const CsrGeom* cg, unsigned grid, size_t smem, uint32_t n_tiles,
+                                   uint32_t tile_words, uint32_t n_bins, cudaStream_t st, const EncDesc& enc, const NarrowParams& ep) {
+    cudaError_t e;
+    if (fg) {
+        e = cudaFuncSetAttribute(hist_fixed_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hist_fixed_kernel<Eng><<<grid, kHistThreads, smem, st>>>(*fg, enc, ep, n_tiles, tile_words, n_bins);
+    } else {
+        e = cudaFuncSetAttribute(hist_csr_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hist_csr_kernel<Eng><<<grid, kHistThreads, smem, st>>>(*cg, enc, ep, n_tiles, n_bins);
+    }
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_hist_smem(bool validate, bool digest, bool khi, const FixedGeom* fg, const CsrGeom* cg, unsigned grid,
+                                    size_t smem, uint32_t n_tiles, uint32_t tile_words, uint32_t n_bins, cudaStream_t st,
+                                    const EncDesc& enc, const NarrowParams& ep) {
+#define KMB_CASE(V, D, H) \
+    if (validate == V && digest == D && khi == H) return launch_hist_eng<NarrowEng<V, D, false, 2, H>>(fg, cg, grid, smem, n_tiles, tile_words, n_bins, st, enc, ep);
+    KMB_CASE(true, false, true) KMB_CASE(true, false, false) KMB_CASE(true, true, true) KMB_CASE(true, true, false)
+    KMB_CASE(false, false, true) KMB_CASE(false, false, false) KMB_CASE(false, true, true) KMB_CASE(false, true, false)
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
+}
+
 static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
     WinConst wc{};
     wc.K = k;
@@ -649,8 +679,28 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
         if (r) return r;
         if (cg.total_slots == 0) return KMB_OK;
     }
-    cudaError_t e = hist ? launch_narrow<1>(validate, want_digest, false, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
-                         : launch_narrow<0>(validate, want_digest, fwrc, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
+    cudaError_t e;
+    if (hist && hist_bits <= 16 && !getenv("KMB_HIST_GLOBAL")) {
+        // shared-memory bins: a persistent grid of as many CTAs as fit (tile + 2 bytes per bin of shared memory each)
+        const uint32_t n_bins = 1u << hist_bits;
+        const size_t smem = l.smem + (size_t)n_bins * 2 + 16;
+        int sms = 148, max_smem = 227 * 1024;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+        if (smem + 2048 <= (size_t)max_smem) {
+            int per_sm = (int)((size_t)(228 * 1024) / (smem + 2048));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 2048 / kHistThreads) per_sm = 2048 / kHistThreads;
+            const unsigned grid = (unsigned)std::min<uint64_t>(l.grid, (uint64_t)sms * per_sm);
+            e = launch_hist_smem(validate, want_digest, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, grid, smem, l.grid,
+                                 (uint32_t)(l.smem / sizeof(uint2)), n_bins, st, enc, ep);
+            CK(ctx, e);
+            ctx->launches++;
+            return KMB_OK;
+        }
+    }
+    e = hist ? launch_narrow<1>(validate, want_digest, false, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
+             : launch_narrow<0>(validate, want_digest, fwrc, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
     CK(ctx, e);
     ctx->launches++;
     return KMB_OK;

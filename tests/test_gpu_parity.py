@@ -442,3 +442,18 @@ def test_pack_tiled_kernel_lengths(ctx, ko):
         nw = kb.word_for_k(wb, L)
         want = np.concatenate([ko.encode(ko.NAIVE["TGCA"], bases[r * L:(r + 1) * L].tobytes(), wb, nw) for r in range(n)])
         assert np.array_equal(img, want), (L, wb)
+
+
+@pytest.mark.parametrize("bits", [4, 12, 16, 20])
+def test_histogram_without_digest_and_bin_counts(ctx, ko, bits):
+    """Shared-memory bins (<= 16 bits) and global bins (> 16), with and without the digest; a counter that
+    wraps its 16-bit shared half (one bin takes > 65535 windows) still ends exact."""
+    n, L, k = 3000, 150, 31
+    bases = np.full(n * L, ord("A"), dtype=np.uint8)  # every window is poly-A: one bin takes all 360 000 counts
+    bases[: 500 * L] = ko.generate_bases(5, 0, 500 * L)
+    ref = ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, hist_bits=bits, n_threads=4, materialize=False)
+    b = ctx.upload(bases, fixed_len=L)
+    for dg in (False, True):
+        hist, d = b.histogram(k, bits, digest=dg, to="host")
+        assert np.array_equal(hist, ref["hist"]), (bits, dg)
+        assert int(hist.max()) > 65535
