@@ -26,6 +26,20 @@ struct CompactParams {
     CompactOut out;
 };
 
+constexpr int kCompactRound = kExtractThreads * kRun;  // entries one round of items can emit (2048)
+
+// Shared memory of the compaction kernels beyond the tile: per-item counts, and the staging buffers through which
+// a round's entries reach global memory as coalesced stores (each thread's <= 8 entries land at arbitrary,
+// unaligned indices; storing them directly would touch every 32-byte sector 4-8 times).
+struct CompactShared {
+    uint64_t canon[kCompactRound];
+    uint64_t hash[kCompactRound];
+    int32_t pos[kCompactRound];
+    uint32_t cnt[kItemsPerCta + 1];
+    uint32_t round_off[kItemsPerCta / kExtractThreads + 2];  // exclusive offset of every round's first item, and the total
+    uint32_t warp_tot[kExtractThreads / 32];
+};
+
 template <bool VALIDATE, bool KHI, bool COUNT_ONLY>
 struct CompactEng {
     using Params = CompactParams;
@@ -34,13 +48,12 @@ struct CompactEng {
     static constexpr bool kTwoPhase = true, kCountOnly = COUNT_ONLY;
     static constexpr int kSpanEntries = 4;
     const CompactParams& p;
-    uint32_t* cnt;           // shared: kItemsPerCta + 1 counts -> exclusive offsets after scan()
-    uint32_t* warp_tot;      // shared: per-warp totals of the scan
+    CompactShared& sh;
     uint64_t pass_base = 0;      // valid windows of this CTA's passes so far
     uint64_t cur_pass_base = 0;  // ... before the current pass
     uint64_t cta_base = 0;       // valid windows of all earlier CTAs
 
-    __device__ CompactEng(const CompactParams& params, uint32_t* s_cnt, uint32_t* s_warp) : p(params), cnt(s_cnt), warp_tot(s_warp) {
+    __device__ CompactEng(const CompactParams& params, CompactShared& shared) : p(params), sh(shared) {
         if (!COUNT_ONLY) cta_base = p.out.cta_counts[blockIdx.x];
     }
     __device__ __forceinline__ uint32_t K() const { return p.wc.K; }
@@ -48,9 +61,9 @@ struct CompactEng {
     __device__ __forceinline__ bool dirty(const Span& s) const { return s.inv != 0ull; }
 
     __device__ __forceinline__ void begin_pass(uint32_t n_items) {
-        for (uint32_t i = threadIdx.x; i <= n_items; i += blockDim.x) cnt[i] = 0;
+        for (uint32_t i = threadIdx.x; i <= n_items; i += blockDim.x) sh.cnt[i] = 0;
     }
-    __device__ __forceinline__ void count(uint32_t li, uint32_t c) { cnt[li] += c; }  // one thread owns item li
+    __device__ __forceinline__ void count(uint32_t li, uint32_t c) { sh.cnt[li] += c; }  // one thread owns item li
 
     // exclusive scan of cnt[0 .. n_items) in place; cnt[n_items] = total.  Called by all threads between barriers.
     __device__ __forceinline__ void scan(uint32_t n_items) {
@@ -58,7 +71,7 @@ struct CompactEng {
         const uint32_t base = threadIdx.x * PER;
         uint32_t v[PER], sum = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { v[i] = (base + i < n_items) ? cnt[base + i] : 0u; sum += v[i]; }
+        for (int i = 0; i < PER; ++i) { v[i] = (base + i < n_items) ? sh.cnt[base + i] : 0u; sum += v[i]; }
         uint32_t incl = sum;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -66,78 +79,98 @@ struct CompactEng {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) warp_tot[warp] = incl;
+        if (lane == 31) sh.warp_tot[warp] = incl;
         __syncthreads();
         uint32_t before = 0, total = 0;
-        for (int w = 0; w < kExtractThreads / 32; ++w) { const uint32_t t = warp_tot[w]; if (w < warp) before += t; total += t; }
+        for (int w = 0; w < kExtractThreads / 32; ++w) { const uint32_t t = sh.warp_tot[w]; if (w < warp) before += t; total += t; }
         uint32_t run = before + incl - sum;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { if (base + i < n_items) cnt[base + i] = run; run += v[i]; }
-        __syncthreads();  // warp_tot / cnt are re-used by the next pass
-        if (threadIdx.x == 0) cnt[n_items] = total;
-        const uint64_t prev = pass_base;
+        for (int i = 0; i < PER; ++i) { if (base + i < n_items) sh.cnt[base + i] = run; run += v[i]; }
+        if (threadIdx.x == 0) sh.cnt[n_items] = total;
+        __syncthreads();
+        // offsets at which the rounds of items start (the emit phase bumps cnt[] for single-window items)
+        const uint32_t rounds = (n_items + kExtractThreads - 1) / kExtractThreads;
+        if (threadIdx.x <= rounds) sh.round_off[threadIdx.x] = sh.cnt[min(threadIdx.x * kExtractThreads, n_items)];
+        cur_pass_base = pass_base;
         pass_base += total;
-        cur_pass_base = prev;
     }
-    __device__ __forceinline__ void put(uint64_t o, const Window& w, uint64_t pos) const {
-        if (p.out.canon) p.out.canon[o] = w.canon;
-        if (p.out.hash) p.out.hash[o] = w.hash;
-        if (p.out.pos) p.out.pos[o] = (int32_t)pos;
+
+    // stage one entry of the current round (local index = its offset inside the round)
+    __device__ __forceinline__ void put(uint32_t local, const Window& w, uint64_t pos) const {
+        sh.canon[local] = w.canon;
+        sh.hash[local] = w.hash;
+        sh.pos[local] = (int32_t)pos;
     }
 
     template <bool TWO, bool CHECK>
     __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t, uint32_t nwin, const ItemCtx& ic) {
-        uint64_t o = cta_base + cur_pass_base + cnt[ic.li];
-        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o;  // this item opens read r_a
+        const uint32_t off = sh.cnt[ic.li];
+        uint32_t local = off - sh.round_off[ic.li / kExtractThreads];
+        const uint64_t o0 = cta_base + cur_pass_base + off;  // global index of this item's first entry
+        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o0;  // this item opens read r_a
+        uint32_t emitted = 0;
 #pragma unroll
         for (int j = 0; j < kRun; ++j) {
             if ((uint32_t)j < nwin) {
                 const bool second = TWO && (uint32_t)j >= n_first;
-                if (TWO && (uint32_t)j == n_first && p.out.emit_offsets) p.out.emit_offsets[ic.r_b] = o;  // opens read r_b
+                if (TWO && (uint32_t)j == n_first && p.out.emit_offsets) p.out.emit_offsets[ic.r_b] = o0 + emitted;  // opens read r_b
                 const Span s = second ? b : a;
                 const bool ok = !CHECK || (((uint32_t)(s.inv >> j)) & p.wc.kmask) == 0u;
                 if (ok) {
-                    put(o, make_window<KHI>(s, j, p.wc), second ? (uint64_t)(j - n_first) : ic.pos_a + j);
-                    ++o;
+                    put(local + emitted, make_window<KHI>(s, j, p.wc), second ? (uint64_t)(j - n_first) : ic.pos_a + j);
+                    ++emitted;
                 }
             }
         }
     }
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t, const ItemCtx& ic) {
         // windows of one item arrive in order; the running index lives in cnt[li] (owned by this thread)
-        const uint64_t o = cta_base + cur_pass_base + cnt[ic.li];
-        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o;
+        const uint32_t off = sh.cnt[ic.li];
+        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = cta_base + cur_pass_base + off;
         const Span s = load_span<VALIDATE>(tile, rel, p.wc);
         const bool ok = !VALIDATE || (((uint32_t)s.inv) & p.wc.kmask) == 0u;
         if (ok) {
-            put(o, make_window<KHI>(s, 0, p.wc), ic.pos_a);
-            cnt[ic.li] += 1;
+            put(off - sh.round_off[ic.li / kExtractThreads], make_window<KHI>(s, 0, p.wc), ic.pos_a);
+            sh.cnt[ic.li] = off + 1;
         }
+    }
+    // all threads, once per round: the staged entries of the round leave as coalesced stores
+    __device__ __forceinline__ void round_end(uint32_t q_round, uint32_t) {
+        __syncthreads();
+        const uint32_t lo = sh.round_off[q_round], n = sh.round_off[q_round + 1] - lo;
+        const uint64_t g0 = cta_base + cur_pass_base + lo;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            if (p.out.canon) p.out.canon[g0 + e] = sh.canon[e];
+            if (p.out.hash) p.out.hash[g0 + e] = sh.hash[e];
+            if (p.out.pos) p.out.pos[g0 + e] = sh.pos[e];
+        }
+        __syncthreads();  // the next round re-uses the staging buffers
     }
     __device__ __forceinline__ void finish() {
         if (COUNT_ONLY && threadIdx.x == 0) p.out.cta_counts[blockIdx.x] = pass_base;
     }
 };
 
+// dynamic shared memory: [tile (+ CSR tables)] then CompactShared
 template <class Eng>
-__global__ void __launch_bounds__(kExtractThreads) compact_fixed_kernel(const FixedGeom g, const EncDesc enc, const CompactParams ep) {
+__global__ void __launch_bounds__(kExtractThreads) compact_fixed_kernel(const FixedGeom g, const EncDesc enc, const CompactParams ep,
+                                                                         uint32_t tile_bytes) {
     extern __shared__ uint2 tile[];
-    __shared__ uint32_t s_cnt[kItemsPerCta + 1];
-    __shared__ uint32_t s_warp[kExtractThreads / 32];
-    Eng eng(ep, s_cnt, s_warp);
+    CompactShared& sh = *reinterpret_cast<CompactShared*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);
+    Eng eng(ep, sh);
     fixed_body(g, enc, eng, tile, blockIdx.x);
     eng.finish();
 }
 
 template <class Eng>
-__global__ void __launch_bounds__(kExtractThreads) compact_csr_kernel(const CsrGeom g, const EncDesc enc, const CompactParams ep) {
+__global__ void __launch_bounds__(kExtractThreads) compact_csr_kernel(const CsrGeom g, const EncDesc enc, const CompactParams ep,
+                                                                       uint32_t tile_bytes) {
     extern __shared__ uint2 tile[];
-    __shared__ uint32_t s_cnt[kItemsPerCta + 1];
-    __shared__ uint32_t s_warp[kExtractThreads / 32];
     __shared__ CsrPass pass;
     uint64_t* c_off = reinterpret_cast<uint64_t*>(tile + g.tile_entries);
     uint64_t* c_win = c_off + (kCsrCache + 2);
-    Eng eng(ep, s_cnt, s_warp);
+    CompactShared& sh = *reinterpret_cast<CompactShared*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);
+    Eng eng(ep, sh);
     csr_body(g, enc, eng, tile, c_off, c_win, &pass, blockIdx.x);
     eng.finish();
 }

@@ -145,6 +145,24 @@ __device__ __forceinline__ uint32_t div_w(uint32_t u, const FixedGeom& g, uint32
     return __umulhi(u, g.w_magic);
 }
 
+// The item loop.  Plain engines stride over the items.  Two-phase engines need every thread of the CTA to reach
+// round_end (it holds barriers) the same number of times and from ONE call site (`__syncthreads` is an aligned
+// barrier: all lanes of a warp must execute the same instruction), so they run CTA-uniform rounds.
+template <bool ROUNDS, class Item, class RoundEnd>
+__device__ __forceinline__ void for_each_item(uint32_t n_items, Item&& item, RoundEnd&& round_end) {
+    if constexpr (ROUNDS) {
+        const uint32_t rounds = (n_items + blockDim.x - 1) / blockDim.x;
+        for (uint32_t q_round = 0; q_round < rounds; ++q_round) {
+            const uint32_t li = q_round * blockDim.x + threadIdx.x;
+            if (li < n_items) item(li);
+            __syncwarp();
+            round_end(q_round);
+        }
+    } else {
+        for (uint32_t li = threadIdx.x; li < n_items; li += blockDim.x) item(li);
+    }
+}
+
 // One pass over the items of a staged tile.  Two-phase engines (compaction) first count the valid
 // windows of every item, scan the counts CTA-wide, then emit at the scanned offsets.
 template <class Eng, class Visit>
@@ -158,7 +176,8 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
                   eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
                                        count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin)); },
               [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
-                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1)); });
+                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1)); },
+              [](uint32_t) {});
         __syncthreads();
         eng.scan(n_items);
         __syncthreads();
@@ -173,7 +192,8 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
               const typename Eng::Span b = eng.load(tile, rel_b);
               if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
               else eng.template run<true, false>(a, b, left, slot0, nwin, ic); },
-          [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); });
+          [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); },
+          [&](uint32_t q_round) { if constexpr (Eng::kTwoPhase) eng.round_end(q_round, n_items); });
 }
 
 template <class Eng>
@@ -200,8 +220,8 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     // ---- phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than
     //      kRun windows, a run of single windows
     const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-    auto visit = [&](auto&& one, auto&& two, auto&& single) {
-        for (uint32_t li = threadIdx.x; li < n_items; li += blockDim.x) {
+    auto visit = [&](auto&& one, auto&& two, auto&& single, auto&& round_end) {
+        auto item = [&](uint32_t li) {
             const uint32_t u = p_first + li * kRun;           // first slot, counted from window 0 of read r_first
             const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
             const uint32_t pos = u - q * g.W32;                 // window position inside its read
@@ -221,7 +241,8 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
                     single(qj * g.L32 + pj - p_first + mis, slot0 + j, ItemCtx{li, r_first + qj, pj, 0});
                 }
             }
-        }
+        };
+        for_each_item<Eng::kTwoPhase>(n_items, item, round_end);
     };
     run_pass(eng, tile, K, n_items, visit);
 }
@@ -323,8 +344,8 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
 
         const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
         const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-        auto visit = [&](auto&& one, auto&& two, auto&& single) {
-            for (uint32_t li = threadIdx.x; li < n_items; li += blockDim.x) {
+        auto visit = [&](auto&& one, auto&& two, auto&& single, auto&& round_end) {
+            auto item = [&](uint32_t li) {
                 const uint64_t slot0 = ps.slot_lo + (uint64_t)li * kRun;
                 const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
                 uint64_t r = last_le(win, ps.r_lo, ps.r_hi, slot0);
@@ -333,13 +354,13 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
                 const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
                 if (left >= nwin) {
                     one(rel, slot0, nwin, ItemCtx{li, r, pos, 0});
-                    continue;
+                    return;
                 }
                 uint64_t r2 = r + 1;
                 while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
                 if (left + (win[r2 + 1] - win[r2]) >= nwin) {
                     two(rel, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left, (uint32_t)left, slot0, nwin, ItemCtx{li, r, pos, r2});
-                    continue;
+                    return;
                 }
                 // several short reads inside one item: window by window
                 uint64_t p = pos, w_r = win[r + 1] - win[r];
@@ -348,7 +369,8 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
                     single((uint32_t)(off[r] + p - ps.g0) + mis, slot0 + j, ItemCtx{li, r, p, 0});
                     ++p;
                 }
-            }
+            };
+            for_each_item<Eng::kTwoPhase>(n_items, item, round_end);
         };
         run_pass(eng, tile, K, n_items, visit);
         __syncthreads();  // the next pass overwrites the tile

@@ -762,10 +762,21 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
 template <bool COUNT_ONLY>
 static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
                                   cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
+    // dynamic shared memory = the geometry's tile (+ tables), 16-byte aligned, then CompactShared: above 48 KiB -> opt in
+    const uint32_t tile_bytes = (uint32_t)((l.smem + 15) & ~(size_t)15);
+    const size_t smem = tile_bytes + sizeof(CompactShared);
 #define KMB_CASE(V, H)                                                                                                  \
     if (validate == V && khi == H) {                                                                                    \
-        if (fg) compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, l.smem, st>>>(*fg, enc, ep); \
-        else compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, l.smem, st>>>(*cg, enc, ep);     \
+        cudaError_t e;                                                                                                  \
+        if (fg) {                                                                                                       \
+            e = cudaFuncSetAttribute(compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                             \
+            compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*fg, enc, ep, tile_bytes); \
+        } else {                                                                                                        \
+            e = cudaFuncSetAttribute(compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                             \
+            compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*cg, enc, ep, tile_bytes); \
+        }                                                                                                               \
         return cudaGetLastError();                                                                                      \
     }
     KMB_CASE(true, true) KMB_CASE(true, false) KMB_CASE(false, true) KMB_CASE(false, false)
