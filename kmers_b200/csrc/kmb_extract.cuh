@@ -134,10 +134,10 @@ __device__ __forceinline__ void smem_hist_add(const OutPtrs& o, uint32_t bin) {
 //      the same index j addresses it).
 // CHECK: some base of a span is invalid -> per-window validity + sentinel.
 // nwin: slots of this item that exist (kRun except at the very end of the batch).
-template <bool TWO, bool CHECK, bool DIGEST, bool FWRC, int MODE, bool KHI>
+template <bool TWO, bool CHECK, bool DIGEST, bool FWRC, int MODE, bool KHI, bool HASH>
 __device__ __forceinline__ void emit_run(const Span& A, const Span& B, uint32_t n_first, const WinConst& wc,
                                          const OutPtrs& o, uint64_t slot0, uint32_t nwin, Acc& acc) {
-    uint64_t oc[kRun], oh[kRun], ofw[FWRC ? kRun : 1], orc[FWRC ? kRun : 1];
+    uint64_t oc[kRun], oh[HASH ? kRun : 1], ofw[FWRC ? kRun : 1], orc[FWRC ? kRun : 1];  // HASH == false: hash_out is NULL
 #pragma unroll
     for (int j = 0; j < kRun; ++j) {
         Span s = A;
@@ -153,7 +153,7 @@ __device__ __forceinline__ void emit_run(const Span& A, const Span& B, uint32_t 
         }
         if (MODE == 0) {
             oc[j] = (CHECK && !ok) ? ~0ull : w.canon;
-            oh[j] = (CHECK && !ok) ? ~0ull : w.hash;
+            if (HASH) oh[j] = (CHECK && !ok) ? ~0ull : w.hash;
             if (FWRC) { ofw[j] = (CHECK && !ok) ? ~0ull : w.fw; orc[j] = (CHECK && !ok) ? ~0ull : w.rc; }
         }
     }
@@ -163,7 +163,7 @@ __device__ __forceinline__ void emit_run(const Span& A, const Span& B, uint32_t 
             st_stream_v4u64(o.canon + slot0, oc[0], oc[1], oc[2], oc[3]);
             st_stream_v4u64(o.canon + slot0 + 4, oc[4], oc[5], oc[6], oc[7]);
         }
-        if (o.hash) {
+        if (HASH && o.hash) {
             st_stream_v4u64(o.hash + slot0, oh[0], oh[1], oh[2], oh[3]);
             st_stream_v4u64(o.hash + slot0 + 4, oh[4], oh[5], oh[6], oh[7]);
         }
@@ -182,7 +182,7 @@ __device__ __forceinline__ void emit_run(const Span& A, const Span& B, uint32_t 
         for (int j = 0; j < kRun; ++j) {
             if ((uint32_t)j < nwin) {
                 if (o.canon) st_stream_u64(o.canon + slot0 + j, oc[j]);
-                if (o.hash) st_stream_u64(o.hash + slot0 + j, oh[j]);
+                if (HASH && o.hash) st_stream_u64(o.hash + slot0 + j, oh[j]);
                 if (FWRC) {
                     if (o.fw) st_stream_u64(o.fw + slot0 + j, ofw[j]);
                     if (o.rc) st_stream_u64(o.rc + slot0 + j, orc[j]);
@@ -235,7 +235,7 @@ __device__ __forceinline__ void reduce_digest(unsigned long long (&red)[3][32],
 // The K <= 32 engine plugged into the geometry of kmb_geometry.cuh.
 // MODE: 0 = materialise, 1 = fused histogram (nothing materialised).
 // ---------------------------------------------------------------------------
-template <bool VALIDATE, bool DIGEST, bool FWRC, int MODE, bool KHI>
+template <bool VALIDATE, bool DIGEST, bool FWRC, int MODE, bool KHI, bool HASH = true>
 struct NarrowEng {
     using Params = NarrowParams;
     using Span = kmb::Span;
@@ -250,7 +250,7 @@ struct NarrowEng {
     __device__ __forceinline__ bool dirty(const Span& s) const { return s.inv != 0ull; }
     template <bool TWO, bool CHECK>
     __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin, const ItemCtx&) {
-        emit_run<TWO, CHECK, DIGEST, FWRC, MODE, KHI>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
+        emit_run<TWO, CHECK, DIGEST, FWRC, MODE, KHI, HASH>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
     }
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
         emit_single<VALIDATE, DIGEST, FWRC, MODE, KHI>(tile, rel, p.wc, p.out, slot, acc);

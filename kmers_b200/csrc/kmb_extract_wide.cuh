@@ -110,10 +110,17 @@ __device__ __forceinline__ WideWindow wide_window(const WideSpan<NW32>& s, int j
     }
     f[NW32 - 2] &= wc.mask_a; r[NW32 - 2] &= wc.mask_a;
     f[NW32 - 1] &= wc.mask_b; r[NW32 - 1] &= wc.mask_b;
-    // unsigned compare of the 2K-bit integers (strict '<', as canonical_kmer.rs:114): one carry-chained compare
-    const unsigned __int128 fw128 = ((unsigned __int128)mk64(f[2], f[3]) << 64) | mk64(f[0], f[1]);
-    const unsigned __int128 rc128 = ((unsigned __int128)mk64(r[2], r[3]) << 64) | mk64(r[0], r[1]);
-    const bool fw_less = fw128 < rc128;
+    // unsigned compare of the 2K-bit integers (strict '<', as canonical_kmer.rs:114): fw < rc <=> fw - rc borrows.
+    // One subtract-with-borrow chain (5 instructions); the compiler's own 128-bit compare costs ~14.
+    uint32_t t_, borrow;
+    asm("sub.cc.u32 %0, %2, %6;\n\t"
+        "subc.cc.u32 %0, %3, %7;\n\t"
+        "subc.cc.u32 %0, %4, %8;\n\t"
+        "subc.cc.u32 %0, %5, %9;\n\t"
+        "subc.u32 %1, 0, 0;"
+        : "=r"(t_), "=r"(borrow)
+        : "r"(f[0]), "r"(f[1]), "r"(f[2]), "r"(f[3]), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]));
+    const bool fw_less = borrow != 0u;
     uint32_t c[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < NW32; ++i) {
@@ -139,7 +146,7 @@ struct WideAcc {
 };
 
 // kRun consecutive slots (128-byte aligned per array).  TWO / CHECK as in emit_run.
-template <int NW32, bool TWO, bool CHECK, bool DIGEST>
+template <int NW32, bool TWO, bool CHECK, bool DIGEST, bool HASH>
 __device__ __forceinline__ void emit_wide_run(const WideSpan<NW32>& A, const WideSpan<NW32>& B, uint32_t n_first,
                                               const WideConst& wc, const WideOut& o, uint64_t slot0, uint32_t nwin,
                                               WideAcc& acc) {
@@ -163,13 +170,13 @@ __device__ __forceinline__ void emit_wide_run(const WideSpan<NW32>& A, const Wid
         const uint64_t slot = slot0 + j2;
         if ((uint32_t)j2 + 1 < nwin && o.vec_ok && (slot & 1ull) == 0ull) {
             if (o.canon) st_stream_v4u64(o.canon + 2 * slot, w[0].c0, w[0].c1, w[1].c0, w[1].c1);
-            if (o.hash) st_stream_v4u64(o.hash + 2 * slot, w[0].h0, w[0].h1, w[1].h0, w[1].h1);
+            if (HASH && o.hash) st_stream_v4u64(o.hash + 2 * slot, w[0].h0, w[0].h1, w[1].h0, w[1].h1);
         } else {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 if ((uint32_t)(j2 + t) < nwin) {
                     if (o.canon) st_stream_v2u64(o.canon + 2 * (slot + t), w[t].c0, w[t].c1);
-                    if (o.hash) st_stream_v2u64(o.hash + 2 * (slot + t), w[t].h0, w[t].h1);
+                    if (HASH && o.hash) st_stream_v2u64(o.hash + 2 * (slot + t), w[t].h0, w[t].h1);
                 }
             }
         }
@@ -204,7 +211,7 @@ __device__ __forceinline__ void wide_reduce(unsigned long long (&red)[3][32], un
 }
 
 // The two-word engine plugged into the geometry of kmb_geometry.cuh (kernels: fixed_kernel / csr_kernel).
-template <int NW32, bool VALIDATE, bool DIGEST>
+template <int NW32, bool VALIDATE, bool DIGEST, bool HASH = true>
 struct WideEng {
     using Params = WideParams;
     using Span = WideSpan<NW32>;
@@ -219,7 +226,7 @@ struct WideEng {
     __device__ __forceinline__ bool dirty(const Span& s) const { return (s.inv_lo | (uint64_t)s.inv_hi) != 0ull; }
     template <bool TWO, bool CHECK>
     __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin, const ItemCtx&) {
-        emit_wide_run<NW32, TWO, CHECK, DIGEST>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
+        emit_wide_run<NW32, TWO, CHECK, DIGEST, HASH>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
     }
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
         emit_wide_single<NW32, VALIDATE, DIGEST>(tile, rel, p.wc, p.out, slot, acc);

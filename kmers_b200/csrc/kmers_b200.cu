@@ -592,10 +592,16 @@ static cudaError_t launch_eng(const FixedGeom* fg, const CsrGeom* cg, const Laun
 // ======================================================================= extract (K <= 32)
 // Template dispatch: VALIDATE x DIGEST x FWRC x KHI for one MODE.
 template <int MODE>
-static cudaError_t launch_narrow(bool validate, bool digest, bool fwrc, bool khi, const FixedGeom* fg, const CsrGeom* cg,
+static cudaError_t launch_narrow(bool validate, bool digest, bool fwrc, bool khi, bool hash, const FixedGeom* fg, const CsrGeom* cg,
                                  const Launch& l, cudaStream_t st, const EncDesc& enc, const NarrowParams& ep) {
 #define KMB_CASE(V, D, F, H) \
     if (validate == V && digest == D && fwrc == F && khi == H) return launch_eng<NarrowEng<V, D, F, MODE, H>>(fg, cg, l, st, enc, ep);
+    if (MODE == 0 && !hash && !digest && !fwrc) {  // canonical words only: the hash arithmetic is compiled out
+#define KMB_NOHASH(V, H) \
+        if (validate == V && khi == H) return launch_eng<NarrowEng<V, false, false, 0, H, false>>(fg, cg, l, st, enc, ep);
+        KMB_NOHASH(true, true) KMB_NOHASH(true, false) KMB_NOHASH(false, true) KMB_NOHASH(false, false)
+#undef KMB_NOHASH
+    }
     KMB_CASE(true, false, false, true) KMB_CASE(true, false, false, false)
     KMB_CASE(true, true, false, true) KMB_CASE(true, true, false, false)
     KMB_CASE(false, false, false, true) KMB_CASE(false, false, false, false)
@@ -699,8 +705,8 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
             return KMB_OK;
         }
     }
-    e = hist ? launch_narrow<1>(validate, want_digest, false, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
-             : launch_narrow<0>(validate, want_digest, fwrc, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
+    e = hist ? launch_narrow<1>(validate, want_digest, false, khi, true, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
+             : launch_narrow<0>(validate, want_digest, fwrc, khi, hash != nullptr, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
     CK(ctx, e);
     ctx->launches++;
     return KMB_OK;
@@ -940,8 +946,11 @@ extern "C" int32_t kmb_minimizer_words(kmb_ctx* ctx, uint32_t k, uint32_t w, uin
 
 // ======================================================================= extract wide (extension, K <= 64)
 template <int NW32>
-static cudaError_t launch_wide(bool validate, bool digest, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
+static cudaError_t launch_wide(bool validate, bool digest, bool hash, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
                                cudaStream_t st, const EncDesc& enc, const WideParams& ep) {
+    if (!hash && !digest)  // canonical words only (BASELINE config 3): the hash arithmetic is compiled out
+        return validate ? launch_eng<WideEng<NW32, true, false, false>>(fg, cg, l, st, enc, ep)
+                        : launch_eng<WideEng<NW32, false, false, false>>(fg, cg, l, st, enc, ep);
     if (validate) return digest ? launch_eng<WideEng<NW32, true, true>>(fg, cg, l, st, enc, ep)
                                 : launch_eng<WideEng<NW32, true, false>>(fg, cg, l, st, enc, ep);
     return digest ? launch_eng<WideEng<NW32, false, true>>(fg, cg, l, st, enc, ep)
@@ -989,9 +998,10 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         }
         const FixedGeom* pf = csr ? nullptr : &fg;
         const CsrGeom* pc = csr ? &cg : nullptr;
-        cudaError_t e = nw32 == 2 ? launch_wide<2>(validate, digest != nullptr, pf, pc, l, ctx->stream, enc, ep)
-                      : nw32 == 3 ? launch_wide<3>(validate, digest != nullptr, pf, pc, l, ctx->stream, enc, ep)
-                                  : launch_wide<4>(validate, digest != nullptr, pf, pc, l, ctx->stream, enc, ep);
+        const bool want_hash = oh.dev != nullptr;
+        cudaError_t e = nw32 == 2 ? launch_wide<2>(validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep)
+                      : nw32 == 3 ? launch_wide<3>(validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep)
+                                  : launch_wide<4>(validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep);
         CK(ctx, e);
         ctx->launches++;
     }
