@@ -9,10 +9,19 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
 raw = os.path.join(ROOT, "profiles", f"ncu_full_fixed_kernel_{tag}_raw.csv")
-with open(raw, "w") as f:
-    subprocess.check_call(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=f, stderr=subprocess.DEVNULL)
+pre = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_raw.csv")  # exported on the GPU box by scripts/profile.sh
+if os.path.exists(pre):
+    with open(pre) as f, open(raw, "w") as g:
+        g.write(f.read())
+    det = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_details.txt")
+    if os.path.exists(det):
+        with open(det) as f, open(os.path.join(ROOT, "profiles", f"ncu_full_fixed_kernel_{tag}_details.txt"), "w") as g:
+            g.write(f.read())
+else:
+    rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+    with open(raw, "w") as f:
+        subprocess.check_call(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=f, stderr=subprocess.DEVNULL)
 src = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(src):
     with open(src) as f, open(os.path.join(ROOT, "profiles", f"launches_{tag}.csv"), "w") as g:
