@@ -8,7 +8,6 @@
 namespace kmb {
 
 constexpr int kRun = 8;             // windows per work item (one thread, 64 B of each output array)
-constexpr int kBasesPerWord = 16;   // packed tile granularity: one uint4 load -> one 32-bit word
 
 // ---------------------------------------------------------------- memory ops
 // Streaming 16-byte read of the read bytes: read once, keep out of L1.

@@ -122,3 +122,36 @@ def test_config4_long_reads_full_size():
             ref = ko.extract_canonical(bases[r0 * Lr:(r0 + 20) * Lr], K, n_reads=20, fixed_len=Lr)
             assert np.array_equal(res.canon[r0 * wr:(r0 + 20) * wr].cpu().numpy().view(np.uint64), ref["canon"])
             assert np.array_equal(res.hash[r0 * wr:(r0 + 20) * wr].cpu().numpy().view(np.uint64), ref["hash"])
+
+
+def test_more_than_2_pow_32_slots():
+    """Maximum sizes: 3.6e7 reads x 150 bp = 4.32e9 output slots (> 2^32): 64-bit slot arithmetic end to end.
+    Digest vs the multi-threaded oracle; the last reads bit-exact; sums of the arrays."""
+    import torch
+    import kmers_b200 as kb
+    import oracle as ko
+    n = 36_000_000
+    assert n * W > 2**32
+    with kb.Context(0, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        batch = ctx.generate(SEED, n, L, n_thresh20=200)
+        res = batch.extract_canonical(K, digest=True, to="device")
+        torch.cuda.synchronize()
+        assert res.n_slots == n * W
+        tail = 2000
+        bases_tail = ko.generate_bases(SEED, (n - tail) * L, tail * L, 200)
+        ref = ko.extract_canonical(bases_tail, K, n_reads=tail, fixed_len=L)
+        assert np.array_equal(res.canon[(n - tail) * W:].cpu().numpy().view(np.uint64), ref["canon"])
+        assert np.array_equal(res.hash[(n - tail) * W:].cpu().numpy().view(np.uint64), ref["hash"])
+        valid = res.canon != -1
+        assert res.digest[0] == int(valid.sum().item())
+        assert res.digest[1] == _u64sum(torch.where(valid, res.canon, torch.zeros_like(res.canon)))
+        del valid
+        # oracle digest over the whole input, in 4 chunks to bound host memory
+        tot = [0, 0, 0]
+        for c in range(4):
+            r0, r1 = n * c // 4, n * (c + 1) // 4
+            hb = ko.generate_bases(SEED, r0 * L, (r1 - r0) * L, 200)
+            d = ko.extract_canonical(hb, K, n_reads=r1 - r0, fixed_len=L, n_threads=os.cpu_count() or 1, materialize=False)
+            tot = [(a + b) % 2**64 for a, b in zip(tot, (d["n_valid"], d["checksum_canon"], d["checksum_hash"]))]
+            del hb
+        assert res.digest == tuple(tot)

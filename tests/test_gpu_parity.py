@@ -279,9 +279,6 @@ def test_wide_agrees_with_narrow(ctx, ko):
 
 
 # ------------------------------------------------------------------ batched Encoding<P,B>
-ALL_ENC = None
-
-
 def _encs(ko):
     return list(ko.NAIVE.items()) + [("XOR10", ko.XOR10)]
 
