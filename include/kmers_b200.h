@@ -208,6 +208,17 @@ int32_t kmb_batch_attach_packed(kmb_ctx *ctx, const uint64_t *dev_words, uint64_
  * at pos[i] of read reads[i], or KMB_SENTINEL where the reference's assert!(pos < len) / the read's end is violated. */
 int32_t kmb_packed_get_kmers(kmb_ctx *ctx, uint32_t k, const uint64_t *reads, const uint64_t *pos, uint64_t n, uint64_t *out);
 
+/* ---- "next" row N4: host ingest -------------------------------------------- */
+/* FASTA ('>' records, multi-line sequences) or FASTQ ('@' four-line records) text in host memory -> the
+ * concatenated bases and their CSR offsets (n_reads + 1 entries), exactly the arguments of kmb_batch_upload.
+ * Bases are copied verbatim (case, N, IUPAC kept; line ends and '\r' dropped).  Call with bases_out == offsets_out ==
+ * NULL to size the outputs.  Pure host code, needs no GPU.  Errors (malformed input) return KMB_ERR_INVALID_ARG with
+ * kmb_last_error(NULL). */
+int32_t kmb_parse_fastx(const char *text, uint64_t n_bytes, uint8_t *bases_out, uint64_t bases_cap, uint64_t *offsets_out,
+                        uint64_t reads_cap, uint64_t *n_reads, uint64_t *n_bases);
+/* parse into pinned host memory and upload as the context's (ragged) read batch */
+int32_t kmb_batch_ingest_fastx(kmb_ctx *ctx, const char *text, uint64_t n_bytes, uint64_t *n_reads_out, uint64_t *n_bases_out);
+
 /* ---- batched Encoding<P,B> (encoding/mod.rs:14-23) --------------------- */
 /* Encoding::encode of every read of the batch (encoding/naive.rs:116-124,
  * xor10.rs:52-60): read r becomes ceil(L_r / (word_bits/2)) words of

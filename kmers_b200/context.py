@@ -145,6 +145,13 @@ class Context:
         self._keep = []
         return ReadBatch(self, n_reads * fixed_len, n_reads, fixed_len, False)
 
+    def ingest_fastx(self, text: bytes) -> "ReadBatch":
+        """FASTA / FASTQ text -> pinned host batch -> device (kmb_batch_ingest_fastx); returns the ragged ReadBatch."""
+        nr, nb = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.kmb_batch_ingest_fastx(self._h, text, len(text), C.byref(nr), C.byref(nb)))
+        self._keep = []
+        return ReadBatch(self, int(nb.value), int(nr.value), 0, True)
+
     # ---- one-shot host path (e2e): chunked, H2D / kernel / D2H overlapped
     def extract_canonical_host(self, host_bases: np.ndarray, n_reads: int, fixed_len: int, k: int, *,
                                host_canon: Optional[np.ndarray] = None, host_hash: Optional[np.ndarray] = None,
@@ -382,3 +389,14 @@ class ReadBatch:
         woff = np.empty(self.n_reads + 1, dtype=np.uint64) if self.ragged else None
         self.ctx._ck(self.ctx._lib.kmb_pack(self.ctx._h, enc, word_bits, _ptr(out), _ptr(woff)))
         return out, woff
+
+
+def parse_fastx(text: bytes):
+    """FASTA / FASTQ text -> (bases uint8, offsets uint64) on the host (kmb_parse_fastx; needs no GPU)."""
+    lib = nv.lib()
+    nr, nb = C.c_uint64(), C.c_uint64()
+    check(None, lib.kmb_parse_fastx(text, len(text), None, 0, None, 0, C.byref(nr), C.byref(nb)))
+    bases = np.empty(int(nb.value), dtype=np.uint8)
+    offs = np.empty(int(nr.value) + 1, dtype=np.uint64)
+    check(None, lib.kmb_parse_fastx(text, len(text), bases.ctypes.data, bases.size, offs.ctypes.data, offs.size, None, None))
+    return bases, offs

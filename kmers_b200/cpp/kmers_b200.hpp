@@ -139,6 +139,10 @@ class Context {
                                              reads.size(), 0));
         return ReadBatch(ctx_);
     }
+    ReadBatch ingest_fastx(const std::string& text) {  // FASTA / FASTQ text -> ragged batch
+        detail::check(ctx_, kmb_batch_ingest_fastx(ctx_, text.data(), text.size(), nullptr, nullptr));
+        return ReadBatch(ctx_);
+    }
     ReadBatch generate(uint64_t seed, uint64_t n_reads, uint64_t fixed_len, uint32_t n_thresh20 = 0, uint64_t first_index = 0) {
         detail::check(ctx_, kmb_batch_generate(ctx_, seed, first_index, n_reads, fixed_len, n_thresh20));
         return ReadBatch(ctx_);

@@ -1203,6 +1203,114 @@ extern "C" int32_t kmb_packed_get_kmers(kmb_ctx* ctx, uint32_t k, const uint64_t
     return KMB_OK;
 }
 
+// ======================================================================= host ingest ("next" row N4)
+// FASTA / FASTQ text -> concatenated bases + CSR offsets.  Host-side I/O plumbing on the caller's side of the
+// boundary (no k-mer arithmetic happens here); the bases go to the device untouched, so lower case, N and IUPAC
+// codes are handled by the kernels exactly as the reference handles them.
+namespace {
+struct FastxSink {
+    uint8_t* bases;      // may be NULL (counting pass)
+    uint64_t* offsets;   // may be NULL
+    uint64_t bases_cap, reads_cap;
+    uint64_t n_bases = 0, n_reads = 0;
+    bool overflow = false;
+    void begin_read() {
+        if (offsets) { if (n_reads < reads_cap) offsets[n_reads] = n_bases; else overflow = true; }
+        ++n_reads;
+    }
+    void append(const char* p, size_t n) {
+        if (bases) { if (n_bases + n <= bases_cap) memcpy(bases + n_bases, p, n); else overflow = true; }
+        n_bases += n;
+    }
+};
+
+inline const char* line_end(const char* p, const char* end) {
+    const void* q = memchr(p, '\n', (size_t)(end - p));
+    return q ? (const char*)q : end;
+}
+inline size_t trim_cr(const char* p, const char* e) { return (e > p && e[-1] == '\r') ? (size_t)(e - p - 1) : (size_t)(e - p); }
+
+// returns NULL on success, else a message
+const char* parse_fastx(const char* text, uint64_t n, FastxSink& out) {
+    const char *p = text, *end = text + n;
+    while (p < end && (*p == '\n' || *p == '\r' || *p == ' ' || *p == '\t')) ++p;
+    if (p == end) return nullptr;
+    if (*p == '>') {  // FASTA: header line, then sequence lines up to the next '>'
+        while (p < end) {
+            if (*p != '>') return "FASTA: expected '>' at the start of a record";
+            p = line_end(p, end);
+            if (p < end) ++p;
+            out.begin_read();
+            while (p < end && *p != '>') {
+                const char* e = line_end(p, end);
+                out.append(p, trim_cr(p, e));
+                p = e < end ? e + 1 : end;
+            }
+        }
+    } else if (*p == '@') {  // FASTQ: four lines per record
+        while (p < end) {
+            if (*p == '\n' || *p == '\r') { ++p; continue; }  // blank lines between / after records
+            if (*p != '@') return "FASTQ: expected '@' at the start of a record";
+            p = line_end(p, end);
+            if (p == end) return "FASTQ: truncated record (no sequence line)";
+            ++p;
+            const char* e = line_end(p, end);
+            const size_t len = trim_cr(p, e);
+            out.begin_read();
+            out.append(p, len);
+            if (e == end) return "FASTQ: truncated record (no '+' line)";
+            p = e + 1;
+            if (p >= end || *p != '+') return "FASTQ: expected '+' on the third line of a record";
+            p = line_end(p, end);
+            if (p == end) return "FASTQ: truncated record (no quality line)";
+            ++p;
+            e = line_end(p, end);
+            if (trim_cr(p, e) != len) return "FASTQ: quality and sequence lengths differ";
+            p = e < end ? e + 1 : end;
+        }
+    } else {
+        return "neither FASTA ('>') nor FASTQ ('@')";
+    }
+    return nullptr;
+}
+}  // namespace
+
+extern "C" int32_t kmb_parse_fastx(const char* text, uint64_t n_bytes, uint8_t* bases_out, uint64_t bases_cap, uint64_t* offsets_out,
+                                   uint64_t reads_cap, uint64_t* n_reads, uint64_t* n_bases) {
+    if (n_bytes && !text) return fail(nullptr, KMB_ERR_INVALID_ARG, "text is NULL");
+    FastxSink sink{bases_out, offsets_out, bases_cap, reads_cap};
+    const char* err = parse_fastx(text, n_bytes, sink);
+    if (err) return fail(nullptr, KMB_ERR_INVALID_ARG, "%s", err);
+    if (n_reads) *n_reads = sink.n_reads;
+    if (n_bases) *n_bases = sink.n_bases;
+    if (offsets_out) { if (sink.n_reads < reads_cap) offsets_out[sink.n_reads] = sink.n_bases; else sink.overflow = true; }
+    if (sink.overflow) return fail(nullptr, KMB_ERR_INVALID_ARG, "output capacity too small: %llu reads, %llu bases",
+                                   (unsigned long long)sink.n_reads, (unsigned long long)sink.n_bases);
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_ingest_fastx(kmb_ctx* ctx, const char* text, uint64_t n_bytes, uint64_t* n_reads_out, uint64_t* n_bases_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    uint64_t n_reads = 0, n_bases = 0;
+    if (kmb_parse_fastx(text, n_bytes, nullptr, 0, nullptr, 0, &n_reads, &n_bases) != KMB_OK) return fail(ctx, KMB_ERR_INVALID_ARG, "%s", g_err.c_str());
+    // parse straight into pinned memory, then one DMA each for the bases and the offsets
+    uint8_t* h_bases = nullptr;
+    uint64_t* h_offs = nullptr;
+    CK(ctx, cudaHostAlloc((void**)&h_bases, n_bases ? n_bases : 1, cudaHostAllocDefault));
+    cudaError_t e = cudaHostAlloc((void**)&h_offs, (n_reads + 1) * 8, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaFreeHost(h_bases); CK(ctx, e); }
+    int32_t rc = kmb_parse_fastx(text, n_bytes, h_bases, n_bases, h_offs, n_reads + 1, nullptr, nullptr);
+    if (rc == KMB_OK) rc = kmb_batch_upload(ctx, h_bases, n_bases, h_offs, n_reads, 0);
+    if (rc == KMB_OK) { cudaError_t s = cudaStreamSynchronize(ctx->stream); if (s != cudaSuccess) rc = fail(ctx, KMB_ERR_CUDA, "%s", cudaGetErrorString(s)); }
+    cudaFreeHost(h_bases);
+    cudaFreeHost(h_offs);
+    if (rc != KMB_OK) return rc;
+    if (n_reads_out) *n_reads_out = n_reads;
+    if (n_bases_out) *n_bases_out = n_bases;
+    return KMB_OK;
+}
+
 // ======================================================================= batched Encoding<P,B>
 static bool word_bits_ok(uint32_t wb) { return wb == 8 || wb == 16 || wb == 32 || wb == 64 || wb == 128; }
 
