@@ -317,10 +317,20 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        r = cpu_reference(3, 1, 2_000_000)
+        r = cpu_reference(10, 1, 2_000_000)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"first {r['sample_reads']} reads of the same workload, iterator + canonical + LexHash materialised, "
-                         f"{r['cores']} threads, mean of 3 passes"}
+                         f"{r['cores']} threads, mean of 10 passes (~{10 * r['ms_per_step'] * r['cores'] / 1e3:.0f} core-seconds)"}
+        try:  # SURVEY 8(d) variant 1: what benches/simple_benchmark.rs does per window (O(K) re-encode + rev-comp), canonicalised
+            import oracle as ko
+            nf = 500_000
+            fb = ko.generate_bases(SEED, 0, nf * READ_LEN)
+            t0 = time.perf_counter()
+            ko.bench_windows(fb, K, n_reads=nf, fixed_len=READ_LEN, n_threads=r["cores"], materialize=False)
+            cpu["bench_faithful"] = {"value": nf * (READ_LEN - K + 1) / (time.perf_counter() - t0), "unit": UNIT, "cores": r["cores"],
+                                     "sample": f"first {nf} reads, per-window Kmer::from + to_reverse_complement + canonical-min, folded"}
+        except Exception as ex:
+            cpu["bench_faithful"] = {"unavailable": str(ex)[:200]}
 
     if rank == 0:
         line = {

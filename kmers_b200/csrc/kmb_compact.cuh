@@ -175,21 +175,4 @@ __global__ void __launch_bounds__(kExtractThreads) compact_csr_kernel(const CsrG
     eng.finish();
 }
 
-// Reads without a window (shorter than k) open no entry: their emit offset is that of the next read that has
-// windows (or the total).  win_offsets[r + 1] == win_offsets[r] identifies them.
-__global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_emitted,
-                                                               uint64_t* emit_offsets) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    if (win_offsets[r + 1] != win_offsets[r]) return;
-    // first read after r whose window offset exceeds win_offsets[r] - 1 ... i.e. first r' > r with windows
-    uint64_t lo = r + 1, hi = n_reads;  // answer in [lo, hi]; n_reads = none
-    const uint64_t v = win_offsets[r];
-    while (lo < hi) {
-        const uint64_t mid = lo + ((hi - lo) >> 1);
-        if (win_offsets[mid + 1] > v) hi = mid; else lo = mid + 1;
-    }
-    emit_offsets[r] = lo < n_reads ? emit_offsets[lo] : total_emitted;
-}
-
 }  // namespace kmb

@@ -131,7 +131,7 @@ __device__ __forceinline__ PackedWord pack16(uint4 v) {
 // Guarded 16-byte fetch of the flat read stream: vector load when the chunk
 // lies wholly inside [base, base+n), else byte-wise with zeros outside (a zero
 // byte is an invalid base, so nothing outside the batch can form a window).
-__device__ __noinline__ uint4 load16_guarded(const uint8_t* base, uint64_t n_bytes, const uint8_t* p) {
+static __device__ __noinline__ uint4 load16_guarded(const uint8_t* base, uint64_t n_bytes, const uint8_t* p) {
     if (p >= base && p + 16 <= base + n_bytes) return ld_stream_v4(p);
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll

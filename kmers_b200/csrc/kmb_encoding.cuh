@@ -329,4 +329,15 @@ __global__ void __launch_bounds__(256) read_counts_kernel(const uint64_t* offset
     else counts[r] = (len + div - 1) / div;                             // packed words
 }
 
+// first_read[b] = read owning slot b * slots_per_cta (b < grid); first_read[grid] = read owning the last slot.
+// One thread per CTA of the extraction grid: the log2(n_reads)-deep searches all run concurrently here
+// instead of serially at the head of every extraction CTA.
+__global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_slots,
+                                                        uint64_t slots_per_cta, uint64_t grid, uint64_t* first_read) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > grid) return;
+    const uint64_t slot = b < grid ? b * slots_per_cta : total_slots - 1;
+    first_read[b] = last_le(win_offsets, 0, n_reads - 1, slot);  // skips window-less reads: takes the last equal entry
+}
+
 }  // namespace kmb

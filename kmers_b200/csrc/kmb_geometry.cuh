@@ -275,17 +275,6 @@ __device__ __forceinline__ uint64_t last_le(const uint64_t* a, uint64_t lo, uint
     return lo;
 }
 
-// first_read[b] = read owning slot b * slots_per_cta (b < grid); first_read[grid] = read owning the last slot.
-// One thread per CTA of the extraction grid: the log2(n_reads)-deep searches all run concurrently here
-// instead of serially at the head of every extraction CTA.
-__global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_slots,
-                                                        uint64_t slots_per_cta, uint64_t grid, uint64_t* first_read) {
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > grid) return;
-    const uint64_t slot = b < grid ? b * slots_per_cta : total_slots - 1;
-    first_read[b] = last_le(win_offsets, 0, n_reads - 1, slot);  // skips window-less reads: takes the last equal entry
-}
-
 struct CsrPass {  // one staged stretch: slots [slot_lo, slot_hi) of reads [r_lo, r_hi]
     uint64_t slot_lo, slot_hi, r_lo, r_hi, g0;
     uint32_t span;

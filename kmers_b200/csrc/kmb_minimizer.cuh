@@ -164,22 +164,4 @@ struct MinimizerEng {
     __device__ __forceinline__ void finish(unsigned long long (&)[3][32]) {}
 };
 
-// Kmer::minimizer_word (naive_impl/kmer.rs:170-191) on every word: leftmost width-mer of minimum LexHash.
-__global__ void __launch_bounds__(256) minimizer_words_kernel(const uint64_t* in, uint64_t n, uint32_t k, uint32_t width,
-                                                              uint32_t hash_k, uint64_t* mmer_out, uint32_t* offset_out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t word = in[i];
-    const uint64_t wmask = width >= 32 ? ~0ull : ((1ull << (2 * width)) - 1ull);
-    uint64_t min_mmer = word & wmask, min_hash = ~0ull;
-    uint32_t off = 0;
-    for (uint32_t pos = 0; pos + width <= k; ++pos) {
-        const uint64_t mm = (word >> (2 * pos)) & wmask;                       // sub_kmer_word, kmer.rs:155-161
-        const uint64_t h = pair_reverse64(mm) >> (2 * (32 - hash_k));          // LexHasher::write_u64, hash.rs:60-71
-        if (h < min_hash) { min_mmer = mm; min_hash = h; off = pos; }
-    }
-    if (mmer_out) mmer_out[i] = min_mmer;
-    if (offset_out) offset_out[i] = off;
-}
-
 }  // namespace kmb

@@ -1,0 +1,61 @@
+// kmb_tu_compact.cu -- instantiates the compaction engines (count pass, emit pass) on both geometries.
+#include "kmb_launch.h"
+
+namespace kmb {
+namespace {
+template <bool COUNT_ONLY>
+static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
+                                  cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
+    // dynamic shared memory = the geometry's tile (+ tables), 16-byte aligned, then CompactShared: above 48 KiB -> opt in
+    const uint32_t tile_bytes = (uint32_t)((l.smem + 15) & ~(size_t)15);
+    const size_t smem = tile_bytes + sizeof(CompactShared);
+#define KMB_CASE(V, H)                                                                                                  \
+    if (validate == V && khi == H) {                                                                                    \
+        cudaError_t e;                                                                                                  \
+        if (fg) {                                                                                                       \
+            e = cudaFuncSetAttribute(compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                             \
+            compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*fg, enc, ep, tile_bytes); \
+        } else {                                                                                                        \
+            e = cudaFuncSetAttribute(compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                             \
+            compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*cg, enc, ep, tile_bytes); \
+        }                                                                                                               \
+        return cudaGetLastError();                                                                                      \
+    }
+    KMB_CASE(true, true) KMB_CASE(true, false) KMB_CASE(false, true) KMB_CASE(false, false)
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
+}
+}  // namespace
+
+cudaError_t launch_compact(bool count_only, bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
+                           cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
+    return count_only ? launch_compact<true>(validate, khi, fg, cg, l, st, enc, ep)
+                      : launch_compact<false>(validate, khi, fg, cg, l, st, enc, ep);
+}
+
+// Reads without a window (shorter than k) open no entry: their emit offset is that of the next read that has
+// windows (or the total).  win_offsets[r + 1] == win_offsets[r] identifies them.
+__global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_emitted,
+                                                               uint64_t* emit_offsets) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    if (win_offsets[r + 1] != win_offsets[r]) return;
+    // first read after r whose window offset exceeds win_offsets[r] - 1 ... i.e. first r' > r with windows
+    uint64_t lo = r + 1, hi = n_reads;  // answer in [lo, hi]; n_reads = none
+    const uint64_t v = win_offsets[r];
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (win_offsets[mid + 1] > v) hi = mid; else lo = mid + 1;
+    }
+    emit_offsets[r] = lo < n_reads ? emit_offsets[lo] : total_emitted;
+}
+
+cudaError_t launch_compact_backfill(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_emitted, uint64_t* emit_offsets,
+                                    cudaStream_t st) {
+    compact_backfill_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(win_offsets, n_reads, total_emitted, emit_offsets);
+    return cudaGetLastError();
+}
+
+}  // namespace kmb

@@ -1,0 +1,35 @@
+// kmb_tu_minimizer.cu -- instantiates the minimizer engines on both geometries, and Kmer::minimizer_word.
+#include "kmb_launch.h"
+
+namespace kmb {
+
+cudaError_t launch_minimizers(bool validate, const FixedGeom* fg, const CsrGeom* cg, const Launch& l, cudaStream_t st,
+                              const EncDesc& enc, const MinParams& ep) {
+    return validate ? launch_eng<MinimizerEng<true>>(fg, cg, l, st, enc, ep) : launch_eng<MinimizerEng<false>>(fg, cg, l, st, enc, ep);
+}
+
+// Kmer::minimizer_word (naive_impl/kmer.rs:170-191) on every word: leftmost width-mer of minimum LexHash.
+__global__ void __launch_bounds__(256) minimizer_words_kernel(const uint64_t* in, uint64_t n, uint32_t k, uint32_t width,
+                                                              uint32_t hash_k, uint64_t* mmer_out, uint32_t* offset_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t word = in[i];
+    const uint64_t wmask = width >= 32 ? ~0ull : ((1ull << (2 * width)) - 1ull);
+    uint64_t min_mmer = word & wmask, min_hash = ~0ull;
+    uint32_t off = 0;
+    for (uint32_t pos = 0; pos + width <= k; ++pos) {
+        const uint64_t mm = (word >> (2 * pos)) & wmask;                       // sub_kmer_word, kmer.rs:155-161
+        const uint64_t h = pair_reverse64(mm) >> (2 * (32 - hash_k));          // LexHasher::write_u64, hash.rs:60-71
+        if (h < min_hash) { min_mmer = mm; min_hash = h; off = pos; }
+    }
+    if (mmer_out) mmer_out[i] = min_mmer;
+    if (offset_out) offset_out[i] = off;
+}
+
+cudaError_t launch_minimizer_words(const uint64_t* in, uint64_t n, uint32_t k, uint32_t w, uint32_t hash_k, uint64_t* mmer_out,
+                                   uint32_t* offset_out, cudaStream_t st) {
+    minimizer_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, n, k, w, hash_k, mmer_out, offset_out);
+    return cudaGetLastError();
+}
+
+}  // namespace kmb

@@ -1,4 +1,6 @@
 // kmers_b200.cu -- C ABI (include/kmers_b200.h) over the sm_100a kernels.
+// The extraction engines are instantiated in their own translation units (kmb_tu_*.cu, declared in kmb_launch.h)
+// so that the library builds in parallel.
 // No torch types, no CPU fallback: every compute entry point needs a device.
 #include "../../include/kmers_b200.h"
 
@@ -14,10 +16,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "kmb_encoding.cuh"
-#include "kmb_extract.cuh"
-#include "kmb_extract_wide.cuh"
-#include "kmb_compact.cuh"
-#include "kmb_minimizer.cuh"
+#include "kmb_launch.h"
 
 using namespace kmb;
 
@@ -521,11 +520,6 @@ static int32_t digest_end(kmb_ctx* ctx, kmb_digest* digest) {
 // ======================================================================= geometry (shared by both engines)
 static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
 
-struct Launch {
-    unsigned grid = 0;
-    size_t smem = 0;
-};
-
 // fixed-length reads: slot-space geometry of fixed_kernel
 static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
                             uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, bool packed = false) {
@@ -581,69 +575,7 @@ static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, Cs
     return KMB_OK;
 }
 
-template <class Eng>
-static cudaError_t launch_eng(const FixedGeom* fg, const CsrGeom* cg, const Launch& l, cudaStream_t st, const EncDesc& enc,
-                              const typename Eng::Params& ep) {
-    if (fg) fixed_kernel<Eng><<<l.grid, kExtractThreads, l.smem, st>>>(*fg, enc, ep);
-    else csr_kernel<Eng><<<l.grid, kExtractThreads, l.smem, st>>>(*cg, enc, ep);
-    return cudaGetLastError();
-}
-
 // ======================================================================= extract (K <= 32)
-// Template dispatch: VALIDATE x DIGEST x FWRC x KHI for one MODE.
-template <int MODE>
-static cudaError_t launch_narrow(bool validate, bool digest, bool fwrc, bool khi, bool hash, const FixedGeom* fg, const CsrGeom* cg,
-                                 const Launch& l, cudaStream_t st, const EncDesc& enc, const NarrowParams& ep) {
-#define KMB_CASE(V, D, F, H) \
-    if (validate == V && digest == D && fwrc == F && khi == H) return launch_eng<NarrowEng<V, D, F, MODE, H>>(fg, cg, l, st, enc, ep);
-    if (MODE == 0 && !hash && !digest && !fwrc) {  // canonical words only: the hash arithmetic is compiled out
-#define KMB_NOHASH(V, H) \
-        if (validate == V && khi == H) return launch_eng<NarrowEng<V, false, false, 0, H, false>>(fg, cg, l, st, enc, ep);
-        KMB_NOHASH(true, true) KMB_NOHASH(true, false) KMB_NOHASH(false, true) KMB_NOHASH(false, false)
-#undef KMB_NOHASH
-    }
-    KMB_CASE(true, false, false, true) KMB_CASE(true, false, false, false)
-    KMB_CASE(true, true, false, true) KMB_CASE(true, true, false, false)
-    KMB_CASE(false, false, false, true) KMB_CASE(false, false, false, false)
-    KMB_CASE(false, true, false, true) KMB_CASE(false, true, false, false)
-    if (MODE == 0) {
-        KMB_CASE(true, false, (MODE == 0), true) KMB_CASE(true, false, (MODE == 0), false)
-        KMB_CASE(true, true, (MODE == 0), true) KMB_CASE(true, true, (MODE == 0), false)
-        KMB_CASE(false, false, (MODE == 0), true) KMB_CASE(false, false, (MODE == 0), false)
-        KMB_CASE(false, true, (MODE == 0), true) KMB_CASE(false, true, (MODE == 0), false)
-    }
-#undef KMB_CASE
-    return cudaErrorInvalidValue;
-}
-
-// MODE 2 (shared-memory bins): persistent grid, opt-in dynamic shared memory above 48 KiB
-template <class Eng>
-static cudaError_t launch_hist_eng(const FixedGeom* fg, const CsrGeom* cg, unsigned grid, size_t smem, uint32_t n_tiles,
-                                   uint32_t tile_words, uint32_t n_bins, cudaStream_t st, const EncDesc& enc, const NarrowParams& ep) {
-    cudaError_t e;
-    if (fg) {
-        e = cudaFuncSetAttribute(hist_fixed_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hist_fixed_kernel<Eng><<<grid, kHistThreads, smem, st>>>(*fg, enc, ep, n_tiles, tile_words, n_bins);
-    } else {
-        e = cudaFuncSetAttribute(hist_csr_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hist_csr_kernel<Eng><<<grid, kHistThreads, smem, st>>>(*cg, enc, ep, n_tiles, n_bins);
-    }
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_hist_smem(bool validate, bool digest, bool khi, const FixedGeom* fg, const CsrGeom* cg, unsigned grid,
-                                    size_t smem, uint32_t n_tiles, uint32_t tile_words, uint32_t n_bins, cudaStream_t st,
-                                    const EncDesc& enc, const NarrowParams& ep) {
-#define KMB_CASE(V, D, H) \
-    if (validate == V && digest == D && khi == H) return launch_hist_eng<NarrowEng<V, D, false, 2, H>>(fg, cg, grid, smem, n_tiles, tile_words, n_bins, st, enc, ep);
-    KMB_CASE(true, false, true) KMB_CASE(true, false, false) KMB_CASE(true, true, true) KMB_CASE(true, true, false)
-    KMB_CASE(false, false, true) KMB_CASE(false, false, false) KMB_CASE(false, true, true) KMB_CASE(false, true, false)
-#undef KMB_CASE
-    return cudaErrorInvalidValue;
-}
-
 static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
     WinConst wc{};
     wc.K = k;
@@ -705,8 +637,8 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
             return KMB_OK;
         }
     }
-    e = hist ? launch_narrow<1>(validate, want_digest, false, khi, true, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
-             : launch_narrow<0>(validate, want_digest, fwrc, khi, hash != nullptr, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
+    e = hist ? launch_narrow_hist_global(validate, want_digest, khi, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep)
+             : launch_narrow_materialise(validate, want_digest, fwrc, khi, hash != nullptr, csr ? nullptr : &fg, csr ? &cg : nullptr, l, st, enc, ep);
     CK(ctx, e);
     ctx->launches++;
     return KMB_OK;
@@ -765,31 +697,6 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
 }
 
 // ======================================================================= compacted (iterator-identical) output
-template <bool COUNT_ONLY>
-static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
-                                  cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
-    // dynamic shared memory = the geometry's tile (+ tables), 16-byte aligned, then CompactShared: above 48 KiB -> opt in
-    const uint32_t tile_bytes = (uint32_t)((l.smem + 15) & ~(size_t)15);
-    const size_t smem = tile_bytes + sizeof(CompactShared);
-#define KMB_CASE(V, H)                                                                                                  \
-    if (validate == V && khi == H) {                                                                                    \
-        cudaError_t e;                                                                                                  \
-        if (fg) {                                                                                                       \
-            e = cudaFuncSetAttribute(compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                             \
-            compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*fg, enc, ep, tile_bytes); \
-        } else {                                                                                                        \
-            e = cudaFuncSetAttribute(compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                             \
-            compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*cg, enc, ep, tile_bytes); \
-        }                                                                                                               \
-        return cudaGetLastError();                                                                                      \
-    }
-    KMB_CASE(true, true) KMB_CASE(true, false) KMB_CASE(false, true) KMB_CASE(false, false)
-#undef KMB_CASE
-    return cudaErrorInvalidValue;
-}
-
 extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint64_t* canon_out, uint64_t* hash_out,
                                        int32_t* pos_out, uint64_t* emit_offsets_out, uint64_t capacity, uint64_t* n_emitted) {
     NEED_CTX(ctx);
@@ -831,7 +738,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     ep.wc = make_winconst(k, enc);
     ep.out.cta_counts = ctx->d_cta_counts;
     // launch 1: valid windows per CTA, then their exclusive scan (entry [grid] becomes the total)
-    CK(ctx, launch_compact<true>(validate, khi, pf, pc, l, ctx->stream, enc, ep));
+    CK(ctx, launch_compact(true, validate, khi, pf, pc, l, ctx->stream, enc, ep));
     ctx->launches++;
     size_t need = 0;
     CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
@@ -852,14 +759,12 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     ep.out.canon = (uint64_t*)oc.dev; ep.out.hash = (uint64_t*)oh.dev; ep.out.pos = (int32_t*)op.dev;
     ep.out.emit_offsets = (uint64_t*)oe.dev;
     // launch 2: emit at the scanned offsets
-    CK(ctx, launch_compact<false>(validate, khi, pf, pc, l, ctx->stream, enc, ep));
+    CK(ctx, launch_compact(false, validate, khi, pf, pc, l, ctx->stream, enc, ep));
     ctx->launches++;
     if (oe.dev) {
         CK(ctx, cudaMemcpyAsync((uint64_t*)oe.dev + ctx->n_reads, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (csr) {
-            compact_backfill_kernel<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_win_offsets, ctx->n_reads,
-                                                                                                   total, (uint64_t*)oe.dev);
-            CK(ctx, cudaGetLastError());
+            CK(ctx, launch_compact_backfill(ctx->d_win_offsets, ctx->n_reads, total, (uint64_t*)oe.dev, ctx->stream));
             ctx->launches++;
         }
     }
@@ -908,9 +813,7 @@ extern "C" int32_t kmb_minimizers(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t
         } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
             return rc;
         }
-        cudaError_t e = validate ? launch_eng<MinimizerEng<true>>(csr ? nullptr : &fg, csr ? &cg : nullptr, l, ctx->stream, enc, ep)
-                                 : launch_eng<MinimizerEng<false>>(csr ? nullptr : &fg, csr ? &cg : nullptr, l, ctx->stream, enc, ep);
-        CK(ctx, e);
+        CK(ctx, launch_minimizers(validate, csr ? nullptr : &fg, csr ? &cg : nullptr, l, ctx->stream, enc, ep));
         ctx->launches++;
     }
     if ((rc = out_finish(ctx, om)) || (rc = out_finish(ctx, op))) return rc;
@@ -935,9 +838,7 @@ extern "C" int32_t kmb_minimizer_words(kmb_ctx* ctx, uint32_t k, uint32_t w, uin
     if ((rc = out_prepare(ctx, 1, offset_out, n * 4, &oo))) return rc;
     const uint64_t ctas = (n + 255) / 256;
     if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
-    minimizer_words_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint64_t*)d_in, n, k, w, hash_k, (uint64_t*)om.dev,
-                                                                   (uint32_t*)oo.dev);
-    CK(ctx, cudaGetLastError());
+    CK(ctx, launch_minimizer_words((const uint64_t*)d_in, n, k, w, hash_k, (uint64_t*)om.dev, (uint32_t*)oo.dev, ctx->stream));
     ctx->launches++;
     if ((rc = out_finish(ctx, om)) || (rc = out_finish(ctx, oo))) return rc;
     if (om.host || oo.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -945,18 +846,6 @@ extern "C" int32_t kmb_minimizer_words(kmb_ctx* ctx, uint32_t k, uint32_t w, uin
 }
 
 // ======================================================================= extract wide (extension, K <= 64)
-template <int NW32>
-static cudaError_t launch_wide(bool validate, bool digest, bool hash, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
-                               cudaStream_t st, const EncDesc& enc, const WideParams& ep) {
-    if (!hash && !digest)  // canonical words only (BASELINE config 3): the hash arithmetic is compiled out
-        return validate ? launch_eng<WideEng<NW32, true, false, false>>(fg, cg, l, st, enc, ep)
-                        : launch_eng<WideEng<NW32, false, false, false>>(fg, cg, l, st, enc, ep);
-    if (validate) return digest ? launch_eng<WideEng<NW32, true, true>>(fg, cg, l, st, enc, ep)
-                                : launch_eng<WideEng<NW32, true, false>>(fg, cg, l, st, enc, ep);
-    return digest ? launch_eng<WideEng<NW32, false, true>>(fg, cg, l, st, enc, ep)
-                  : launch_eng<WideEng<NW32, false, false>>(fg, cg, l, st, enc, ep);
-}
-
 extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t enc_id, uint32_t flags,
                                               uint64_t* canon_out, uint64_t* hash_out, kmb_digest* digest) {
     NEED_CTX(ctx);
@@ -999,10 +888,7 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         const FixedGeom* pf = csr ? nullptr : &fg;
         const CsrGeom* pc = csr ? &cg : nullptr;
         const bool want_hash = oh.dev != nullptr;
-        cudaError_t e = nw32 == 2 ? launch_wide<2>(validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep)
-                      : nw32 == 3 ? launch_wide<3>(validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep)
-                                  : launch_wide<4>(validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep);
-        CK(ctx, e);
+        CK(ctx, launch_wide(nw32, validate, digest != nullptr, want_hash, pf, pc, l, ctx->stream, enc, ep));
         ctx->launches++;
     }
     if ((rc = out_finish(ctx, oc))) return rc;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run ONE kernel family a few times so that ncu can capture it:  python scripts/prof_one.py wide|hist|compact|minimizers|csr|canon"""
+"""Run ONE kernel family a few times so that ncu can capture it:  python scripts/prof_one.py wide|hist|compact|minimizers|csr|canon|full|pack8|pack64"""
 import ctypes as C
 import os
 import sys
@@ -28,7 +28,20 @@ for _ in range(3):
     elif what == "minimizers":
         batch.minimizers(31, 15, to="device")
     elif what == "csr":
-        pass
+        if _ == 0:
+            offs = torch.arange(0, n + 1, dtype=torch.int64, device="cuda") * L   # same reads, ragged (CSR) geometry
+            bases = batch.download()
+            batch = ctx.upload(bases, offsets=offs.cpu().numpy().astype("uint64"))
+            out = kb.CanonicalKmers(k=K, n_slots=n * (L - K + 1), canon=i64(n * (L - K + 1)), hash=i64(n * (L - K + 1)))
+        batch.extract_canonical(K, out=out)
+    elif what == "full":
+        if _ == 0:
+            out = kb.CanonicalKmers(k=K, n_slots=n * (L - K + 1), canon=i64(n * (L - K + 1)), hash=i64(n * (L - K + 1)))
+        batch.extract_canonical(K, out=out)
+    elif what == "pack8":
+        batch.pack(kb.ENC_ACGT, 8, to="device")
+    elif what == "pack64":
+        batch.pack(kb.ENC_ACGT, 64, to="device")
     elif what == "canon":
         out = kb.CanonicalKmers(k=K, n_slots=n * (L - K + 1), canon=i64(n * (L - K + 1)), hash=None)
         batch.extract_canonical(K, out=out)
