@@ -45,6 +45,7 @@ struct CompactEng {
     using Params = CompactParams;
     using Span = kmb::Span;
     static constexpr bool kValidate = VALIDATE;
+    using Shape = ShapeRun;
     static constexpr bool kTwoPhase = true, kCountOnly = COUNT_ONLY;
     static constexpr int kSpanEntries = 4;
     const CompactParams& p;

@@ -240,6 +240,7 @@ struct NarrowEng {
     using Params = NarrowParams;
     using Span = kmb::Span;
     static constexpr bool kValidate = VALIDATE;
+    using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;  // tile entries one span reads
     const NarrowParams& p;

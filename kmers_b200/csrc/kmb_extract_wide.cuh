@@ -9,9 +9,11 @@
 // 2K-bit integers, hash = 2K-bit pair reversal -- the natural extension of
 // naive_impl/canonical_kmer.rs:113-119 and naive_impl/hash.rs:60-71.
 //
-// Same structure as kmb_extract.cuh: slot-space work items (8 slots = 128 B of
-// each output array per thread, 32-byte stores), a span of NW32+1 packed words
-// per item, one multiword compare per window, hash by XOR fold.
+// Same structure as kmb_extract.cuh: slot-space work items (8 windows per thread,
+// 32-byte stores), a span of NW32+1 packed words per item, one multiword compare
+// per window, hash by XOR fold.  The items have ShapePair (kmb_geometry.cuh): two
+// neighbouring lanes interleave their windows so that a store covers 64 contiguous
+// bytes per lane pair instead of 32 bytes in each of 32 different lines.
 // NW32 = live 32-bit words of a k-mer = ceil(2K / 32) in {2, 3, 4} (K <= 32 uses 2).
 #pragma once
 #include "kmb_extract.cuh"
@@ -20,7 +22,7 @@ namespace kmb {
 
 struct WideConst {
     uint32_t K;
-    uint32_t shiftD;     // 2 * (16 * (NW32 + 1) - (kRun + K - 1))
+    uint32_t shiftD;     // 2 * (16 * (NW32 + 1) - (ShapePair::kSpanSlots + K - 1))
     uint32_t mask_a;     // mask of word NW32 - 2
     uint32_t mask_b;     // mask of word NW32 - 1 (the top live word)
     uint32_t cmask;      // complement constant replicated over 16 fields
@@ -43,7 +45,7 @@ struct WideParams {
 template <int NW32>
 struct WideSpan {
     uint32_t a[NW32 + 1];  // forward span, 16 * (NW32 + 1) bases
-    uint32_t d[NW32 + 1];  // reverse complement of its first kRun + K - 1 bases, at bit 0
+    uint32_t d[NW32 + 1];  // reverse complement of its first ShapePair::kSpanSlots + K - 1 bases, at bit 0
     uint64_t inv_lo;       // invalid-base bits 0..63 of the span
     uint32_t inv_hi;       // bits 64..95
 };
@@ -100,13 +102,14 @@ struct WideWindow {
     uint64_t c0, c1, h0, h1;
 };
 
+// the window that starts j bases (= slots) after the span's first base
 template <int NW32>
 __device__ __forceinline__ WideWindow wide_window(const WideSpan<NW32>& s, int j, const WideConst& wc) {
     uint32_t f[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < NW32; ++i) {
         f[i] = __funnelshift_r(s.a[i], s.a[i + 1], 2 * j);
-        r[i] = __funnelshift_r(s.d[i], s.d[i + 1], 2 * (kRun - 1 - j));
+        r[i] = __funnelshift_r(s.d[i], s.d[i + 1], 2 * (ShapePair::kSpanSlots - 1 - j));
     }
     f[NW32 - 2] &= wc.mask_a; r[NW32 - 2] &= wc.mask_a;
     f[NW32 - 1] &= wc.mask_b; r[NW32 - 1] &= wc.mask_b;
@@ -145,36 +148,38 @@ struct WideAcc {
     uint32_t valid = 0;
 };
 
-// kRun consecutive slots (128-byte aligned per array).  TWO / CHECK as in emit_run.
+// One item = 4 chunks of two neighbouring slots (ShapePair: slots 4i, 4i+1 from the item's first).  TWO / CHECK as in
+// emit_run; a slot s exists iff s < nwin and belongs to span B iff s >= n_first.
 template <int NW32, bool TWO, bool CHECK, bool DIGEST, bool HASH>
 __device__ __forceinline__ void emit_wide_run(const WideSpan<NW32>& A, const WideSpan<NW32>& B, uint32_t n_first,
                                               const WideConst& wc, const WideOut& o, uint64_t slot0, uint32_t nwin,
                                               WideAcc& acc) {
 #pragma unroll
-    for (int j2 = 0; j2 < kRun; j2 += 2) {  // two windows = one 32-byte store per array
+    for (int i = 0; i < kRun / 2; ++i) {  // two windows = one 32-byte store per array
         WideWindow w[2];
         bool ok[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            const int j = j2 + t;
+            const int s_off = ShapePair::off(2 * i + t);
             WideSpan<NW32> s = A;
-            if (TWO && (uint32_t)j >= n_first) s = B;
-            w[t] = wide_window<NW32>(s, j, wc);
+            if (TWO && (uint32_t)s_off >= n_first) s = B;
+            w[t] = wide_window<NW32>(s, s_off, wc);
             ok[t] = true;
-            if (CHECK) ok[t] = wide_ok<NW32>(s, j, wc);
-            if (DIGEST && ok[t] && (uint32_t)j < nwin) {
+            if (CHECK) ok[t] = wide_ok<NW32>(s, s_off, wc);
+            if (DIGEST && ok[t] && (uint32_t)s_off < nwin) {
                 acc.canon += w[t].c0 + w[t].c1; acc.hash += w[t].h0 + w[t].h1; acc.valid += 1;
             }
             if (CHECK && !ok[t]) { w[t].c0 = w[t].c1 = w[t].h0 = w[t].h1 = ~0ull; }
         }
-        const uint64_t slot = slot0 + j2;
-        if ((uint32_t)j2 + 1 < nwin && o.vec_ok && (slot & 1ull) == 0ull) {
+        const int s0 = ShapePair::off(2 * i);
+        const uint64_t slot = slot0 + s0;
+        if ((uint32_t)s0 + 1 < nwin && o.vec_ok && (slot & 1ull) == 0ull) {
             if (o.canon) st_stream_v4u64(o.canon + 2 * slot, w[0].c0, w[0].c1, w[1].c0, w[1].c1);
             if (HASH && o.hash) st_stream_v4u64(o.hash + 2 * slot, w[0].h0, w[0].h1, w[1].h0, w[1].h1);
         } else {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                if ((uint32_t)(j2 + t) < nwin) {
+                if ((uint32_t)(s0 + t) < nwin) {
                     if (o.canon) st_stream_v2u64(o.canon + 2 * (slot + t), w[t].c0, w[t].c1);
                     if (HASH && o.hash) st_stream_v2u64(o.hash + 2 * (slot + t), w[t].h0, w[t].h1);
                 }
@@ -216,6 +221,7 @@ struct WideEng {
     using Params = WideParams;
     using Span = WideSpan<NW32>;
     static constexpr bool kValidate = VALIDATE;
+    using Shape = ShapePair;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = NW32 + 2;  // tile entries one span reads
     const WideParams& p;

@@ -72,6 +72,32 @@ struct ItemCtx {
     uint64_t r_b;    // read of span B's windows (two-span items; they start at position 0 of r_b)
 };
 
+// Which slots a work item covers, counted from its first slot.  An item always has kRun windows; `nwin` handed to
+// the engine is the number of SLOTS that exist from the item's first slot on (capped at kSpanSlots), so window j is
+// present iff off(j) < nwin, and comes from span B of a two-span item iff off(j) >= n_first.
+//   ShapeRun : kRun consecutive slots (64 B of an 8-byte array: one lane's two 32-byte stores fill half a line).
+//   ShapePair: for 16-byte slots.  kRun consecutive slots would be 128 B per lane, and a warp-wide 32-byte store would
+//              touch 32 different lines -- measured 5.1 TB/s instead of 6.1 (scripts/micro/store_patterns.cu; ncu: the
+//              L1 LSU data pipe is 93 % busy).  So lanes 2i and 2i+1 share 16 slots: lane 2i takes slots
+//              {0,1, 4,5, 8,9, 12,13}, lane 2i+1 the same + 2, and every store instruction covers 64 contiguous bytes per
+//              lane pair.  Still one span and kRun windows per lane.
+struct ShapeRun {
+    static constexpr int kSpanSlots = kRun;  // slots from the first to the last window, inclusive
+    static constexpr int kAlign = kRun;      // a pass must start at a multiple of this many slots
+    __device__ static __forceinline__ uint32_t first(uint32_t li) { return li * kRun; }
+    __device__ static __forceinline__ constexpr int off(int j) { return j; }
+    __device__ static __forceinline__ bool owns(uint32_t) { return true; }
+    __device__ static __forceinline__ uint32_t n_items(uint32_t n_slots) { return (n_slots + kRun - 1) / kRun; }
+};
+struct ShapePair {
+    static constexpr int kSpanSlots = 2 * kRun - 2;
+    static constexpr int kAlign = 2 * kRun;
+    __device__ static __forceinline__ uint32_t first(uint32_t li) { return (li >> 1) * (2 * kRun) + (li & 1u) * 2u; }
+    __device__ static __forceinline__ constexpr int off(int j) { return (j >> 1) * 4 + (j & 1); }
+    __device__ static __forceinline__ bool owns(uint32_t s) { return (s & 2u) == 0u; }
+    __device__ static __forceinline__ uint32_t n_items(uint32_t n_slots) { return ((n_slots + 2 * kRun - 1) / (2 * kRun)) * 2; }
+};
+
 // Number of windows j in [j0, j1) starting at tile base rel + j whose K bases are all valid
 // (K <= 64, j1 <= kRun).  NE = tile entries that may be read (the engine's span size).
 template <int NE>
@@ -163,37 +189,82 @@ __device__ __forceinline__ void for_each_item(uint32_t n_items, Item&& item, Rou
     }
 }
 
-// One pass over the items of a staged tile.  Two-phase engines (compaction) first count the valid
-// windows of every item, scan the counts CTA-wide, then emit at the scanned offsets.
-template <class Eng, class Visit>
-__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Visit&& visit) {
+// Items off the common path -- two-span items, spans that hold an invalid base -- are few, but a warp that meets one
+// executes that path for a handful of lanes at the full instruction cost of the common path (measured: +60..100 %
+// ALU work whenever W is not a multiple of the item size).  Plain engines therefore only note such items during the
+// first sweep and run them afterwards, densely packed: 32 of them per warp instruction.
+struct Deferred {
+    uint32_t n;
+    uint16_t li[kItemsPerCta];
+};
+static_assert(kItemsPerCta <= 65536, "deferred item indices are 16-bit");
+__device__ __forceinline__ Deferred& deferred() {
+    __shared__ Deferred d;
+    return d;
+}
+// called by the bodies ahead of the barrier that ends staging
+__device__ __forceinline__ void deferred_reset() {
+    if (threadIdx.x == 0) deferred().n = 0;
+}
+__device__ __forceinline__ void defer(uint32_t li) {
+    Deferred& d = deferred();
+    d.li[atomicAdd(&d.n, 1u)] = (uint16_t)li;
+}
+
+// One pass over the items of a staged tile.  `item(li, one, two, single)` classifies item li and calls exactly one of
+// the three handlers (single: once per window).  Two-phase engines (compaction) first count the valid windows of
+// every item, scan the counts CTA-wide, then emit at the scanned offsets.
+template <class Eng, class Item>
+__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item) {
+    constexpr uint32_t kAll = (uint32_t)Eng::Shape::kSpanSlots;
+    auto emit_one = [&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+        const typename Eng::Span s = eng.load(tile, rel);
+        if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kAll, slot0, nwin, ic);
+        else eng.template run<false, false>(s, s, kAll, slot0, nwin, ic);
+    };
+    auto emit_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+        const typename Eng::Span a = eng.load(tile, rel_a);
+        const typename Eng::Span b = eng.load(tile, rel_b);
+        if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
+        else eng.template run<true, false>(a, b, left, slot0, nwin, ic);
+    };
+    auto emit_single = [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); };
+
     if constexpr (Eng::kTwoPhase) {
         eng.begin_pass(n_items);
         __syncthreads();
-        visit([&](uint32_t rel, uint64_t, uint32_t nwin, const ItemCtx& ic) {
-                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, nwin)); },
-              [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t, uint32_t nwin, const ItemCtx& ic) {
-                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
-                                       count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin)); },
-              [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
-                  eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1)); },
-              [](uint32_t) {});
+        auto count_one = [&](uint32_t rel, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+            eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, nwin));
+        };
+        auto count_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+            eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
+                                 count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin));
+        };
+        auto count_single = [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
+            eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1));
+        };
+        for_each_item<true>(n_items, [&](uint32_t li) { item(li, count_one, count_two, count_single); }, [](uint32_t) {});
         __syncthreads();
         eng.scan(n_items);
         __syncthreads();
         if (Eng::kCountOnly) return;
+        for_each_item<true>(n_items, [&](uint32_t li) { item(li, emit_one, emit_two, emit_single); },
+                            [&](uint32_t q_round) { eng.round_end(q_round, n_items); });
+    } else {
+        // sweep 1: the common path (one clean span); everything else is noted
+        auto fast_one = [&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+            const typename Eng::Span s = eng.load(tile, rel);
+            if (Eng::kValidate && eng.dirty(s)) defer(ic.li);
+            else eng.template run<false, false>(s, s, kAll, slot0, nwin, ic);
+        };
+        auto later_two = [&](uint32_t, uint32_t, uint32_t, uint64_t, uint32_t, const ItemCtx& ic) { defer(ic.li); };
+        for_each_item<false>(n_items, [&](uint32_t li) { item(li, fast_one, later_two, emit_single); }, [](uint32_t) {});
+        __syncthreads();
+        // sweep 2: the noted items, one per lane
+        const Deferred& d = deferred();
+        const uint32_t n_def = d.n;
+        for (uint32_t i = threadIdx.x; i < n_def; i += blockDim.x) item(d.li[i], emit_one, emit_two, emit_single);
     }
-    visit([&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
-              const typename Eng::Span s = eng.load(tile, rel);
-              if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kRun, slot0, nwin, ic);
-              else eng.template run<false, false>(s, s, kRun, slot0, nwin, ic); },
-          [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
-              const typename Eng::Span a = eng.load(tile, rel_a);
-              const typename Eng::Span b = eng.load(tile, rel_b);
-              if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
-              else eng.template run<true, false>(a, b, left, slot0, nwin, ic); },
-          [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); },
-          [&](uint32_t q_round) { if constexpr (Eng::kTwoPhase) eng.round_end(q_round, n_items); });
 }
 
 template <class Eng>
@@ -215,42 +286,47 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
     const uint32_t span = q_last * g.L32 + (u_last - q_last * g.W32) - p_first + K;
     const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile);
+    deferred_reset();
     __syncthreads();
 
     // ---- phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than
     //      kRun windows, a run of single windows
-    const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-    auto visit = [&](auto&& one, auto&& two, auto&& single, auto&& round_end) {
-        auto item = [&](uint32_t li) {
-            const uint32_t u = p_first + li * kRun;           // first slot, counted from window 0 of read r_first
+    using Shape = typename Eng::Shape;
+    const uint32_t n_items = Shape::n_items(n_slots);
+    auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
+        {
+            const uint32_t fs = Shape::first(li);              // the item's first slot, counted from the CTA's
+            if (fs >= n_slots) return;
+            const uint32_t u = p_first + fs;                   // ... and from window 0 of read r_first
             const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
             const uint32_t pos = u - q * g.W32;                 // window position inside its read
-            const uint64_t slot0 = slot_base + (uint64_t)li * kRun;
-            const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
+            const uint64_t slot0 = slot_base + fs;
+            const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, n_slots - fs);
             const uint32_t rel = q * g.L32 + pos - p_first + mis;  // first base, relative to tile entry 0
             const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
             const ItemCtx ic{li, r_first + q, pos, r_first + q + 1};
-            if (left >= (uint32_t)kRun || left >= nwin) {
+            if (left >= (uint32_t)Shape::kSpanSlots || left >= nwin) {
                 one(rel, slot0, nwin, ic);
-            } else if (g.W32 >= (uint32_t)kRun) {
-                // straddles exactly one boundary: windows j >= left start read q+1 at position j - left
+            } else if (g.W32 >= (uint32_t)Shape::kSpanSlots) {
+                // straddles exactly one boundary: slots s >= left start read q+1 at position s - left
                 two(rel, (q + 1) * g.L32 - p_first + mis - left, left, slot0, nwin, ic);
             } else {
-                for (uint32_t j = 0; j < nwin; ++j) {
-                    const uint32_t uj = u + j, qj = div_w(uj, g, slots_per_cta), pj = uj - qj * g.W32;
-                    single(qj * g.L32 + pj - p_first + mis, slot0 + j, ItemCtx{li, r_first + qj, pj, 0});
+                for (uint32_t s = 0; s < nwin; ++s) {
+                    if (!Shape::owns(s)) continue;
+                    const uint32_t us = u + s, qs = div_w(us, g, slots_per_cta), ps = us - qs * g.W32;
+                    single(qs * g.L32 + ps - p_first + mis, slot0 + s, ItemCtx{li, r_first + qs, ps, 0});
                 }
             }
-        };
-        for_each_item<Eng::kTwoPhase>(n_items, item, round_end);
+        }
     };
-    run_pass(eng, tile, K, n_items, visit);
+    run_pass(eng, tile, K, n_items, item);
 }
 
 // ---------------------------------------------------------------------------
 // ragged reads (CSR offsets)
 // ---------------------------------------------------------------------------
 constexpr int kCsrCache = 1024;  // reads whose offsets a CTA keeps in shared memory per pass
+constexpr int kCsrGroup = 8;     // items per entry of the per-pass owner table
 
 struct CsrGeom {
     const uint8_t* bases;
@@ -283,11 +359,13 @@ struct CsrPass {  // one staged stretch: slots [slot_lo, slot_hi) of reads [r_lo
 template <class Eng>
 __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint64_t* c_off,
                                          uint64_t* c_win, CsrPass* pass, uint32_t tile_idx) {
+    using Shape = typename Eng::Shape;
     const uint32_t K = eng.K();
     const uint64_t slots_per_cta = (uint64_t)g.items_per_cta * kRun;
     const uint64_t slot_begin = (uint64_t)tile_idx * slots_per_cta;
     const uint64_t slot_end = min(g.total_slots, slot_begin + slots_per_cta);
     const uint32_t tile_bases = (g.tile_entries - Eng::kSpanEntries - 1) * 16;  // bases one pass can stage
+    __shared__ uint64_t grp[kItemsPerCta / kCsrGroup + 1];
 
     // reads this CTA can touch; their offsets go to shared memory when they fit (the common case)
     const uint64_t R_lo = g.first_read[tile_idx], R_hi = g.first_read[tile_idx + 1];
@@ -309,35 +387,53 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         if (threadIdx.x == 0) {
             CsrPass ps;
             ps.slot_lo = cur;
-            ps.r_lo = last_le(win, r_cur, R_hi, cur);  // owner of slot `cur`
+            ps.r_lo = cur == slot_begin ? R_lo : last_le(win, r_cur, R_hi, cur);  // owner of slot `cur`
             ps.g0 = off[ps.r_lo] + (cur - win[ps.r_lo]);
-            // windows starting before g_lim fit wholly in a tile that starts at g0
-            const uint64_t g_lim = ps.g0 + tile_bases - K + 1;
-            uint64_t lim = slot_end;
-            if (g_lim < g.n_bases) {
-                const uint64_t r = last_le(off, ps.r_lo, R_hi, g_lim);
-                const uint64_t w_r = win[r + 1] - win[r];
-                lim = min(lim, win[r] + min(g_lim - off[r], w_r));  // slots whose window starts before g_lim
+            // The common case needs no search: everything up to the CTA's last slot fits one tile.  That slot's owner is
+            // R_hi or, when R_hi starts exactly at slot_end, the nearest earlier read that has windows.
+            uint64_t r_last = R_hi;
+            while (win[r_last] > slot_end - 1) --r_last;
+            const uint64_t g_end_all = off[r_last] + (slot_end - 1 - win[r_last]) + K;
+            if (g_end_all - ps.g0 <= (uint64_t)tile_bases) {
+                ps.slot_hi = slot_end;
+                ps.r_hi = r_last;
+                ps.span = (uint32_t)(g_end_all - ps.g0);
+            } else {
+                // windows starting before g_lim fit wholly in a tile that starts at g0
+                const uint64_t g_lim = ps.g0 + tile_bases - K + 1;
+                uint64_t lim = slot_end;
+                if (g_lim < g.n_bases) {
+                    const uint64_t r = last_le(off, ps.r_lo, R_hi, g_lim);
+                    const uint64_t w_r = win[r + 1] - win[r];
+                    lim = min(lim, win[r] + min(g_lim - off[r], w_r));  // slots whose window starts before g_lim
+                }
+                if (lim < slot_end && lim - cur >= (uint64_t)Shape::kAlign) lim = cur + ((lim - cur) / Shape::kAlign) * Shape::kAlign;  // keep items aligned
+                ps.slot_hi = lim;
+                ps.r_hi = last_le(win, ps.r_lo, R_hi, lim - 1);
+                const uint64_t g_end = off[ps.r_hi] + (lim - 1 - win[ps.r_hi]) + K;
+                ps.span = (uint32_t)(g_end - ps.g0);
             }
-            if (lim < slot_end && lim - cur >= (uint64_t)kRun) lim = cur + ((lim - cur) / kRun) * kRun;  // keep items aligned
-            ps.slot_hi = lim;
-            ps.r_hi = last_le(win, ps.r_lo, R_hi, lim - 1);
-            const uint64_t g_end = off[ps.r_hi] + (lim - 1 - win[ps.r_hi]) + K;
-            ps.span = (uint32_t)(g_end - ps.g0);
             *pass = ps;
         }
         __syncthreads();
         const CsrPass ps = *pass;
+        const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
+        const uint32_t n_items = Shape::n_items(n_slots);
+        // owner of the first slot of every group of kCsrGroup items: an item then searches a handful of reads, not the pass
+        const uint32_t n_groups = (n_items + kCsrGroup - 1) / kCsrGroup;
+        for (uint32_t t = threadIdx.x; t <= n_groups; t += blockDim.x)
+            grp[t] = last_le(win, ps.r_lo, ps.r_hi, min(ps.slot_lo + (uint64_t)t * (kCsrGroup * kRun), ps.slot_hi - 1));
         const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, ps.g0, ps.span, Eng::kSpanEntries, enc, tile);
+        deferred_reset();
         __syncthreads();
 
-        const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
-        const uint32_t n_items = (n_slots + kRun - 1) / kRun;
-        auto visit = [&](auto&& one, auto&& two, auto&& single, auto&& round_end) {
-            auto item = [&](uint32_t li) {
-                const uint64_t slot0 = ps.slot_lo + (uint64_t)li * kRun;
-                const uint32_t nwin = min((uint32_t)kRun, n_slots - li * kRun);
-                uint64_t r = last_le(win, ps.r_lo, ps.r_hi, slot0);
+        auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
+            {
+                const uint32_t fs = Shape::first(li);
+                if (fs >= n_slots) return;
+                const uint64_t slot0 = ps.slot_lo + fs;
+                const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, n_slots - fs);
+                uint64_t r = last_le(win, grp[li / kCsrGroup], grp[li / kCsrGroup + 1], slot0);
                 const uint64_t pos = slot0 - win[r];
                 const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
                 const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
@@ -353,15 +449,14 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
                 }
                 // several short reads inside one item: window by window
                 uint64_t p = pos, w_r = win[r + 1] - win[r];
-                for (uint32_t j = 0; j < nwin; ++j) {
+                for (uint32_t s = 0; s < nwin; ++s) {
                     while (p >= w_r) { ++r; p = 0; w_r = win[r + 1] - win[r]; }
-                    single((uint32_t)(off[r] + p - ps.g0) + mis, slot0 + j, ItemCtx{li, r, p, 0});
+                    if (Shape::owns(s)) single((uint32_t)(off[r] + p - ps.g0) + mis, slot0 + s, ItemCtx{li, r, p, 0});
                     ++p;
                 }
-            };
-            for_each_item<Eng::kTwoPhase>(n_items, item, round_end);
+            }
         };
-        run_pass(eng, tile, K, n_items, visit);
+        run_pass(eng, tile, K, n_items, item);
         __syncthreads();  // the next pass overwrites the tile
         cur = ps.slot_hi;
         r_cur = ps.r_hi;

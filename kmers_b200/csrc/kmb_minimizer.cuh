@@ -109,6 +109,7 @@ struct MinimizerEng {
     using Params = MinParams;
     using Span = kmb::Span;
     static constexpr bool kValidate = VALIDATE;
+    using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;
     const MinParams& p;

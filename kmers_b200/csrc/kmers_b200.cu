@@ -869,7 +869,7 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         for (int i = 0; i < 4; ++i) mask[i] = 2 * k > 32u * i ? mask32(2 * k - 32 * i) : 0u;
         WideParams ep{};
         ep.wc.K = k;
-        ep.wc.shiftD = 2 * (16 * (nw32 + 1) - (kRun + k - 1));
+        ep.wc.shiftD = 2 * (16 * (nw32 + 1) - (ShapePair::kSpanSlots + k - 1));
         ep.wc.mask_a = mask[nw32 - 2]; ep.wc.mask_b = mask[nw32 - 1];
         ep.wc.cmask = enc.cmask; ep.wc.cm_a = enc.cmask & ep.wc.mask_a; ep.wc.cm_b = enc.cmask & ep.wc.mask_b;
         ep.wc.kmask = k >= 64 ? ~0ull : ((1ull << k) - 1ull);

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Run ONE kernel family a few times so that ncu can capture it:  python scripts/prof_one.py wide|hist|compact|minimizers|csr|canon|full|pack8|pack64"""
-import ctypes as C
+"""Run ONE kernel family a few times (for ncu), or time it with CUDA events:
+    python scripts/prof_one.py wide|hist|compact|minimizers|csr|canon|full|pack8|pack64|csr_wide|csr_min [--time]
+4M x 150 bp reads, K=31 (wide: K=63).  --time prints ms per launch and algorithmic GB/s."""
+import json
 import os
 import sys
 
@@ -11,39 +13,63 @@ import kmers_b200 as kb
 from kmers_b200.context import _ptr
 
 what = sys.argv[1]
+timed = "--time" in sys.argv
 n, L, K = 4_000_000, 150, 31
 torch.cuda.set_device(0)
-ctx = kb.Context(0)
+stream = torch.cuda.Stream()
+ctx = kb.Context(0, stream=stream.cuda_stream)
 i64 = lambda m: torch.empty(m, dtype=torch.int64, device="cuda")
 batch = ctx.generate(42, n, L, n_thresh20=1049 if what == "compact" else 0)
+W = L - K + 1
+if what.startswith("csr"):  # same reads, ragged (CSR) geometry
+    offs = (torch.arange(0, n + 1, dtype=torch.int64) * L).numpy().astype("uint64")
+    batch = ctx.upload(batch.download(), offsets=offs)
+
+if what in ("wide", "csr_wide"):
+    w = L - 63 + 1
+    c = i64(2 * n * w)
+    alg = n * (L + w * 16)
+    step = lambda: ctx._ck(ctx._lib.kmb_extract_canonical_wide(ctx._h, 63, kb.ENC_ACGT, 0, _ptr(c), None, None))
+elif what == "hist":
+    alg = n * L
+    step = lambda: batch.histogram(K, 16, digest=False)
+elif what == "compact":
+    alg = None
+    step = lambda: batch.extract_compact(K, to="device")
+elif what in ("minimizers", "csr_min"):
+    alg = n * (L + W * 12)
+    mm, pp = i64(n * W), torch.empty(n * W, dtype=torch.int32, device="cuda")
+    step = lambda: ctx._ck(ctx._lib.kmb_minimizers(ctx._h, 31, 15, 15, 0, _ptr(mm), _ptr(pp)))
+elif what in ("csr", "full"):
+    alg = n * (L + W * 16)
+    out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=i64(n * W))
+    step = lambda: batch.extract_canonical(K, out=out)
+elif what == "canon":
+    alg = n * (L + W * 8)
+    out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=None)
+    step = lambda: batch.extract_canonical(K, out=out)
+elif what in ("pack8", "pack64"):
+    alg = n * L + n * ((L + 31) // 32) * 8
+    bits = int(what[4:])
+    step = lambda: batch.pack(kb.ENC_ACGT, bits, to="device")
+else:
+    raise SystemExit(f"unknown kernel family {what}")
+
 for _ in range(3):
-    if what == "wide":
-        w = L - 63 + 1
-        c = i64(2 * n * w)
-        ctx._ck(ctx._lib.kmb_extract_canonical_wide(ctx._h, 63, kb.ENC_ACGT, 0, _ptr(c), None, None))
-    elif what == "hist":
-        batch.histogram(K, 16, digest=False)
-    elif what == "compact":
-        r = batch.extract_compact(K, to="device")
-    elif what == "minimizers":
-        batch.minimizers(31, 15, to="device")
-    elif what == "csr":
-        if _ == 0:
-            offs = torch.arange(0, n + 1, dtype=torch.int64, device="cuda") * L   # same reads, ragged (CSR) geometry
-            bases = batch.download()
-            batch = ctx.upload(bases, offsets=offs.cpu().numpy().astype("uint64"))
-            out = kb.CanonicalKmers(k=K, n_slots=n * (L - K + 1), canon=i64(n * (L - K + 1)), hash=i64(n * (L - K + 1)))
-        batch.extract_canonical(K, out=out)
-    elif what == "full":
-        if _ == 0:
-            out = kb.CanonicalKmers(k=K, n_slots=n * (L - K + 1), canon=i64(n * (L - K + 1)), hash=i64(n * (L - K + 1)))
-        batch.extract_canonical(K, out=out)
-    elif what == "pack8":
-        batch.pack(kb.ENC_ACGT, 8, to="device")
-    elif what == "pack64":
-        batch.pack(kb.ENC_ACGT, 64, to="device")
-    elif what == "canon":
-        out = kb.CanonicalKmers(k=K, n_slots=n * (L - K + 1), canon=i64(n * (L - K + 1)), hash=None)
-        batch.extract_canonical(K, out=out)
+    step()
+ctx.sync()
+if timed:
+    reps = 20
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record(stream)
+        step()
+        b.record(stream)
     ctx.sync()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    avg = sum(ms) / len(ms)
+    row = {"kernel": what, "avg_ms": round(avg, 4), "best_ms": round(ms[0], 4)}
+    if alg:
+        row.update(algorithmic_GB=alg / 1e9, GBps=round(alg / avg / 1e6, 1), frac_of_6535=round(alg / avg / 1e6 / 6535.7, 3))
+    print(json.dumps(row), flush=True)
 ctx.close()
