@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kExtractThreads) fixed_kernel(const FixedGeom 
 
 // dynamic shared memory: [tile_entries x uint2][kCsrCache + 2 offsets][kCsrCache + 2 window offsets]
 template <class Eng>
-__global__ void __launch_bounds__(kExtractThreads) csr_kernel(const CsrGeom g, const EncDesc enc, const typename Eng::Params ep) {
+__global__ void __launch_bounds__(kExtractThreads, 4) csr_kernel(const CsrGeom g, const EncDesc enc, const typename Eng::Params ep) {
     extern __shared__ uint2 tile[];
     __shared__ unsigned long long red[3][32];
     __shared__ CsrPass pass;

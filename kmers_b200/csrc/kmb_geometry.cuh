@@ -325,7 +325,7 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
 // ---------------------------------------------------------------------------
 // ragged reads (CSR offsets)
 // ---------------------------------------------------------------------------
-constexpr int kCsrCache = 1024;  // reads whose offsets a CTA keeps in shared memory per pass
+constexpr int kCsrCache = 512;   // reads whose offsets a CTA keeps in shared memory (more: read from global)
 constexpr int kCsrGroup = 8;     // items per entry of the per-pass owner table
 
 struct CsrGeom {

@@ -5,7 +5,12 @@ namespace kmb {
 
 cudaError_t launch_minimizers(bool validate, const FixedGeom* fg, const CsrGeom* cg, const Launch& l, cudaStream_t st,
                               const EncDesc& enc, const MinParams& ep) {
-    return validate ? launch_eng<MinimizerEng<true>>(fg, cg, l, st, enc, ep) : launch_eng<MinimizerEng<false>>(fg, cg, l, st, enc, ep);
+    const int cls = ep.mc.w <= 13 ? 0 : (ep.mc.w <= 15 ? 1 : 2);  // width class of the candidate compare (kmb_minimizer.cuh)
+#define KMB_CASE(V, C) \
+    if (validate == V && cls == C) return launch_eng<MinimizerEng<V, C>>(fg, cg, l, st, enc, ep);
+    KMB_CASE(true, 0) KMB_CASE(true, 1) KMB_CASE(true, 2) KMB_CASE(false, 0) KMB_CASE(false, 1) KMB_CASE(false, 2)
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
 }
 
 // Kmer::minimizer_word (naive_impl/kmer.rs:170-191) on every word: leftmost width-mer of minimum LexHash.

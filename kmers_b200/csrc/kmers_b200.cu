@@ -796,8 +796,11 @@ extern "C" int32_t kmb_minimizers(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t
     if (n_slots) {
         MinParams ep{};
         ep.mc.wc = make_winconst(k, enc);
-        ep.mc.w = w; ep.mc.m = k - w + 1; ep.mc.hshift = hash_k < w ? 2 * (w - hash_k) : 0;
+        ep.mc.w = w; ep.mc.m = k - w + 1;
         ep.mc.wmask = w >= 32 ? ~0ull : ((1ull << (2 * w)) - 1ull);
+        const uint32_t hshift = hash_k < w ? 2 * (w - hash_k) : 0;  // the hash keeps only the first hash_k bases (hash.rs:69)
+        ep.mc.hmask64 = ep.mc.wmask & ~((1ull << hshift) - 1ull);
+        ep.mc.hmask32 = w <= 13 ? (uint32_t)ep.mc.hmask64 << 6 : (uint32_t)ep.mc.hmask64;
         const unsigned __int128 c96 = ((unsigned __int128)enc.cmask) | ((unsigned __int128)enc.cmask << 32) | ((unsigned __int128)enc.cmask << 64);
         const unsigned __int128 vm = c96 >> ep.mc.wc.shiftD;
         ep.mc.vm0 = (uint32_t)vm; ep.mc.vm1 = (uint32_t)(vm >> 32); ep.mc.vm2 = (uint32_t)(vm >> 64);

@@ -29,7 +29,10 @@ def test_reference_minimizer_goldens(ctx):
 
 
 @pytest.mark.parametrize("k,w,hk", [(31, 15, 15), (31, 21, 21), (31, 24, 32), (31, 31, 31), (31, 1, 1), (32, 17, 17), (21, 11, 11),
-                                     (15, 12, 5), (9, 3, 3), (7, 7, 7), (31, 19, 10), (5, 2, 2), (32, 32, 32), (20, 13, 13)])
+                                     (15, 12, 5), (9, 3, 3), (7, 7, 7), (31, 19, 10), (5, 2, 2), (32, 32, 32), (20, 13, 13),
+                                     # the three width classes of the compare (w <= 13, <= 15, wider), short / long windows
+                                     (31, 14, 14), (31, 15, 7), (16, 15, 15), (32, 13, 13), (32, 8, 8), (32, 1, 1), (20, 14, 3),
+                                     (31, 16, 16), (22, 15, 15), (21, 14, 14), (32, 13, 2)])
 def test_minimizers_fixed_vs_oracle(ctx, k, w, hk):
     import oracle as ko
     rng = np.random.default_rng(k * 100 + w)
@@ -45,7 +48,7 @@ def test_minimizers_low_complexity_ties(ctx):
     import oracle as ko
     reads = [b"A" * 100, b"AC" * 50, b"ACG" * 34, b"T" * 40 + b"A" * 60, (b"ACGT" * 30)[:100], b"G" * 99 + b"N"]
     bases = np.frombuffer(b"".join(r[:100].ljust(100, b"A") for r in reads), dtype=np.uint8)
-    for k, w in [(31, 15), (17, 5), (9, 9), (32, 8)]:
+    for k, w in [(31, 15), (17, 5), (9, 9), (32, 8), (31, 13), (20, 14), (31, 16), (14, 13), (32, 2)]:
         mm, pos = ctx.upload(bases, fixed_len=100).minimizers(k, w)
         rmm, rpos = ko.minimizers_batch(bases, k, w, w, n_reads=len(reads), fixed_len=100)
         assert np.array_equal(mm, rmm) and np.array_equal(pos, rpos), (k, w)
