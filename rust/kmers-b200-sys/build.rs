@@ -1,17 +1,19 @@
 // UNVERIFIED SOURCE (no Rust toolchain in the build image).
-// Compiles the CUDA translation unit for sm_100a and links it plus the CUDA runtime.
+// Compiles the CUDA translation units (kmers_b200/csrc/*.cu) for sm_100a into one shared library and links it.
 use std::{env, path::PathBuf, process::Command};
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
-    let src = root.join("kmers_b200/csrc/kmers_b200.cu");
+    let mut srcs: Vec<PathBuf> = std::fs::read_dir(root.join("kmers_b200/csrc")).unwrap()
+        .map(|e| e.unwrap().path()).filter(|p| p.extension().map_or(false, |x| x == "cu")).collect();
+    srcs.sort();
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libkmers_b200.so");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let status = Command::new(nvcc)
         .args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
-        .arg(&src)
+        .args(&srcs)
         .status()
         .expect("nvcc not runnable");
     assert!(status.success(), "nvcc failed");
