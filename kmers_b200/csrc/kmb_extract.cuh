@@ -243,6 +243,7 @@ struct NarrowEng {
     using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;  // tile entries one span reads
+    static constexpr int kMinCtas = 1, kMinCtasCsr = 4;  // resident CTAs per SM the register allocation must allow
     const NarrowParams& p;
     Acc acc;
     __device__ explicit NarrowEng(const NarrowParams& params) : p(params) {}
@@ -262,7 +263,7 @@ struct NarrowEng {
 };
 
 template <class Eng>
-__global__ void __launch_bounds__(kExtractThreads) fixed_kernel(const FixedGeom g, const EncDesc enc, const typename Eng::Params ep) {
+__global__ void __launch_bounds__(kExtractThreads, Eng::kMinCtas) fixed_kernel(const FixedGeom g, const EncDesc enc, const typename Eng::Params ep) {
     extern __shared__ uint2 tile[];
     __shared__ unsigned long long red[3][32];
     Eng eng(ep);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kExtractThreads) fixed_kernel(const FixedGeom 
 
 // dynamic shared memory: [tile_entries x uint2][kCsrCache + 2 offsets][kCsrCache + 2 window offsets]
 template <class Eng>
-__global__ void __launch_bounds__(kExtractThreads, 4) csr_kernel(const CsrGeom g, const EncDesc enc, const typename Eng::Params ep) {
+__global__ void __launch_bounds__(kExtractThreads, Eng::kMinCtasCsr) csr_kernel(const CsrGeom g, const EncDesc enc, const typename Eng::Params ep) {
     extern __shared__ uint2 tile[];
     __shared__ unsigned long long red[3][32];
     __shared__ CsrPass pass;

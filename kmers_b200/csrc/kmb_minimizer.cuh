@@ -218,6 +218,7 @@ struct MinimizerEng {
     using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;
+    static constexpr int kMinCtas = 4, kMinCtasCsr = 4;
     const MinParams& p;
     __device__ explicit MinimizerEng(const MinParams& params) : p(params) {}
     __device__ __forceinline__ uint32_t K() const { return p.mc.wc.K; }
