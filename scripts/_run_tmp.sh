@@ -1,3 +1,5 @@
-timeout 600 python -m pytest tests/test_gpu_minimizers.py -x -q -m gpu 2>&1 | tail -2
-for k in minimizers csr_min hist; do timeout 120 python scripts/prof_one.py $k --time 2>&1 | tail -1; done
-bash scripts/profile_kernels.sh r01h "hist" 2>&1 | tail -1
+export PATH=/usr/local/cuda/bin:$PATH
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_minimizers.py tests/test_gpu_compact.py tests/test_gpu_packed.py -x -q -m gpu 2>&1 | tail -6
+echo "memcheck rc=$?"
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "geometry or ragged or wide or straddl or short" 2>&1 | tail -6
+echo "racecheck rc=$?"
