@@ -194,61 +194,84 @@ __device__ __forceinline__ uint32_t get32_signed(const uint32_t* w, int nw, int 
     return __funnelshift_r(lo, hi, sh);
 }
 
+// how an item is read and written: widest natural vector when item size and addresses allow, else words, else bytes
+template <int NW32>
+struct ItemIo {
+    static constexpr int VB = NW32 >= 4 ? 16 : 4 * NW32;
+    bool aligned, vec;
+    __device__ __forceinline__ ItemIo(const uint8_t* src, const uint8_t* dst, uint32_t item_bytes) {
+        aligned = (item_bytes == 4u * NW32) && ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0);
+        vec = aligned && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (VB - 1)) == 0;
+    }
+    __device__ __forceinline__ void load(const uint8_t* src, uint32_t item_bytes, uint32_t (&w)[NW32]) const {
+        if (vec && NW32 >= 4) {
+#pragma unroll
+            for (int i = 0; i < NW32 / 4; ++i) {
+                const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+        } else if (vec && NW32 == 2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(src);
+            w[0] = v.x; w[1] = v.y;
+        } else if (aligned) {
+#pragma unroll
+            for (int i = 0; i < NW32; ++i) w[i] = reinterpret_cast<const uint32_t*>(src)[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW32; ++i) {
+                uint32_t v = 0;
+                for (int b = 0; b < 4; ++b)
+                    if ((uint32_t)(4 * i + b) < item_bytes) v |= (uint32_t)src[4 * i + b] << (8 * b);
+                w[i] = v;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(uint8_t* dst, uint32_t item_bytes, const uint32_t (&o)[NW32]) const {
+        if (vec && NW32 >= 4) {
+#pragma unroll
+            for (int i = 0; i < NW32 / 4; ++i)
+                reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        } else if (vec && NW32 == 2) {
+            *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+        } else if (aligned) {
+#pragma unroll
+            for (int i = 0; i < NW32; ++i) reinterpret_cast<uint32_t*>(dst)[i] = o[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW32; ++i)
+                for (int b = 0; b < 4; ++b)
+                    if ((uint32_t)(4 * i + b) < item_bytes) dst[4 * i + b] = (uint8_t)(o[i] >> (8 * b));
+        }
+    }
+};
+
+// kRevItems items per thread, a warp's items interleaved (item = base + u * 32 + lane) so that every load and store
+// instruction stays coalesced while each thread keeps kRevItems independent loads in flight.
+constexpr int kRevItems = 4;
 template <int NW32>
 __global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, uint8_t* out, uint64_t n_items,
                                                             uint32_t item_bytes, uint32_t K, uint32_t cmask) {
-    const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= n_items) return;
-    const uint8_t* src = in + item * item_bytes;
-    uint8_t* dst = out + item * item_bytes;
-    uint32_t w[NW32];
-    const bool aligned = (item_bytes == 4u * NW32) && ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0);
-    constexpr int VB = NW32 >= 4 ? 16 : 4 * NW32;  // widest natural vector for the item
-    const bool vec = aligned && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (VB - 1)) == 0;
-    if (vec && NW32 >= 4) {
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * kRevItems + (threadIdx.x & 31u);
+    const ItemIo<NW32> io(in, out, item_bytes);  // item stride keeps every item's alignment class equal to the first's
+    uint32_t w[kRevItems][NW32];
 #pragma unroll
-        for (int i = 0; i < NW32 / 4; ++i) {
-            const uint4 v = reinterpret_cast<const uint4*>(src)[i];
-            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-        }
-    } else if (vec && NW32 == 2) {
-        const uint2 v = *reinterpret_cast<const uint2*>(src);
-        w[0] = v.x; w[1] = v.y;
-    } else if (aligned) {
+    for (int u = 0; u < kRevItems; ++u) {
+        const uint64_t item = warp0 + (uint64_t)u * 32;
+        if (item < n_items) io.load(in + item * item_bytes, item_bytes, w[u]);
+    }
 #pragma unroll
-        for (int i = 0; i < NW32; ++i) w[i] = reinterpret_cast<const uint32_t*>(src)[i];
-    } else {
+    for (int u = 0; u < kRevItems; ++u) {
+        const uint64_t item = warp0 + (uint64_t)u * 32;
+        if (item >= n_items) continue;
+        uint32_t o[NW32];
 #pragma unroll
         for (int i = 0; i < NW32; ++i) {
-            uint32_t v = 0;
-            for (int b = 0; b < 4; ++b)
-                if ((uint32_t)(4 * i + b) < item_bytes) v |= (uint32_t)src[4 * i + b] << (8 * b);
-            w[i] = v;
+            const int nvalid = max(0, min(16, (int)K - 16 * i));  // fields of this group below K
+            const uint32_t vmask = nvalid == 16 ? 0xFFFFFFFFu : ((1u << (2 * nvalid)) - 1u);
+            const uint32_t srcbits = get32_signed(w[u], NW32, 2 * ((int)K - 16 * i - 16));
+            o[i] = (pair_reverse32(srcbits ^ cmask) & vmask) | (w[u][i] & ~vmask);
         }
-    }
-    uint32_t o[NW32];
-#pragma unroll
-    for (int i = 0; i < NW32; ++i) {
-        const int nvalid = max(0, min(16, (int)K - 16 * i));  // fields of this group below K
-        const uint32_t vmask = nvalid == 16 ? 0xFFFFFFFFu : ((1u << (2 * nvalid)) - 1u);
-        const uint32_t srcbits = get32_signed(w, NW32, 2 * ((int)K - 16 * i - 16));
-        o[i] = (pair_reverse32(srcbits ^ cmask) & vmask) | (w[i] & ~vmask);
-    }
-    if (vec && NW32 >= 4) {
-#pragma unroll
-        for (int i = 0; i < NW32 / 4; ++i)
-            reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-    } else if (vec && NW32 == 2) {
-        *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
-    } else if (aligned) {
-#pragma unroll
-        for (int i = 0; i < NW32; ++i) reinterpret_cast<uint32_t*>(dst)[i] = o[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < NW32; ++i)
-            for (int b = 0; b < 4; ++b)
-                if ((uint32_t)(4 * i + b) < item_bytes) dst[4 * i + b] = (uint8_t)(o[i] >> (8 * b));
+        io.store(out + item * item_bytes, item_bytes, o);
     }
 }
 

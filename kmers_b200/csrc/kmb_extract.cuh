@@ -40,7 +40,7 @@ struct OutPtrs {
     uint64_t* rc;
     unsigned long long* digest;  // n_valid, checksum_canon, checksum_hash
     unsigned long long* hist;    // fused histogram mode: global u64 bins
-    unsigned int* s_hist;        // MODE 2: this CTA's bins in shared memory, two 16-bit counters per word
+    unsigned int* s_hist;        // MODE 2: this CTA's bins in shared memory, two 16-bit counters per word (smem_hist_add)
     uint32_t hist_shift;         // 2K - hist_bits
     uint32_t vec_ok;             // output pointers are 32-byte aligned
 };
@@ -116,15 +116,17 @@ struct Acc {
     uint32_t valid = 0;
 };
 
-// MODE 2: one count into this CTA's shared-memory histogram.  Two 16-bit counters share a 32-bit word; when a
-// counter wraps (the returned old value shows 0xFFFF) the 65536 it stood for moves to the global bin at once, and a
-// carry out of the low half into the high half is taken back -- so the shared counts stay exact modulo 2^16.
+// MODE 2: one count into this CTA's shared-memory histogram.  Two 16-bit counters share a 32-bit word.  The
+// increment that takes a counter to 2^15 (its atomicAdd returned 0x7FFF: exactly one thread per lap sees that) moves
+// those 2^15 to the global bin at once.  A counter therefore stays far below 2^16 -- it would take another 32768
+// increments of the same bin between that thread's two consecutive atomics to overflow it -- so no carry ever
+// crosses into the neighbouring counter and the shared counts stay exact.
 __device__ __forceinline__ void smem_hist_add(const OutPtrs& o, uint32_t bin) {
     const uint32_t sh = (bin & 1u) * 16;
     const uint32_t old = atomicAdd(o.s_hist + (bin >> 1), 1u << sh);
-    if (((old >> sh) & 0xFFFFu) == 0xFFFFu) {
-        if (sh == 0) atomicSub(o.s_hist + (bin >> 1), 1u << 16);  // undo the carry into the neighbouring counter
-        atomicAdd(o.hist + bin, 65536ull);
+    if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {
+        atomicSub(o.s_hist + (bin >> 1), 0x8000u << sh);
+        atomicAdd(o.hist + bin, 32768ull);
     }
 }
 

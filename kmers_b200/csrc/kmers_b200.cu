@@ -1346,7 +1346,7 @@ extern "C" int32_t kmb_revcomp_words(kmb_ctx* ctx, int32_t enc_id, uint32_t k, u
     if (rc) return rc;
     OutBuf ob;
     if ((rc = out_prepare(ctx, 0, words_out, n_items * item_bytes, &ob))) return rc;
-    const uint64_t ctas = (n_items + 255) / 256;
+    const uint64_t ctas = (n_items + 256 * kRevItems - 1) / (256 * kRevItems);
     if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
     const unsigned grid = (unsigned)ctas;
     const uint8_t* in8 = (const uint8_t*)d_in;

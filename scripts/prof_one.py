@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run ONE kernel family a few times (for ncu), or time it with CUDA events:
-    python scripts/prof_one.py wide|hist|compact|minimizers|csr|canon|full|pack8|pack64|csr_wide|csr_min [--time]
+    python scripts/prof_one.py wide|hist|compact|minimizers|csr|canon|full|pack8|pack64|csr_wide|csr_min|csr_var|revcomp [--time]
 4M x 150 bp reads, K=31 (wide: K=63).  --time prints ms per launch and algorithmic GB/s."""
 import json
 import os
@@ -21,7 +21,14 @@ ctx = kb.Context(0, stream=stream.cuda_stream)
 i64 = lambda m: torch.empty(m, dtype=torch.int64, device="cuda")
 batch = ctx.generate(42, n, L, n_thresh20=1049 if what == "compact" else 0)
 W = L - K + 1
-if what.startswith("csr"):  # same reads, ragged (CSR) geometry
+n_slots = n * W
+if what == "csr_var":  # ragged reads of 100..150 bases cut from the same stream
+    import numpy as np
+    lens = np.random.default_rng(1).integers(100, 151, size=n).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    batch = ctx.upload(batch.download()[:int(offs[-1])], offsets=offs)
+    n_slots, n_bases = int((lens - (K - 1)).sum()), int(offs[-1])
+elif what.startswith("csr"):  # same reads, ragged (CSR) geometry
     offs = (torch.arange(0, n + 1, dtype=torch.int64) * L).numpy().astype("uint64")
     batch = ctx.upload(batch.download(), offsets=offs)
 
@@ -40,10 +47,17 @@ elif what in ("minimizers", "csr_min"):
     alg = n * (L + W * 12)
     mm, pp = i64(n * W), torch.empty(n * W, dtype=torch.int32, device="cuda")
     step = lambda: ctx._ck(ctx._lib.kmb_minimizers(ctx._h, 31, 15, 15, 0, _ptr(mm), _ptr(pp)))
-elif what in ("csr", "full"):
-    alg = n * (L + W * 16)
-    out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=i64(n * W))
+elif what in ("csr", "full", "csr_var"):
+    alg = n * (L + W * 16) if what != "csr_var" else n_bases + n_slots * 16
+    out = kb.CanonicalKmers(k=K, n_slots=n_slots, canon=i64(n_slots), hash=i64(n_slots))
     step = lambda: batch.extract_canonical(K, out=out)
+elif what == "revcomp":
+    import numpy as np
+    ni = 32_000_000
+    words = torch.randint(0, 2**62, (2 * ni,), dtype=torch.int64, device="cuda")
+    outw = torch.empty_like(words)
+    alg = ni * 32
+    step = lambda: ctx._ck(ctx._lib.kmb_revcomp_words(ctx._h, kb.ENC_ACGT, 63, 64, 2, _ptr(words), _ptr(outw), ni))
 elif what == "canon":
     alg = n * (L + W * 8)
     out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=None)

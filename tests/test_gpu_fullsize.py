@@ -155,3 +155,26 @@ def test_more_than_2_pow_32_slots():
             tot = [(a + b) % 2**64 for a, b in zip(tot, (d["n_valid"], d["checksum_canon"], d["checksum_hash"]))]
             del hb
         assert res.digest == tuple(tot)
+
+
+def test_histogram_exact_under_maximum_contention():
+    """Shared-memory bins: every thread of every CTA hammers the two 16-bit counters of ONE 32-bit word (hist_bits = 2:
+    poly-A / poly-T reads fall into bin 0, poly-G reads -- canonical poly-C -- into bin 1).  240 M increments; the
+    totals must still be exact: no carry may leak from one counter into its neighbour."""
+    import torch
+    import kmers_b200 as kb
+    n, k = 2_000_000, 31
+    reads = torch.full((n, L), ord("A"), dtype=torch.uint8, device="cuda")
+    reads[1::2] = ord("T")      # canonical poly-A again (reverse complement): same bin
+    reads[2::5] = ord("G")      # canonical poly-C
+    n_c = len(range(2, n, 5))
+    poly_c = int("01" * k, 2)   # LexHash of CCC...C
+    with kb.Context(0) as ctx:
+        batch = ctx.attach(reads.reshape(-1), fixed_len=L, n_reads=n)
+        for bits in (1, 2, 16, 20):
+            hist, dig = batch.histogram(k, bits, to="host")
+            assert dig[0] == n * (L - k + 1)
+            want = np.zeros(1 << bits, dtype=np.uint64)
+            want[0] = (n - n_c) * (L - k + 1)
+            want[poly_c >> (2 * k - bits)] += n_c * (L - k + 1)
+            assert np.array_equal(hist, want), bits
