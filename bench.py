@@ -101,7 +101,7 @@ class ClockSampler(threading.Thread):
 def cpu_reference(steps: int, warmup: int, sample_reads: int):
     """The reference's CPU path (oracle port) on all host threads, on a bounded sample of the workload."""
     import oracle as ko
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     bases = ko.generate_bases(SEED, 0, sample_reads * READ_LEN)
     n_kmers = sample_reads * (READ_LEN - K + 1)
 
@@ -148,6 +148,31 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+ORIG_AFFINITY = None  # the affinity this process started with (restored for the CPU baseline leg)
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank to the CPU cores next to its GPU (NVML's CPU affinity) BEFORE any pinned host memory is allocated, so
+    that the staging buffers land on the GPU's own NUMA node: with 8 ranks pulling 50+ GB/s each over PCIe, buffers on the
+    far socket would all squeeze through the inter-socket link.  Returns a short description for the JSON line."""
+    global ORIG_AFFINITY
+    try:
+        ORIG_AFFINITY = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus near gpu {local_rank}"
+    except Exception as ex:  # no NVML / restricted container: keep the inherited affinity
+        return f"inherited ({type(ex).__name__})"
+    return "inherited"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +201,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    host_affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "inherited (single rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
@@ -282,7 +308,7 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * n_slots / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": n_reads * L,
+        e2e = {"value": world * n_slots / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": n_reads * L, "host_affinity": host_affinity,
                "d2h_bytes_per_step": 24, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "what": "kmb_extract_canonical_host: pinned host reads -> chunked H2D overlapped with the kernel; canonical+hash "
                        "arrays stay device-resident, the (n_valid, checksum_canon, checksum_hash) digest is read back"}
@@ -317,6 +343,8 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu:
+        if ORIG_AFFINITY:
+            os.sched_setaffinity(0, ORIG_AFFINITY)  # the CPU path gets every core the job was given, not just the GPU's node
         r = cpu_reference(10, 1, 2_000_000)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"first {r['sample_reads']} reads of the same workload, iterator + canonical + LexHash materialised, "

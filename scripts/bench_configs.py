@@ -104,6 +104,17 @@ def main():
     avg, best = time_ms(stream, lambda: rb.extract_canonical(K, out=out))
     row("config2 bytes through the CSR (ragged) path", n * W, "kmers", n * (L + W * 16 + 16), avg, best)
 
+    # ragged reads of 100..150 bases cut from the same stream (items straddle read boundaries everywhere)
+    lens = torch.from_numpy(np.random.default_rng(1).integers(100, 151, size=n)).cuda()
+    voffs = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    voffs[1:] = torch.cumsum(lens, 0)
+    nb, ns = int(voffs[-1].item()), int((lens - (K - 1)).sum().item())
+    vb = ctx.attach(bases_dev[:nb], dev_offsets=voffs)
+    vout = kb.CanonicalKmers(k=K, n_slots=ns, canon=out.canon[:ns], hash=out.hash[:ns])
+    avg, best = time_ms(stream, lambda: vb.extract_canonical(K, out=vout))
+    row("ragged reads of 100..150 bp, K=31 canon+hash", ns, "kmers", nb + ns * 16 + n * 16, avg, best)
+    del vout, voffs, lens
+
     # ---------------- config 3: K=63 two words
     batch = ctx.attach(bases_dev, fixed_len=L)
     w63 = L - 63 + 1
@@ -138,6 +149,15 @@ def main():
     row("lexhash_words K=31", nk, "kmers", nk * 16, avg, best)
     avg, best = time_ms(stream, lambda: ctx._ck(ctx._lib.kmb_revcomp_words(ctx._h, kb.ENC_ACGT, 63, 64, 2, _ptr(words), _ptr(dst), nk // 2)))
     row("Encoding::rev_comp::<63> on [u64;2]", nk // 2, "kmers", nk * 16, avg, best)
+    mmw, mmo = torch.empty_like(words), torch.empty(nk, dtype=torch.int32, device="cuda")
+    avg, best = time_ms(stream, lambda: ctx._ck(ctx._lib.kmb_minimizer_words(ctx._h, 31, 15, 15, _ptr(words), nk, _ptr(mmw), _ptr(mmo))))
+    row("Kmer::minimizer_word k=31 w=15 on u64 words", nk, "kmers", nk * 20, avg, best)
+    del mmw, mmo
+    ni = nk // 4  # decode 25 M packed 31-mers (one u64 each) back to ASCII: 8 B in, 31 B out
+    txt = torch.empty(ni * 31, dtype=torch.uint8, device="cuda")
+    avg, best = time_ms(stream, lambda: ctx._ck(ctx._lib.kmb_unpack(ctx._h, kb.ENC_ACGT, 64, _ptr(words), ni, 1, 31, _ptr(txt))))
+    row("Encoding::decode of u64 31-mers (bulk unpack)", ni * 31, "bases", ni * (8 + 31), avg, best)
+    del txt
     del words, dst, out, out1, bases_dev, offs
 
     # ---------------- "next" rows: compacted output, minimizers, packed store (config-2 reads)
