@@ -83,62 +83,96 @@ __global__ void __launch_bounds__(256) pack_fixed_kernel(const PackParams p, uin
     store_packed32(p.out + r * p.out_bytes_per_read, g * 4, p.out_bytes_per_read, bits);
 }
 
-// Fixed-length reads whose packed region is a whole number of 32-bit groups: the same two-phase
-// shape as the extraction kernel.  A CTA owns kPackGroups consecutive OUTPUT groups (coalesced 4-byte
-// stores); it stages the stretch of reads they cover into shared memory with aligned 16-byte loads,
-// then every group is one funnel-shift extract of two packed entries.
+// Fixed-length reads: the same two-phase shape as the extraction kernel, in OUTPUT space.  A CTA owns kPackGroups
+// consecutive 32-bit words of the packed image (coalesced 4-byte stores); it stages the stretch of reads they cover
+// into shared memory with aligned 16-byte loads, then a word is one funnel-shift extract of two packed entries --
+// or, where a read's region ends inside the word (u8 / u16 word types: regions are whole words of P, not of 32 bits),
+// four one-byte extracts.
 constexpr int kPackGroups = 2048;
 
 struct PackTileParams {
     const uint8_t* bases;
     uint64_t n_bytes;
     uint64_t L;
-    uint64_t total_groups;  // n_reads * gpr
-    uint64_t gpr_magic64;   // floor(2^64 / gpr) + 1 (gpr >= 2), 0 = divide
+    uint64_t total_bytes;   // n_reads * obr
+    uint64_t obr_magic64;   // floor(2^64 / obr) + 1 (obr >= 2), 0 = divide
     uint32_t L32;
-    uint32_t gpr;           // 32-bit output groups per read
-    uint32_t gpr_magic;     // floor(2^32 / gpr) + 1
-    uint32_t* out;
+    uint32_t obr;           // output bytes per read = ceil(L / bases per word) * word bytes
+    uint32_t obr_magic;     // floor(2^32 / obr) + 1
+    uint8_t* out;           // 4-byte aligned
     EncDesc enc;
 };
 
-__device__ __forceinline__ uint32_t div_gpr(uint32_t u, const PackTileParams& p) {
-    if (p.gpr >= (uint32_t)kPackGroups) return (u >= p.gpr) ? 1u : 0u;
-    if (p.gpr == 1) return u;
-    return __umulhi(u, p.gpr_magic);
+// u / obr for u < obr + 4 * kPackGroups
+__device__ __forceinline__ uint32_t div_obr(uint32_t u, const PackTileParams& p) {
+    if (p.obr >= 4u * kPackGroups) return (u >= p.obr) ? 1u : 0u;
+    if (p.obr == 1) return u;
+    return __umulhi(u, p.obr_magic);
 }
 
 __global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) {
     extern __shared__ uint2 tile[];
-    const uint64_t grp_base = (uint64_t)blockIdx.x * kPackGroups;
-    const uint32_t n_groups = (uint32_t)min((uint64_t)kPackGroups, p.total_groups - grp_base);
+    const uint64_t byte_base = (uint64_t)blockIdx.x * (4u * kPackGroups);
+    const uint32_t n_out = (uint32_t)min((uint64_t)(4u * kPackGroups), p.total_bytes - byte_base);  // output bytes of this CTA
     uint64_t r_first;
-    if (p.gpr == 1) r_first = grp_base;
-    else if (p.gpr_magic64) r_first = div_magic64(grp_base, p.gpr_magic64);
-    else r_first = grp_base / p.gpr;
-    const uint32_t g_first = (uint32_t)(grp_base - r_first * p.gpr);
-    // bases from the first group's first base to the end of the last group's read (or of its 16 bases)
-    const uint64_t b_start = r_first * p.L + min((uint64_t)g_first * 16, p.L);
-    const uint32_t u_last = g_first + n_groups - 1, q_last = div_gpr(u_last, p);
-    const uint64_t g_last = u_last - q_last * p.gpr;
-    const uint64_t b_end = (r_first + q_last) * p.L + min(g_last * 16 + 16, p.L);
-    const uint8_t* first = p.bases + b_start;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
-    const uint32_t n_entries = (uint32_t)((b_end - b_start + mis + 15) >> 4) + 1;  // +1: a group reads 2 entries
+    if (p.obr == 1) r_first = byte_base;
+    else if (p.obr_magic64) r_first = div_magic64(byte_base, p.obr_magic64);
+    else r_first = byte_base / p.obr;
+    const uint32_t b_first = (uint32_t)(byte_base - r_first * p.obr);
+    // bases from the first byte's first base to the last byte's last base (a byte holds 4 bases; clipped to the read)
+    const uint64_t s_start = r_first * p.L + min((uint64_t)b_first * 4, p.L);
+    const uint32_t u_last = b_first + n_out - 1, q_last = div_obr(u_last, p);
+    const uint64_t s_end = (r_first + q_last) * p.L + min((uint64_t)(u_last - q_last * p.obr) * 4 + 4, p.L);
+    const uint8_t* first = p.bases + s_start;
+    // one entry of margin in front: the extract for the second read of a word starts before that read's first base
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u) + 16u;
+    const uint32_t n_entries = (uint32_t)((s_end - s_start + mis + 15) >> 4) + 2;  // an extract reads 2 entries, possibly from the stretch's very end
     stage_tile<false>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
     __syncthreads();
-    for (uint32_t li = threadIdx.x; li < n_groups; li += blockDim.x) {
-        const uint32_t u = g_first + li, q = div_gpr(u, p);
-        const uint64_t b0 = (uint64_t)(u - q * p.gpr) * 16;  // first base of the group inside its read
+    // the 16 bases from tile position rel (relative to the staged stretch)
+    auto extract = [&](uint32_t rel) -> uint32_t {
+        const uint32_t e = rel >> 4, o2 = (rel & 15u) * 2;
+        return __funnelshift_r(tile[e].x, tile[e + 1].x, o2);
+    };
+    auto low_bits = [](uint32_t n) -> uint32_t { return n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u); };
+    const uint32_t n_words = (n_out + 3) / 4;
+    for (uint32_t li = threadIdx.x; li < n_words; li += blockDim.x) {
+        const uint32_t u = b_first + 4 * li, q = div_obr(u, p), b = u - q * p.obr;  // first byte of the word inside its read
+        const uint32_t here = min(4u, n_out - 4 * li);                              // bytes of this word that exist
         uint32_t bits = 0;
-        if (b0 < p.L) {
-            const uint32_t rel = (uint32_t)((r_first + q) * p.L + b0 - b_start) + mis;
-            const uint32_t e = rel >> 4, o2 = (rel & 15u) * 2;
-            bits = __funnelshift_r(tile[e].x, tile[e + 1].x, o2);
-            const uint64_t left = p.L - b0;
-            if (left < 16) bits &= (1u << (2 * (uint32_t)left)) - 1u;  // padding is zero bits (naive.rs:117 mem::zeroed)
+        if ((p.obr & 3u) == 0) {  // kernel-uniform: regions are whole 32-bit words (u32 / u64 / u128 words of P, or lucky lengths)
+            const uint64_t b0 = (uint64_t)b * 4;
+            if (b0 < p.L) bits = extract((uint32_t)((r_first + q) * p.L + b0 - s_start) + mis) & low_bits(2 * (uint32_t)min((uint64_t)16, p.L - b0));
+        } else if (p.obr >= 4) {  // kernel-uniform
+            // A word holds bytes of at most two reads: n_a from read q (bases 4b ..), the rest from read q+1 (from its base
+            // 0 on).  Both parts are one 16-base extract, masked to the bases that exist -- the same instructions for every
+            // lane, whether its word straddles a region boundary or not (a branch here would cost every warp both paths).
+            const uint32_t n_a = min(here, p.obr - b);
+            const uint64_t b0 = (uint64_t)b * 4;
+            const uint32_t have_a = b0 < p.L ? (uint32_t)min((uint64_t)(4 * n_a), p.L - b0) : 0u;  // bases of read q in this word
+            const uint32_t rel_a = (uint32_t)((r_first + q) * p.L + min(b0, p.L) - s_start) + mis;
+            bits = extract(rel_a) & low_bits(2 * have_a);
+            const bool two = n_a < here;
+            const uint32_t have_b = two ? (uint32_t)min((uint64_t)(4 * (here - n_a)), p.L) : 0u;
+            // read q+1's base 0 lands at base 4 * n_a of the word: start 4 * n_a bases early (inside the margin at worst)
+            const uint32_t rel_b = two ? (uint32_t)((r_first + q + 1) * p.L - s_start) + mis - 4 * n_a : rel_a;
+            bits |= extract(rel_b) & (low_bits(8 * n_a + 2 * have_b) & ~low_bits(8 * n_a));
+        } else {
+            for (uint32_t j = 0; j < here; ++j) {  // regions of 1..3 bytes: byte by byte
+                const uint32_t uj = u + j, qj = div_obr(uj, p), bj = uj - qj * p.obr;
+                const uint64_t bj0 = (uint64_t)bj * 4;
+                if (bj0 < p.L) {
+                    const uint32_t have = (uint32_t)min((uint64_t)4, p.L - bj0);
+                    bits |= (extract((uint32_t)((r_first + qj) * p.L + bj0 - s_start) + mis) & low_bits(2 * have)) << (8 * j);
+                }
+            }
         }
-        p.out[grp_base + li] = bits;
+        uint8_t* dst = p.out + byte_base + 4 * li;
+        if (here == 4) {
+            *reinterpret_cast<uint32_t*>(dst) = bits;
+        } else {
+            for (uint32_t j = 0; j < here; ++j) dst[j] = (uint8_t)(bits >> (8 * j));  // the image's last, partial word
+        }
     }
 }
 

@@ -1247,19 +1247,19 @@ extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, vo
     if (total && words_out) {
         p.bases = ctx->d_bases; p.offsets = ctx->d_offsets; p.word_offsets = d_woff; p.n_reads = ctx->n_reads;
         p.L = ctx->fixed_len; p.word_bytes = word_bytes; p.bases_per_word = bpw; p.out = (uint8_t*)ob.dev;
-        if (!ctx->d_offsets && ((((ctx->fixed_len + bpw - 1) / bpw) * word_bytes) % 4 == 0) && ((uintptr_t)ob.dev & 3u) == 0 &&
-            ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes / 4 <= 0xFFFFFFFFull) {
-            // regions are whole 32-bit groups: tiled kernel (aligned loads, coalesced stores)
+        const uint64_t obr = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;  // bytes of one read's packed region
+        if (!ctx->d_offsets && ((uintptr_t)ob.dev & 3u) == 0 && obr <= 0xFFFFFFFFull) {
+            // tiled kernel (aligned loads, coalesced 4-byte stores)
             PackTileParams t{};
             t.bases = ctx->d_bases; t.n_bytes = ctx->n_bytes; t.L = ctx->fixed_len; t.L32 = (uint32_t)ctx->fixed_len;
-            t.gpr = (uint32_t)(((ctx->fixed_len + bpw - 1) / bpw) * word_bytes / 4);
-            t.total_groups = ctx->n_reads * t.gpr;
-            t.gpr_magic = t.gpr > 1 ? (uint32_t)((1ull << 32) / t.gpr + 1) : 0;
-            t.gpr_magic64 = (t.gpr > 1 && (double)t.total_groups * (double)t.gpr < 9.0e18) ? (~0ull / t.gpr + 1) : 0;
-            t.out = (uint32_t*)ob.dev; t.enc = p.enc;
-            const uint64_t ctas = (t.total_groups + kPackGroups - 1) / kPackGroups;
+            t.obr = (uint32_t)obr;
+            t.total_bytes = ctx->n_reads * obr;
+            t.obr_magic = t.obr > 1 ? (uint32_t)((1ull << 32) / t.obr + 1) : 0;
+            t.obr_magic64 = (t.obr > 1 && (double)t.total_bytes * (double)t.obr < 9.0e18) ? (~0ull / t.obr + 1) : 0;
+            t.out = (uint8_t*)ob.dev; t.enc = p.enc;
+            const uint64_t ctas = (t.total_bytes + 4 * kPackGroups - 1) / (4 * kPackGroups);
             if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
-            const size_t smem = (size_t)(kPackGroups + 8) * sizeof(uint2);
+            const size_t smem = (size_t)(kPackGroups + 10) * sizeof(uint2);
             pack_tile_kernel<<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
         } else if (!ctx->d_offsets) {
             p.out_bytes_per_read = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;

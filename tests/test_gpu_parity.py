@@ -429,10 +429,12 @@ def test_straddling_items_with_invalid_bases(ctx, ko):
 
 
 def test_pack_tiled_kernel_lengths(ctx, ko):
-    """Tiled pack kernel (regions that are whole 32-bit groups) across read lengths incl. L < 16 and padding-only groups."""
+    """Tiled pack kernel across read lengths incl. L < 16, padding-only groups, and (u8 / u16 words) regions that end
+    inside a 32-bit word of the image, so that one stored word holds bytes of up to four reads."""
     import kmers_b200 as kb
     rng = np.random.default_rng(31)
-    for L, wb in [(150, 64), (31, 64), (1, 32), (16, 32), (17, 32), (100, 128), (5, 128), (1000, 64), (40000, 64)]:
+    for L, wb in [(150, 64), (31, 64), (1, 32), (16, 32), (17, 32), (100, 128), (5, 128), (1000, 64), (40000, 64),
+                  (150, 8), (150, 16), (1, 8), (2, 8), (3, 8), (4, 8), (5, 8), (7, 16), (9, 16), (33, 8), (101, 16), (40001, 8)]:
         n = max(2, 20000 // L)
         bases, _ = random_reads(rng, n, L, L, p_bad=0.05)
         img, _ = ctx.upload(bases, fixed_len=L).pack(int(kb.Naive.TGCA), wb)
