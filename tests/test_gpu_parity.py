@@ -415,6 +415,32 @@ def test_fixed_reads_with_fewer_than_eight_windows(ctx, ko, L, k):
     assert np.array_equal(w.host("hash")[:ref["hash"].shape[0]], ref["hash"])
 
 
+@pytest.mark.parametrize("W,k", [(9, 63), (13, 63), (14, 63), (15, 63), (16, 63), (17, 40), (23, 33), (88, 63), (89, 64), (14, 17)])
+def test_wide_pair_shape_boundaries(ctx, ko, W, k):
+    """Two-word engine, paired item shape (an item spans 14 slots): reads with fewer windows than that go window by
+    window, W around 14..17 and odd W make nearly every item straddle a read boundary; invalid bases at read edges."""
+    rng = np.random.default_rng(W * 100 + k)
+    L, n = k + W - 1, 3000
+    bases, _ = random_reads(rng, n, L, L, p_bad=0.002)
+    b2 = bases.reshape(n, L)
+    b2[::5, 0] = ord("N")
+    b2[3::7, -1] = ord("n")
+    res = ctx.upload(bases, fixed_len=L).extract_canonical_wide(k, digest=True)
+    ref = ko.extract_canonical_wide(bases, k, n_reads=n, fixed_len=L)
+    assert np.array_equal(res.host("canon"), ref["canon"])
+    assert np.array_equal(res.host("hash"), ref["hash"])
+    assert res.digest == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+    # the same reads as a ragged batch, with a few window-less reads mixed in
+    lens = np.full(n, L, dtype=np.int64)
+    lens[::11] = k - 1
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    rb = bases[: int(offs[-1])]
+    res = ctx.upload(rb, offsets=offs).extract_canonical_wide(k, digest=True)
+    ref = ko.extract_canonical_wide(rb, k, offsets=offs)
+    assert np.array_equal(res.host("canon"), ref["canon"]) and np.array_equal(res.host("hash"), ref["hash"])
+    assert res.digest == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+
+
 def test_straddling_items_with_invalid_bases(ctx, ko):
     """W = 130 (not a multiple of 8): every 16th item straddles a read boundary; N's at read edges."""
     rng = np.random.default_rng(5)
