@@ -24,6 +24,7 @@ namespace kmb {
 #endif
 constexpr int kExtractThreads = KMB_EXTRACT_THREADS;
 constexpr int kItemsPerCta = KMB_ITEMS_PER_CTA;  // default 1024 items = 8192 slots per CTA
+constexpr int kMaxItemsPerCta = 4 * kItemsPerCta;  // the 1024-thread histogram CTAs take 4096 items per tile (fixed-length reads)
 constexpr int kStageBatch = 3;                   // 16-byte loads a thread keeps in flight while staging
 
 // ---------------------------------------------------------------------------
@@ -195,9 +196,9 @@ __device__ __forceinline__ void for_each_item(uint32_t n_items, Item&& item, Rou
 // first sweep and run them afterwards, densely packed: 32 of them per warp instruction.
 struct Deferred {
     uint32_t n;
-    uint16_t li[kItemsPerCta];
+    uint16_t li[kMaxItemsPerCta];
 };
-static_assert(kItemsPerCta <= 65536, "deferred item indices are 16-bit");
+static_assert(kMaxItemsPerCta <= 65536, "deferred item indices are 16-bit");
 __device__ __forceinline__ Deferred& deferred() {
     __shared__ Deferred d;
     return d;
@@ -365,7 +366,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
     const uint64_t slot_begin = (uint64_t)tile_idx * slots_per_cta;
     const uint64_t slot_end = min(g.total_slots, slot_begin + slots_per_cta);
     const uint32_t tile_bases = (g.tile_entries - Eng::kSpanEntries - 1) * 16;  // bases one pass can stage
-    __shared__ uint64_t grp[kItemsPerCta / kCsrGroup + 1];
+    __shared__ uint64_t grp[kMaxItemsPerCta / kCsrGroup + 1];
 
     // reads this CTA can touch; their offsets go to shared memory when they fit (the common case)
     const uint64_t R_lo = g.first_read[tile_idx], R_hi = g.first_read[tile_idx + 1];

@@ -522,7 +522,8 @@ static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u
 
 // fixed-length reads: slot-space geometry of fixed_kernel
 static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
-                            uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, bool packed = false) {
+                            uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, bool packed = false,
+                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 44 * 1024) {
     if (stride == 0) stride = L;
     g->bases = d_bases; g->n_bytes = n_bytes; g->L = stride; g->L32 = (uint32_t)stride; g->packed = packed ? 1u : 0u;
     g->W = L - k + 1;
@@ -534,13 +535,13 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
     const bool magic_ok = g->W > 1 && (double)g->total_slots * (double)g->W < 9.0e18;
     g->w_magic64 = magic_ok ? (~0ull / g->W + 1) : 0;
     // items per CTA: as many as keep the staged stretch of reads under ~44 KiB of shared memory
-    uint32_t ipc = kItemsPerCta;
+    uint32_t ipc = ipc_max;
     for (;;) {
         const uint64_t slots = (uint64_t)ipc * kRun;
         const uint64_t crossings = slots / g->W + 2;
         const uint64_t span = slots + crossings * (k - 1 + (stride - L)) + k + 32;
         l->smem = (size_t)((span + 15) / 16 + span_entries + 2) * sizeof(uint2);
-        if (l->smem <= 44 * 1024 || ipc <= 64) break;
+        if (l->smem <= smem_max || ipc <= 64) break;
         ipc /= 2;
     }
     g->items_per_cta = ipc;
@@ -552,14 +553,14 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
 }
 
 // ragged reads: window offsets (cached per k), per-CTA first-read index, shared-memory layout of csr_kernel
-static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, CsrGeom* g, Launch* l) {
+static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, CsrGeom* g, Launch* l, uint32_t ipc = kItemsPerCta) {
     int32_t rc = ensure_win_offsets(ctx, k);
     if (rc) return rc;
     g->bases = ctx->d_bases; g->n_bytes = ctx->n_bytes; g->n_bases = ctx->n_bases_flat; g->packed = ctx->packed ? 1u : 0u;
     g->offsets = ctx->packed ? ctx->d_base_starts : ctx->d_offsets; g->win_offsets = ctx->d_win_offsets;
-    g->n_reads = ctx->n_reads; g->total_slots = ctx->win_total; g->items_per_cta = kItemsPerCta;
-    g->tile_entries = 2304 + span_entries;  // ~36.8 K bases per pass
-    const uint64_t slots_per_cta = (uint64_t)kItemsPerCta * kRun;
+    g->n_reads = ctx->n_reads; g->total_slots = ctx->win_total; g->items_per_cta = ipc;
+    g->tile_entries = 2304 * (ipc / kItemsPerCta) + span_entries;  // ~36.8 K bases per pass and 1024 items
+    const uint64_t slots_per_cta = (uint64_t)ipc * kRun;
     const uint64_t ctas = (g->total_slots + slots_per_cta - 1) / slots_per_cta;
     if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
     l->grid = (unsigned)ctas;
@@ -607,13 +608,16 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
     FixedGeom fg{};
     CsrGeom cg{};
     Launch l;
+    // shared-memory histogram: 1024-thread CTAs, so four times the items per tile (as many per thread as elsewhere)
+    const bool big = hist && hist_bits <= 16 && !getenv("KMB_HIST_GLOBAL");
     if (!csr) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
-        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l, stride, packed))
+        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l, stride, packed, big ? kMaxItemsPerCta : kItemsPerCta,
+                             big ? 64 * 1024 : 44 * 1024))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else {
         if (n_bytes == 0 || n_reads == 0) return KMB_OK;
-        int32_t r = make_csr_geom(ctx, k, 4, &cg, &l);
+        int32_t r = make_csr_geom(ctx, k, 4, &cg, &l, big ? kMaxItemsPerCta : kItemsPerCta);
         if (r) return r;
         if (cg.total_slots == 0) return KMB_OK;
     }
