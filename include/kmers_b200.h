@@ -146,8 +146,10 @@ int32_t kmb_extract_canonical(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t
  *   pos_out[i] = pos (i32, as the reference), canon_out[i], hash_out[i] as in kmb_extract_canonical,
  *   emit_offsets_out[r] = index of read r's first entry (n_reads + 1 entries; [n_reads] = total).
  * *n_emitted receives the number of emitted k-mers.  Call once with every output pointer NULL to
- * size the arrays, then with arrays of `capacity` >= *n_emitted entries.  Outputs may be host or
- * device memory; any of them may be NULL.  Synchronous. */
+ * size the arrays, then with arrays of `capacity` >= *n_emitted entries (when the context owns the
+ * batch -- upload / generate / ingest, not attach -- that second call reuses the first one's counts
+ * instead of counting again).  Outputs may be host or device memory; any of them may be NULL.
+ * Synchronous. */
 int32_t kmb_extract_compact(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t *canon_out, uint64_t *hash_out,
                             int32_t *pos_out, uint64_t *emit_offsets_out, uint64_t capacity, uint64_t *n_emitted);
 

@@ -218,15 +218,18 @@ __device__ __forceinline__ void defer(uint32_t li) {
 template <class Eng, class Item>
 __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item) {
     constexpr uint32_t kAll = (uint32_t)Eng::Shape::kSpanSlots;
+    // Two-phase engines cannot put their dirty items off to a second sweep (their output order is fixed by the scan), so
+    // they run every item through the checking variant: a few instructions per window instead of both variants per warp.
+    constexpr bool kAlwaysCheck = Eng::kTwoPhase && Eng::kValidate;
     auto emit_one = [&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
         const typename Eng::Span s = eng.load(tile, rel);
-        if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kAll, slot0, nwin, ic);
+        if (kAlwaysCheck || (Eng::kValidate && eng.dirty(s))) eng.template run<false, true>(s, s, kAll, slot0, nwin, ic);
         else eng.template run<false, false>(s, s, kAll, slot0, nwin, ic);
     };
     auto emit_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
         const typename Eng::Span a = eng.load(tile, rel_a);
         const typename Eng::Span b = eng.load(tile, rel_b);
-        if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
+        if (kAlwaysCheck || (Eng::kValidate && (eng.dirty(a) || eng.dirty(b)))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
         else eng.template run<true, false>(a, b, left, slot0, nwin, ic);
     };
     auto emit_single = [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); };

@@ -59,6 +59,12 @@ struct kmb_ctx {
     size_t first_read_cap = 0;
     unsigned long long* d_cta_counts = nullptr;  // compaction: valid windows per CTA / their scan
     size_t cta_counts_cap = 0;
+    // a counting call (all outputs NULL) leaves its scan for the emit call that follows it (same k / flags, batch owned
+    // by the context so that nobody can have changed the bases in between); used once
+    bool compact_ready = false;
+    uint32_t compact_k = 0, compact_flags = 0;
+    unsigned compact_grid = 0;
+    uint64_t compact_total = 0;
 
     // scratch
     unsigned long long* d_digest = nullptr;  // 3 words
@@ -280,6 +286,7 @@ static bool make_enc(int32_t enc, EncDesc* d, uint32_t* dec_letters) {
 
 // ======================================================================= batch
 static void drop_batch(kmb_ctx* ctx) {
+    ctx->compact_ready = false;
     ctx->have_batch = false;
     ctx->win_valid = false;
     ctx->d_bases = nullptr;
@@ -737,23 +744,36 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     const FixedGeom* pf = csr ? nullptr : &fg;
     const CsrGeom* pc = csr ? &cg : nullptr;
     if ((rc = grow(ctx, (void**)&ctx->d_cta_counts, &ctx->cta_counts_cap, ((size_t)l.grid + 1) * 8))) return rc;
-    CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 1) * 8, ctx->stream));
     CompactParams ep{};
     ep.wc = make_winconst(k, enc);
     ep.out.cta_counts = ctx->d_cta_counts;
-    // launch 1: valid windows per CTA, then their exclusive scan (entry [grid] becomes the total)
-    CK(ctx, launch_compact(true, validate, khi, pf, pc, l, ctx->stream, enc, ep));
-    ctx->launches++;
-    size_t need = 0;
-    CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
-    if ((rc = grow(ctx, &ctx->d_cub, &ctx->cub_cap, need))) return rc;
-    CK(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
-    ctx->launches++;
-    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    const uint64_t total = ctx->h_digest[3];
+    const bool counting_call = !canon_out && !hash_out && !pos_out && !emit_offsets_out;
+    const bool owned = ctx->d_bases == ctx->own_bases || ctx->d_bases == (const uint8_t*)ctx->own_packed;
+    uint64_t total;
+    if (!counting_call && ctx->compact_ready && ctx->compact_k == k && ctx->compact_flags == flags && ctx->compact_grid == l.grid) {
+        total = ctx->compact_total;  // the counting call just before this one already left the scan in d_cta_counts
+    } else {
+        CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 1) * 8, ctx->stream));
+        // launch 1: valid windows per CTA, then their exclusive scan (entry [grid] becomes the total)
+        CK(ctx, launch_compact(true, validate, khi, pf, pc, l, ctx->stream, enc, ep));
+        ctx->launches++;
+        size_t need = 0;
+        CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
+        if ((rc = grow(ctx, &ctx->d_cub, &ctx->cub_cap, need))) return rc;
+        CK(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
+        ctx->launches++;
+        CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        total = ctx->h_digest[3];
+    }
+    ctx->compact_ready = false;
     *n_emitted = total;
-    if (!canon_out && !hash_out && !pos_out && !emit_offsets_out) return KMB_OK;  // counting call
+    if (counting_call) {
+        if (owned) {
+            ctx->compact_ready = true; ctx->compact_k = k; ctx->compact_flags = flags; ctx->compact_grid = l.grid; ctx->compact_total = total;
+        }
+        return KMB_OK;
+    }
     if (total > capacity) return fail(ctx, KMB_ERR_INVALID_ARG, "capacity %llu < %llu emitted k-mers", (unsigned long long)capacity,
                                       (unsigned long long)total);
     OutBuf oc, oh, op;

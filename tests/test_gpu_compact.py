@@ -125,3 +125,40 @@ def test_compact_capacity_and_empty(ctx):
     assert got["n"] == 0 and got["emit_offsets"].tolist() == [0, 0]
     with pytest.raises(kb.KmbPanic):
         b.extract_compact(33)
+
+
+def test_counting_call_then_emit_reuses_counts(ctx):
+    """The sizing protocol (count with NULL outputs, then emit): the emit call may reuse the counting call's scan, but only
+    for the same k / flags and an unchanged, context-owned batch; anything in between must not leave stale counts."""
+    import oracle as ko
+    rng = np.random.default_rng(77)
+    bases, _ = random_reads(rng, 3000, 150, 150, p_bad=0.01)
+    lib, h = ctx._lib, ctx._h
+    batch = ctx.upload(bases, fixed_len=150)
+
+    def count(k):
+        n = C.c_uint64()
+        ctx._ck(lib.kmb_extract_compact(h, k, 0, None, None, None, None, 0, C.byref(n)))
+        return int(n.value)
+
+    def emit(k, cap):
+        canon, pos, n = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.int32), C.c_uint64()
+        ctx._ck(lib.kmb_extract_compact(h, k, 0, canon.ctypes.data, None, pos.ctypes.data, None, cap, C.byref(n)))
+        return canon[: n.value], pos[: n.value]
+
+    n31 = count(31)
+    c_a, p_a = emit(31, n31)            # reuses the counts
+    c_b, p_b = emit(31, n31)            # counts again
+    assert np.array_equal(c_a, c_b) and np.array_equal(p_a, p_b)
+    n21 = count(21)
+    c31, p31 = emit(31, n31)            # different k: the pending counts of k=21 must not be used
+    assert np.array_equal(c31, c_a) and np.array_equal(p31, p_a)
+    count(31)
+    bases2, _ = random_reads(rng, 3000, 150, 150, p_bad=0.05)
+    ctx.upload(bases2, fixed_len=150)    # new batch: pending counts dropped
+    n2 = count(31)
+    c2, p2 = emit(31, n2)
+    r = ko.extract_canonical(bases2, 31, n_reads=3000, fixed_len=150)
+    keep = r["canon"] != np.uint64(2**64 - 1)
+    assert n2 == int(keep.sum()) and np.array_equal(c2, r["canon"][keep])
+    assert n21 > n31
