@@ -195,8 +195,8 @@ int32_t kmb_minimizer_words(kmb_ctx *ctx, uint32_t k, uint32_t w, uint32_t hash_
 /* SeqVector twin (naive_impl/seq_vector.rs:18-258): 32 bases per u64 word, base i of a read at bits 2i+1:2i of its
  * region, A0 C1 G2 T3 -- the layout SeqVector::from(&[u8]) builds (:230-242) and kmb_pack(KMB_ENC_ACGT, 64) writes;
  * every read starts on a word boundary.  Once the batch is packed, kmb_extract_canonical (fw_out = iter_kmers,
- * :117-124), kmb_extract_compact, kmb_histogram and kmb_minimizers (= iter_minimizers, :126-139) read 0.25 B/base
- * instead of 1 B/base.  A packed store holds no invalid base, so every window is emitted. */
+ * :117-124), kmb_extract_canonical_wide, kmb_extract_compact, kmb_histogram and kmb_minimizers (= iter_minimizers,
+ * :126-139) read 0.25 B/base instead of 1 B/base.  A packed store holds no invalid base, so every window is emitted. */
 /* pack the resident ASCII batch on the device and switch the batch to the packed copy.  strict != 0: fail with
  * KMB_ERR_PANIC if any byte is outside ACGTacgt, as SeqVector::from would panic; strict == 0: such bytes encode
  * by (c >> 1) & 3 like Encoding::encode. */

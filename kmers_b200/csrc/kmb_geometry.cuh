@@ -126,10 +126,13 @@ __device__ __forceinline__ uint32_t count_valid_windows(const uint2* tile, uint3
 // naive_impl/seq_vector.rs:230-242): the tile entries are the packed 32-bit words themselves.
 // A packed store cannot hold an invalid base, so the invalid masks are zero.
 __device__ __forceinline__ void stage_packed(const uint32_t* words, uint64_t n_words32, uint64_t first_word,
-                                             uint32_t n_entries, uint2* tile) {
+                                             uint32_t n_entries, const EncDesc& enc, uint2* tile) {
     for (uint32_t v = threadIdx.x; v < n_entries; v += blockDim.x) {
         const uint64_t i = first_word + v;
-        tile[v] = make_uint2(i < n_words32 ? __ldg(words + i) : 0u, 0u);
+        uint32_t w = i < n_words32 ? __ldg(words + i) : 0u;
+        // the store holds A0 C1 G2 T3; x ^ (x >> 1) per field is its own inverse and leads back to the internal code
+        if (!enc.is_acgt) w = apply_encoding(w ^ ((w >> 1) & 0x55555555u), enc);
+        tile[v] = make_uint2(w, 0u);
     }
 }
 
@@ -139,7 +142,7 @@ __device__ __forceinline__ uint32_t stage_stretch(const uint8_t* bases, uint64_t
                                                   uint32_t span, uint32_t span_entries, const EncDesc& enc, uint2* tile) {
     if (packed) {
         const uint32_t mis = (uint32_t)(g_start & 15u);
-        stage_packed(reinterpret_cast<const uint32_t*>(bases), n_bytes >> 2, g_start >> 4, ((span + mis + 15) >> 4) + span_entries - 1, tile);
+        stage_packed(reinterpret_cast<const uint32_t*>(bases), n_bytes >> 2, g_start >> 4, ((span + mis + 15) >> 4) + span_entries - 1, enc, tile);
         return mis;
     }
     const uint8_t* first = bases + g_start;
@@ -290,7 +293,7 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
     const uint32_t span = q_last * g.L32 + (u_last - q_last * g.W32) - p_first + K;
     const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile);
-    deferred_reset();
+    if constexpr (!Eng::kTwoPhase) deferred_reset();
     __syncthreads();
 
     // ---- phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than
@@ -428,7 +431,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         for (uint32_t t = threadIdx.x; t <= n_groups; t += blockDim.x)
             grp[t] = last_le(win, ps.r_lo, ps.r_hi, min(ps.slot_lo + (uint64_t)t * (kCsrGroup * kRun), ps.slot_hi - 1));
         const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, ps.g0, ps.span, Eng::kSpanEntries, enc, tile);
-        deferred_reset();
+        if constexpr (!Eng::kTwoPhase) deferred_reset();
         __syncthreads();
 
         auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {

@@ -530,7 +530,7 @@ static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u
 // fixed-length reads: slot-space geometry of fixed_kernel
 static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
                             uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, bool packed = false,
-                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 44 * 1024) {
+                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 36 * 1024) {
     if (stride == 0) stride = L;
     g->bases = d_bases; g->n_bytes = n_bytes; g->L = stride; g->L32 = (uint32_t)stride; g->packed = packed ? 1u : 0u;
     g->W = L - k + 1;
@@ -541,7 +541,8 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
     // slot / W by multiplication is exact while slot * W < 2^64; otherwise the kernel divides
     const bool magic_ok = g->W > 1 && (double)g->total_slots * (double)g->W < 9.0e18;
     g->w_magic64 = magic_ok ? (~0ull / g->W + 1) : 0;
-    // items per CTA: as many as keep the staged stretch of reads under ~44 KiB of shared memory
+    // items per CTA: as many as keep the staged stretch of reads under smem_max (default 36 KiB: with the kernels' ~10 KiB of
+    // static shared memory that stays below the 48 KiB a launch gets without opting in)
     uint32_t ipc = ipc_max;
     for (;;) {
         const uint64_t slots = (uint64_t)ipc * kRun;
@@ -620,7 +621,7 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
     if (!csr) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
         if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l, stride, packed, big ? kMaxItemsPerCta : kItemsPerCta,
-                             big ? 64 * 1024 : 44 * 1024))
+                             big ? 64 * 1024 : 36 * 1024))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else {
         if (n_bytes == 0 || n_reads == 0) return KMB_OK;
@@ -879,7 +880,6 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
     BIND(ctx);
     NEED_BATCH(ctx);
     if (k < 1 || k > 64) return fail(ctx, KMB_ERR_INVALID_ARG, "k = %u: the two-word path supports 1 <= k <= 64", k);
-    if (ctx->packed) return fail(ctx, KMB_ERR_STATE, "the two-word path reads ASCII batches, not packed ones");
     EncDesc enc;
     if (!make_enc(enc_id, &enc, nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
     uint64_t n_slots = 0;
@@ -889,7 +889,7 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
     if ((rc = out_prepare(ctx, 0, canon_out, n_slots * 16, &oc))) return rc;
     if ((rc = out_prepare(ctx, 1, hash_out, n_slots * 16, &oh))) return rc;
     if (digest && (rc = digest_begin(ctx))) return rc;
-    const bool validate = !(flags & KMB_F_NO_VALIDATE);
+    const bool validate = !(flags & KMB_F_NO_VALIDATE) && !ctx->packed;  // a packed store holds no invalid base
     if (n_slots) {
         const int nw32 = k <= 32 ? 2 : (k <= 48 ? 3 : 4);  // live 32-bit words of a k-mer
         uint32_t mask[4];
@@ -907,7 +907,7 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         Launch l;
         const bool csr = ctx->d_offsets != nullptr;
         if (!csr) {
-            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, nw32 + 2, &fg, &l))
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, nw32 + 2, &fg, &l, ctx->stride_len, ctx->packed))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
         } else if ((rc = make_csr_geom(ctx, k, nw32 + 2, &cg, &l))) {
             return rc;

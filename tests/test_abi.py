@@ -86,3 +86,30 @@ def test_naive_enum_matches_reference_table():
         for k, want in cases:
             assert kb.word_for_k(wb, k) == want == ko.lib().ko_word_for_k(wb, k)
     assert [kb.num_bytes(wb, 15) for wb in (8, 16, 32, 64, 128)] == [4, 4, 4, 8, 16]  # kmer.rs:120-153
+
+
+def test_static_shared_memory_leaves_room_for_the_tile():
+    """fixed_kernel / csr_kernel are launched without opting in to more than 48 KiB of shared memory; the host sizes
+    their dynamic tile up to 36 KiB (make_fixed_geom) resp. ~27 KiB (make_csr_geom), so their static part must stay
+    below 12 KiB -- a launch that exceeds the limit fails with 'invalid argument' only for unusual read geometries."""
+    import re
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", g.SO], capture_output=True, text=True).stdout
+    names = re.findall(r"Function (\S+):\n\s*REG:\d+ STACK:\d+ SHARED:(\d+)", out)
+    checked = 0
+    for name, shared in names:
+        if "hist_" in name or "compact_" in name:
+            continue
+        if "12fixed_kernel" in name:
+            assert int(shared) <= 12 * 1024, (name, shared)   # + at most 36 KiB of tile
+            checked += 1
+        elif "10csr_kernel" in name:
+            assert int(shared) <= 20 * 1024, (name, shared)   # + ~27 KiB of tile and offset tables
+            checked += 1
+    assert checked >= 40

@@ -110,3 +110,24 @@ def test_repack_strict_panics_on_invalid_bases(ctx):
     p = ctx.upload(bases, fixed_len=100).to_packed(strict=False)  # Encoding::encode semantics: (c >> 1) & 3
     r = p.extract_canonical(31, to="host")
     assert np.array_equal(a.canon, r.canon) and np.array_equal(a.hash, r.hash)
+
+
+@pytest.mark.parametrize("enc_name", ["ACGT", "TGCA", "XOR10"])
+def test_two_word_path_reads_the_packed_store(ctx, enc_name):
+    """kmb_extract_canonical_wide on a packed batch (fixed and ragged) == the same call on the ASCII batch, for the
+    store's own code and for other encodings (the staged words are re-coded on the fly)."""
+    import kmers_b200 as kb
+    import oracle as ko
+    rng = np.random.default_rng(len(enc_name) + 40)
+    enc = kb.ENC_XOR10 if enc_name == "XOR10" else ko.NAIVE[enc_name]
+    for k in (31, 47, 63):
+        bases = _acgt(rng, 700 * 150)
+        a = ctx.upload(bases, fixed_len=150).extract_canonical_wide(k, enc, digest=True, to="host")
+        p = ctx.upload(bases, fixed_len=150).to_packed().extract_canonical_wide(k, enc, digest=True, to="host")
+        assert np.array_equal(a.canon, p.canon) and np.array_equal(a.hash, p.hash) and a.digest == p.digest, k
+    lens = rng.integers(0, 200, size=900)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    bases = _acgt(rng, int(offs[-1]))
+    a = ctx.upload(bases, offsets=offs).extract_canonical_wide(63, enc, digest=True, to="host")
+    p = ctx.upload(bases, offsets=offs).to_packed().extract_canonical_wide(63, enc, digest=True, to="host")
+    assert np.array_equal(a.canon, p.canon) and np.array_equal(a.hash, p.hash) and a.digest == p.digest
