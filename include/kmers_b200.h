@@ -210,6 +210,14 @@ int32_t kmb_batch_attach_packed(kmb_ctx *ctx, const uint64_t *dev_words, uint64_
  * at pos[i] of read reads[i], or KMB_SENTINEL where the reference's assert!(pos < len) / the read's end is violated. */
 int32_t kmb_packed_get_kmers(kmb_ctx *ctx, uint32_t k, const uint64_t *reads, const uint64_t *pos, uint64_t n, uint64_t *out);
 
+/* ---- final reduction across GPUs ------------------------------- */
+/* One process driving several GPUs: in-place element-wise wrapping-u64 sum of dev_bufs[i] (count words in the memory of
+ * ctxs[i]'s GPU, e.g. [histogram | n_valid | checksum_canon | checksum_hash]) over the n_ctx contexts -- NCCL
+ * ncclAllReduce(ncclUint64, ncclSum) over NVLink, enqueued on each context's stream behind its kernels; returns after
+ * every stream has drained.  One context per GPU.  libnccl.so.2 is loaded on first use (KMB_ERR_STATE if absent).  Hosts
+ * that run one process per GPU reduce with their own communicator instead (kmers_b200/dist.py). */
+int32_t kmb_allreduce_u64(kmb_ctx *const *ctxs, int32_t n_ctx, uint64_t *const *dev_bufs, uint64_t count);
+
 /* ---- "next" row N4: host ingest -------------------------------------------- */
 /* FASTA ('>' records, multi-line sequences) or FASTQ ('@' four-line records) text in host memory -> the
  * concatenated bases and their CSR offsets (n_reads + 1 entries), exactly the arguments of kmb_batch_upload.

@@ -292,4 +292,12 @@ std::vector<uint8_t> ReadBatch::pack(Enc enc, uint32_t word_bits) const {
     return out;
 }
 
+// final reduction across the GPUs one process drives: in-place wrapping-u64 sum of dev_bufs[i] (device memory of
+// ctxs[i]'s GPU) through NCCL (kmb_allreduce_u64)
+inline void allreduce_u64(const std::vector<Context*>& ctxs, const std::vector<uint64_t*>& dev_bufs, uint64_t count) {
+    std::vector<kmb_ctx*> raw;
+    for (Context* c : ctxs) raw.push_back(c->raw());
+    detail::check(raw.empty() ? nullptr : raw[0], kmb_allreduce_u64(raw.data(), (int32_t)raw.size(), dev_bufs.data(), count));
+}
+
 }  // namespace kmers_b200

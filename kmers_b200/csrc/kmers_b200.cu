@@ -4,14 +4,18 @@
 // No torch types, no CPU fallback: every compute entry point needs a device.
 #include "../../include/kmers_b200.h"
 
+#include <dlfcn.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include <cub/device/device_scan.cuh>
 
@@ -1113,6 +1117,88 @@ extern "C" int32_t kmb_packed_get_kmers(kmb_ctx* ctx, uint32_t k, const uint64_t
     ctx->launches++;
     if ((rc = out_finish(ctx, ob))) return rc;
     if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ======================================================================= final reduction across GPUs
+// One process driving several GPUs (what a Rust host would do): NCCL all-reduce of u64 words over the contexts'
+// devices.  libnccl is loaded on first use, so the library itself has no link-time dependency on it.
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::vector<int> devices;  // the communicator clique currently held
+    std::vector<void*> comms;
+    std::mutex mu;
+};
+NcclApi g_nccl;
+constexpr int kNcclUint64 = 5, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h; stable ABI)
+
+bool nccl_load(NcclApi& a) {
+    if (a.lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (a.lib) break;
+    }
+    if (!a.lib) return false;
+    a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+    if (a.CommInitAll && a.CommDestroy && a.AllReduce && a.GroupStart && a.GroupEnd && a.GetErrorString) return true;
+    dlclose(a.lib);
+    a.lib = nullptr;
+    return false;
+}
+}  // namespace
+
+extern "C" int32_t kmb_allreduce_u64(kmb_ctx* const* ctxs, int32_t n_ctx, uint64_t* const* dev_bufs, uint64_t count) {
+    if (n_ctx < 1 || !ctxs || !dev_bufs) return fail(nullptr, KMB_ERR_INVALID_ARG, "need n_ctx >= 1 contexts and buffers");
+    for (int i = 0; i < n_ctx; ++i)
+        if (!ctxs[i] || (count && !dev_bufs[i])) return fail(nullptr, KMB_ERR_INVALID_ARG, "NULL context or buffer at index %d", i);
+    kmb_ctx* c0 = ctxs[0];
+    if (count == 0) return KMB_OK;
+    if (n_ctx == 1) { BIND(c0); CK(c0, cudaStreamSynchronize(c0->stream)); return KMB_OK; }
+    std::vector<int> devs(n_ctx);
+    for (int i = 0; i < n_ctx; ++i) {
+        devs[i] = ctxs[i]->device;
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(c0, KMB_ERR_INVALID_ARG, "contexts %d and %d share device %d: one context per GPU", j, i, devs[i]);
+    }
+    std::lock_guard<std::mutex> lock(g_nccl.mu);
+    if (!nccl_load(g_nccl)) return fail(c0, KMB_ERR_STATE, "libnccl.so.2 could not be loaded: %s", dlerror());
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0) return fail(c0, KMB_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_));   \
+    } while (0)
+    if (g_nccl.devices != devs) {  // a new clique: (re)build the communicators
+        for (void* c : g_nccl.comms) g_nccl.CommDestroy(c);
+        g_nccl.comms.assign(n_ctx, nullptr);
+        g_nccl.devices.clear();
+        NK(g_nccl.CommInitAll(g_nccl.comms.data(), n_ctx, devs.data()));
+        g_nccl.devices = devs;
+    }
+    NK(g_nccl.GroupStart());
+    for (int i = 0; i < n_ctx; ++i) {
+        cudaSetDevice(devs[i]);
+        int r_ = g_nccl.AllReduce(dev_bufs[i], dev_bufs[i], count, kNcclUint64, kNcclSum, g_nccl.comms[i], ctxs[i]->stream);
+        if (r_ != 0) { g_nccl.GroupEnd(); return fail(c0, KMB_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r_)); }
+        ctxs[i]->launches++;
+    }
+    NK(g_nccl.GroupEnd());
+#undef NK
+    for (int i = 0; i < n_ctx; ++i) {
+        cudaSetDevice(devs[i]);
+        CK(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));
+    }
     return KMB_OK;
 }
 

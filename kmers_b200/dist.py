@@ -63,3 +63,19 @@ def sharded_histogram(ctx, seed: int, n_bases: int, k: int, hist_bits: int, rank
     # loaded range ends at stop + k - 1, so the last window starts at stop - 1 (or earlier at the sequence end)
     g_hist, g_digest = allreduce_histogram(hist, digest, group=group)
     return g_hist, g_digest, max(0, n - k + 1)
+
+
+def allreduce_single_process(ctxs, bufs):
+    """The same reduction for ONE process that drives several GPUs (the shape a Rust host has): in-place wrapping-u64
+    sum of the int64 CUDA tensors `bufs[i]` (one per context / GPU) through the C ABI's kmb_allreduce_u64 (NCCL)."""
+    import ctypes as C
+
+    from . import _native as nv
+    n = len(ctxs)
+    assert n == len(bufs) and n >= 1
+    count = bufs[0].numel()
+    assert all(b.numel() == count and b.is_cuda and b.is_contiguous() for b in bufs)
+    handles = (C.c_void_p * n)(*[c._h for c in ctxs])
+    ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in bufs])
+    nv.check(ctxs[0]._h, nv.lib().kmb_allreduce_u64(handles, n, ptrs, count))
+    return bufs

@@ -68,3 +68,34 @@ def test_sharded_histogram_nccl_multi_gpu(tmp_path):
                                  hist_bits=16, materialize=False)
     assert np.array_equal(np.load(out), whole["hist"])
     assert tuple(json.load(open(out + ".json"))) == (whole["n_valid"], whole["checksum_canon"], whole["checksum_hash"])
+
+
+def test_single_process_allreduce_through_the_c_abi():
+    """kmb_allreduce_u64: one process, one context per GPU (the Rust host's shape).  With one GPU the call is a
+    synchronising no-op; with >= 2 it must equal the sum of the per-GPU [histogram | digest] vectors."""
+    import torch
+    import kmers_b200 as kb
+    import oracle as ko
+    from kmers_b200 import dist as kd
+    n = min(torch.cuda.device_count(), 4)
+    G, k, bits, seed, thr = 2_000_000, 31, 12, 44, 105
+    whole = ko.extract_canonical(ko.generate_bases(seed, 0, G, thr), k, n_reads=1, fixed_len=G, hist_bits=bits,
+                                 materialize=False)
+    ctxs = [kb.Context(d) for d in range(n)]
+    try:
+        bufs = []
+        for r, ctx in enumerate(ctxs):
+            start, stop, load_stop = kd.shard_sequence(G, k, r, n)
+            with torch.cuda.device(r):
+                batch = ctx.generate(seed, 1, load_stop - start, n_thresh20=thr, first_index=start)
+                hist, dig = batch.histogram(k, bits, to="device")
+                tail = torch.tensor([kd._to_i64(int(d)) for d in dig], dtype=torch.int64, device=f"cuda:{r}")
+                bufs.append(torch.cat([hist.reshape(-1).to(torch.int64), tail]).contiguous())
+        kd.allreduce_single_process(ctxs, bufs)
+        for b in bufs:   # every GPU holds the global result
+            got = b.cpu().numpy().view(np.uint64)
+            assert np.array_equal(got[:-3], whole["hist"])
+            assert tuple(int(v) for v in got[-3:]) == (whole["n_valid"], whole["checksum_canon"], whole["checksum_hash"])
+    finally:
+        for c in ctxs:
+            c.close()
