@@ -243,6 +243,9 @@ int32_t kmb_pack_num_words(kmb_ctx *ctx, uint32_t word_bits, uint64_t *n_words);
  * padding positions. */
 int32_t kmb_unpack(kmb_ctx *ctx, int32_t enc, uint32_t word_bits, const void *words_in, uint64_t n_items,
                    uint32_t words_per_item, uint32_t bases_per_item, uint8_t *bases_out);
+/* `impl From<Kmer> for String` (naive_impl/kmer.rs:196-207) on n k-mer words: k lower-case letters each (BASE_TABLE,
+ * kmer.rs:24), base 0 first, written back to back (no terminators).  1 <= k <= 32. */
+int32_t kmb_words_to_strings(kmb_ctx *ctx, uint32_t k, const uint64_t *words, uint64_t n, uint8_t *bases_out);
 /* Encoding::rev_comp::<K> (encoding/naive.rs:138-154; xor10.rs:86-103 -- the
  * swap-loop result for every B, NOT the arithmetic of xor10.rs:75-85, SURVEY
  * Q2) on n_items arrays of words_per_item words; bits >= 2k are preserved.

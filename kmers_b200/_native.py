@@ -78,6 +78,7 @@ SIGNATURES = {
     "kmb_batch_ingest_fastx": (_i32, [_vp, C.c_char_p, _u64, _pu64, _pu64]),
     "kmb_pack": (_i32, [_vp, _i32, _u32, _vp, _vp]),
     "kmb_pack_num_words": (_i32, [_vp, _u32, _pu64]),
+    "kmb_words_to_strings": (_i32, [_vp, _u32, _vp, _u64, _vp]),
     "kmb_unpack": (_i32, [_vp, _i32, _u32, _vp, _u64, _u32, _u32, _vp]),
     "kmb_revcomp_words": (_i32, [_vp, _i32, _u32, _u32, _u32, _vp, _vp, _u64]),
     "kmb_reverse_complement_words": (_i32, [_vp, _u32, _vp, _vp, _u64]),

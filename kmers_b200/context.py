@@ -227,6 +227,13 @@ class Context:
         return mm, off
 
     # ---- batched Encoding::decode / rev_comp on arrays [P; B]
+    def words_to_strings(self, words, k: int) -> np.ndarray:
+        """Batched `String::from(Kmer)` (naive_impl/kmer.rs:196-207): (n, k) lower-case ASCII (kmb_words_to_strings)."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        out = np.empty((w.size, k), dtype=np.uint8)
+        self._ck(self._lib.kmb_words_to_strings(self._h, k, w.ctypes.data, w.size, out.ctypes.data))
+        return out
+
     def unpack(self, enc: int, word_bits: int, words: np.ndarray, n_items: int, words_per_item: int,
                bases_per_item: Optional[int] = None) -> np.ndarray:
         """Encoding::decode (encoding/naive.rs:126-136) of n_items arrays; default length reproduces the

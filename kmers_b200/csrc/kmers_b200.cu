@@ -1409,14 +1409,30 @@ static int32_t in_prepare(kmb_ctx* ctx, int slot, const void* user, size_t bytes
     return KMB_OK;
 }
 
+static int32_t unpack_impl(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, const void* words_in, uint64_t n_items,
+                           uint32_t words_per_item, uint32_t bases_per_item, uint8_t* bases_out, uint32_t case_bit);
+
 extern "C" int32_t kmb_unpack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, const void* words_in, uint64_t n_items,
                               uint32_t words_per_item, uint32_t bases_per_item, uint8_t* bases_out) {
+    return unpack_impl(ctx, enc_id, word_bits, words_in, n_items, words_per_item, bases_per_item, bases_out, 0u);
+}
+
+// `impl From<Kmer> for String` (naive_impl/kmer.rs:196-207): BASE_TABLE = ['a','c','g','t'] (kmer.rs:24), base 0 first
+extern "C" int32_t kmb_words_to_strings(kmb_ctx* ctx, uint32_t k, const uint64_t* words, uint64_t n, uint8_t* bases_out) {
+    NEED_CTX(ctx);
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    return unpack_impl(ctx, KMB_ENC_ACGT, 64, words, n, 1, k, bases_out, 0x20202020u);
+}
+
+static int32_t unpack_impl(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, const void* words_in, uint64_t n_items,
+                           uint32_t words_per_item, uint32_t bases_per_item, uint8_t* bases_out, uint32_t case_bit) {
     NEED_CTX(ctx);
     BIND(ctx);
     if (!word_bits_ok(word_bits)) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128");
     EncDesc enc;
     uint32_t dec = 0;
     if (!make_enc(enc_id, &enc, &dec)) return fail(ctx, KMB_ERR_INVALID_ARG, "enc 0x%x is not a Naive discriminant / Xor10", enc_id);
+    dec |= case_bit;  // the four letters of the decode table, upper case by default
     const uint64_t in_bytes_per_item = (uint64_t)words_per_item * (word_bits / 8);
     if (bases_per_item > in_bytes_per_item * 4) return fail(ctx, KMB_ERR_INVALID_ARG, "bases_per_item exceeds the array capacity");
     if (n_items == 0 || bases_per_item == 0) return KMB_OK;

@@ -364,6 +364,19 @@ def test_word_ops(ctx, ko, k):
     assert np.array_equal(c2, canon) and f2.all()
 
 
+def test_words_to_strings(ctx, ko):
+    """String::from(Kmer) in batch (naive_impl/kmer.rs:196-207): lower case, base 0 first; goldens of kmer.rs:434-448."""
+    for k in (1, 3, 16, 31, 32):
+        rng = np.random.default_rng(k)
+        words = rng.integers(0, 2**63, size=500, dtype=np.uint64) & np.uint64((1 << (2 * k)) - 1 if k < 32 else 2**64 - 1)
+        got = ctx.words_to_strings(words, k)
+        for w, row in zip(words[:100].tolist(), got[:100]):
+            assert row.tobytes().decode() == ko.kmer_str(ko.Kmer(k, int(w)))
+    assert ctx.words_to_strings(np.array([0b010000, 0b100100], dtype=np.uint64), 3).tobytes() == b"aacacg"
+    with pytest.raises(Exception):
+        ctx.words_to_strings(np.zeros(1, dtype=np.uint64), 33)
+
+
 def test_word_ops_on_device_tensors(ctx, ko):
     import torch
     words = torch.randint(0, 2**62, (5000,), dtype=torch.int64, device="cuda")
