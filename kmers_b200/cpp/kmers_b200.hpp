@@ -204,6 +204,14 @@ class Context {
         for (size_t i = 0; i < arrays.size(); ++i) out[i] = flat.substr(i * per, per);
         return out;
     }
+    // String::from(Kmer) (naive_impl/kmer.rs:196-207): lower-case letters, base 0 first
+    std::vector<std::string> to_strings(const std::vector<uint64_t>& words, uint32_t k) {
+        std::string flat(words.size() * k, '\0');
+        detail::check(ctx_, kmb_words_to_strings(ctx_, k, words.data(), words.size(), reinterpret_cast<uint8_t*>(&flat[0])));
+        std::vector<std::string> out(words.size());
+        for (size_t i = 0; i < words.size(); ++i) out[i] = flat.substr(i * k, k);
+        return out;
+    }
     // Encoding::rev_comp::<K> (encoding/naive.rs:138-154)
     template <size_t K, class P, size_t B, class Enc>
     std::vector<std::array<P, B>> rev_comp(Enc enc, const std::vector<std::array<P, B>>& arrays) {

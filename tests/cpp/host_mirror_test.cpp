@@ -74,6 +74,10 @@ int main() {
         auto h = ctx.lex_hash({kmer_word("aaa"), kmer_word("aac"), kmer_word("caa"), kmer_word("cac")}, 3);
         CHECK(h[0] == 0 && h[1] == 1 && h[2] == 0b010000 && h[3] == 0b010001);
     }
+    {  // naive_impl/kmer.rs:196-207 String::from(Kmer): lower case, base 0 first
+        auto t = ctx.to_strings({kmer_word("gatacataggatgg"), kmer_word("ccatcctatgtatc")}, 14);
+        CHECK(t[0] == "gatacataggatgg" && t[1] == "ccatcctatgtatc");
+    }
     {  // naive_impl/canonical_kmer.rs:283-297 test_equivalency
         auto m = ctx.get_word_equivalency({kmer_word("acttg"), kmer_word("acttg"), kmer_word("acttg")},
                                           {kmer_word("caagt"), kmer_word("acttg"), kmer_word("cttgc")}, 5);
