@@ -110,6 +110,10 @@ __device__ __forceinline__ uint32_t div_obr(uint32_t u, const PackTileParams& p)
     return __umulhi(u, p.obr_magic);
 }
 
+// MODE 0: regions are whole 32-bit words (u32 / u64 / u128 words of P, or lucky lengths): one extract per word
+// MODE 1: regions of >= 4 bytes that may end inside a word: two masked extracts per word, branch-free
+// MODE 2: regions of 1..3 bytes: byte by byte
+template <int MODE>
 __global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) {
     extern __shared__ uint2 tile[];
     const uint64_t byte_base = (uint64_t)blockIdx.x * (4u * kPackGroups);
@@ -124,8 +128,8 @@ __global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) 
     const uint32_t u_last = b_first + n_out - 1, q_last = div_obr(u_last, p);
     const uint64_t s_end = (r_first + q_last) * p.L + min((uint64_t)(u_last - q_last * p.obr) * 4 + 4, p.L);
     const uint8_t* first = p.bases + s_start;
-    // one entry of margin in front: the extract for the second read of a word starts before that read's first base
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u) + 16u;
+    // MODE 1: one entry of margin in front -- the extract for the second read of a word starts before that read's first base
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u) + (MODE == 1 ? 16u : 0u);
     const uint32_t n_entries = (uint32_t)((s_end - s_start + mis + 15) >> 4) + 2;  // an extract reads 2 entries, possibly from the stretch's very end
     stage_tile<false>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
     __syncthreads();
@@ -140,10 +144,10 @@ __global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) 
         const uint32_t u = b_first + 4 * li, q = div_obr(u, p), b = u - q * p.obr;  // first byte of the word inside its read
         const uint32_t here = min(4u, n_out - 4 * li);                              // bytes of this word that exist
         uint32_t bits = 0;
-        if ((p.obr & 3u) == 0) {  // kernel-uniform: regions are whole 32-bit words (u32 / u64 / u128 words of P, or lucky lengths)
+        if (MODE == 0) {
             const uint64_t b0 = (uint64_t)b * 4;
             if (b0 < p.L) bits = extract((uint32_t)((r_first + q) * p.L + b0 - s_start) + mis) & low_bits(2 * (uint32_t)min((uint64_t)16, p.L - b0));
-        } else if (p.obr >= 4) {  // kernel-uniform
+        } else if (MODE == 1) {
             // A word holds bytes of at most two reads: n_a from read q (bases 4b ..), the rest from read q+1 (from its base
             // 0 on).  Both parts are one 16-base extract, masked to the bases that exist -- the same instructions for every
             // lane, whether its word straddles a region boundary or not (a branch here would cost every warp both paths).

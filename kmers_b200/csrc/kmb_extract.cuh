@@ -245,7 +245,10 @@ struct NarrowEng {
     using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;  // tile entries one span reads
-    static constexpr int kMinCtas = 1, kMinCtasCsr = 4;  // resident CTAs per SM the register allocation must allow
+    // resident CTAs per SM the register allocation must allow (an explicit 1 would let the compiler take ~80-90
+    // registers and halve the occupancy): 4 = 64 registers; the canonical-words-only variant is ALU-bound and fits 5, the four-array
+    // variant needs ~100 registers
+    static constexpr int kMinCtas = FWRC ? 2 : ((!HASH && !DIGEST && MODE == 0) ? 5 : 4), kMinCtasCsr = FWRC ? 2 : 4;
     const NarrowParams& p;
     Acc acc;
     __device__ explicit NarrowEng(const NarrowParams& params) : p(params) {}

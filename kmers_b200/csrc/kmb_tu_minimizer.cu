@@ -20,13 +20,19 @@ __global__ void __launch_bounds__(256) minimizer_words_kernel(const uint64_t* in
     if (i >= n) return;
     const uint64_t word = in[i];
     const uint64_t wmask = width >= 32 ? ~0ull : ((1ull << (2 * width)) - 1ull);
+    // LexHasher::write_u64 (hash.rs:60-71) of an lmer = its first hash_k bases read as a number, base 0 most significant.
+    // Pair-reversing the whole k-mer ONCE puts base 0 in the top field, so the rank of the lmer at `pos` is a plain
+    // field extract: v = (rev >> 2 (k - pos - width)) & wmask; the hash is v >> 2 (width - hash_k) for hash_k < width and
+    // v << 2 (hash_k - width) otherwise -- the latter orders and ties exactly like v itself.
+    const uint64_t rev = pair_reverse64(word) >> (2 * (32 - k));
+    const uint32_t hs = hash_k < width ? 2 * (width - hash_k) : 0;
     uint64_t min_mmer = word & wmask, min_hash = ~0ull;
     uint32_t off = 0;
-    for (uint32_t pos = 0; pos + width <= k; ++pos) {
-        const uint64_t mm = (word >> (2 * pos)) & wmask;                       // sub_kmer_word, kmer.rs:155-161
-        const uint64_t h = pair_reverse64(mm) >> (2 * (32 - hash_k));          // LexHasher::write_u64, hash.rs:60-71
-        if (h < min_hash) { min_mmer = mm; min_hash = h; off = pos; }
+    for (uint32_t pos = 0; pos + width <= k; ++pos) {                    // sub_kmer_word, kmer.rs:155-161
+        const uint64_t h = ((rev >> (2 * (k - pos - width))) & wmask) >> hs;
+        if (h < min_hash) { min_hash = h; off = pos; }                   // strict '<': the leftmost minimum (kmer.rs:183)
     }
+    if (off) min_mmer = (word >> (2 * off)) & wmask;
     if (mmer_out) mmer_out[i] = min_mmer;
     if (offset_out) offset_out[i] = off;
 }

@@ -1370,7 +1370,9 @@ extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, vo
             const uint64_t ctas = (t.total_bytes + 4 * kPackGroups - 1) / (4 * kPackGroups);
             if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
             const size_t smem = (size_t)(kPackGroups + 10) * sizeof(uint2);
-            pack_tile_kernel<<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
+            if ((t.obr & 3u) == 0) pack_tile_kernel<0><<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
+            else if (t.obr >= 4) pack_tile_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
+            else pack_tile_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
         } else if (!ctx->d_offsets) {
             p.out_bytes_per_read = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;
             const uint64_t gpr = (p.out_bytes_per_read + 3) / 4;
