@@ -220,6 +220,38 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint8_t* in, uint64_t
     }
 }
 
+// The same through shared memory: a CTA decodes `ipc` consecutive items (<= kUnpackTile letters) into a staging buffer
+// laid out with the misalignment of its slice of the text, then writes the slice with aligned 16-byte stores.
+// (Items are bases_per_item letters long -- 31 for a 31-mer -- so per-item stores would be byte-granular.)
+constexpr int kUnpackTile = 16384;
+__global__ void __launch_bounds__(256) unpack_tile_kernel(const uint8_t* in, uint64_t n_items, uint32_t in_bytes_per_item,
+                                                          uint32_t bases_per_item, uint32_t dec, uint8_t* out, uint32_t ipc) {
+    __shared__ __align__(16) uint8_t text[kUnpackTile + 32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * ipc;
+    const uint32_t ni = (uint32_t)min((uint64_t)ipc, n_items - i0);
+    const uint64_t g0 = i0 * bases_per_item;  // first letter of this CTA's slice
+    const uint32_t n_bytes = ni * bases_per_item;
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(out) + g0) & 15u);
+    const uint32_t groups = (bases_per_item + 3) / 4;  // input bytes of an item that hold letters
+    for (uint32_t t = threadIdx.x; t < ni * groups; t += blockDim.x) {
+        const uint32_t it = t / groups, g = t - it * groups;
+        const uint32_t byte = in[(i0 + it) * in_bytes_per_item + g];
+        const uint32_t n = min(4u, bases_per_item - 4 * g);
+        uint8_t* d = text + mis + it * bases_per_item + 4 * g;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (j < n) d[j] = (uint8_t)(dec >> (((byte >> (2 * j)) & 3u) * 8));
+    }
+    __syncthreads();
+    uint8_t* dst = out + g0;
+    const uint32_t head = min(n_bytes, (16u - mis) & 15u);  // letters before the first 16-byte boundary
+    const uint32_t n_vec = (n_bytes - head) / 16;
+    for (uint32_t j = threadIdx.x; j < head; j += blockDim.x) dst[j] = text[mis + j];
+    for (uint32_t c = threadIdx.x; c < n_vec; c += blockDim.x)
+        *reinterpret_cast<uint4*>(dst + head + 16 * c) = *reinterpret_cast<const uint4*>(text + mis + head + 16 * c);
+    for (uint32_t j = head + 16 * n_vec + threadIdx.x; j < n_bytes; j += blockDim.x) dst[j] = text[mis + j];
+}
+
 // ---------------------------------------------------------------- Encoding::rev_comp::<K>
 // encoding/naive.rs:138-154 / xor10.rs:86-103: fields 0..K-1 are reversed and
 // complemented, bits >= 2K untouched.  One thread = one item of NW32 32-bit

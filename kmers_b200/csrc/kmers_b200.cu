@@ -1444,11 +1444,20 @@ static int32_t unpack_impl(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, con
     if (rc) return rc;
     OutBuf ob;
     if ((rc = out_prepare(ctx, 0, bases_out, n_items * bases_per_item, &ob))) return rc;
-    const uint64_t threads = n_items * ((bases_per_item + 3) / 4);
-    const uint64_t ctas = (threads + 255) / 256;
-    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
-    unpack_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items, (uint32_t)in_bytes_per_item,
-                                                          bases_per_item, dec, (uint8_t*)ob.dev);
+    if (bases_per_item <= (uint32_t)kUnpackTile) {
+        // staged through shared memory: aligned 16-byte stores whatever the item length
+        const uint32_t ipc = (uint32_t)kUnpackTile / bases_per_item;
+        const uint64_t ctas = (n_items + ipc - 1) / ipc;
+        if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+        unpack_tile_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items, (uint32_t)in_bytes_per_item,
+                                                                   bases_per_item, dec, (uint8_t*)ob.dev, ipc);
+    } else {
+        const uint64_t threads = n_items * ((bases_per_item + 3) / 4);
+        const uint64_t ctas = (threads + 255) / 256;
+        if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+        unpack_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items, (uint32_t)in_bytes_per_item,
+                                                              bases_per_item, dec, (uint8_t*)ob.dev);
+    }
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     if ((rc = out_finish(ctx, ob))) return rc;

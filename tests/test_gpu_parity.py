@@ -307,6 +307,29 @@ def test_pack_unpack_revcomp_all_encodings(ctx, ko, word_bits):
                 assert np.array_equal(rc, want_rc), (name, k)
 
 
+@pytest.mark.parametrize("k,word_bits", [(1, 8), (3, 8), (31, 64), (33, 64), (100, 32), (20000, 64)])
+def test_unpack_bulk_any_item_length(ctx, ko, k, word_bits):
+    """Bulk decode of many items whose text length is not a multiple of 4 or 16 (staged through shared memory), into
+    host memory and into a deliberately misaligned device buffer."""
+    import torch
+    import kmers_b200 as kb
+    from kmers_b200.context import _ptr
+    rng = np.random.default_rng(k)
+    n = 3 if k > 1000 else 7001
+    nw = kb.word_for_k(word_bits, k)
+    seqs = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, k))]
+    img = kb.encode(ctx, kb.ENC_ACGT, seqs, word_bits)
+    assert np.array_equal(kb.decode(ctx, kb.ENC_ACGT, img, word_bits, length=k), seqs)
+    dev_in = torch.from_numpy(img.reshape(-1).copy()).cuda()
+    for shift in (1, 5, 16):
+        buf = torch.zeros(n * k + 64, dtype=torch.uint8, device="cuda")
+        ctx._ck(ctx._lib.kmb_unpack(ctx._h, kb.ENC_ACGT, word_bits, _ptr(dev_in), n, nw, k, buf.data_ptr() + shift))
+        ctx.sync()
+        got = buf.cpu().numpy()
+        assert np.array_equal(got[shift:shift + n * k].reshape(n, k), seqs), shift
+        assert not got[:shift].any() and not got[shift + n * k:].any()
+
+
 def test_revcomp_preserves_bits_above_2k(ctx, ko):
     """encoding/naive.rs:138-154 touches fields 0..K-1 only."""
     import kmers_b200 as kb
