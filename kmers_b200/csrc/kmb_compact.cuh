@@ -9,6 +9,8 @@
 // only); after an exclusive scan of the CTA counts the emit launch re-derives the per-item offsets with a
 // CTA-wide scan and stores each valid window at its final index.
 #pragma once
+#include <cstddef>
+
 #include "kmb_extract.cuh"
 
 namespace kmb {
@@ -32,13 +34,15 @@ constexpr int kCompactRound = kExtractThreads * kRun;  // entries one round of i
 // a round's entries reach global memory as coalesced stores (each thread's <= 8 entries land at arbitrary,
 // unaligned indices; storing them directly would touch every 32-byte sector 4-8 times).
 struct CompactShared {
-    uint64_t canon[kCompactRound];
-    uint64_t hash[kCompactRound];
-    int32_t pos[kCompactRound];
     uint32_t cnt[kItemsPerCta + 1];
     uint32_t round_off[kItemsPerCta / kExtractThreads + 2];  // exclusive offset of every round's first item, and the total
     uint32_t warp_tot[kExtractThreads / 32];
+    // staging buffers of the emit launch; the counting launch allocates the struct only up to here (kCompactCountBytes)
+    alignas(16) uint64_t canon[kCompactRound];
+    uint64_t hash[kCompactRound];
+    int32_t pos[kCompactRound];
 };
+constexpr size_t kCompactCountBytes = offsetof(CompactShared, canon);
 
 template <bool VALIDATE, bool KHI, bool COUNT_ONLY>
 struct CompactEng {

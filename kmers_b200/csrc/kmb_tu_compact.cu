@@ -8,7 +8,7 @@ static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, 
                                   cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
     // dynamic shared memory = the geometry's tile (+ tables), 16-byte aligned, then CompactShared: above 48 KiB -> opt in
     const uint32_t tile_bytes = (uint32_t)((l.smem + 15) & ~(size_t)15);
-    const size_t smem = tile_bytes + sizeof(CompactShared);
+    const size_t smem = tile_bytes + (COUNT_ONLY ? kCompactCountBytes : sizeof(CompactShared));
 #define KMB_CASE(V, H)                                                                                                  \
     if (validate == V && khi == H) {                                                                                    \
         cudaError_t e;                                                                                                  \
