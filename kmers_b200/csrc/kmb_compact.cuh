@@ -38,8 +38,8 @@ struct CompactShared {
     uint32_t round_off[kItemsPerCta / kExtractThreads + 2];  // exclusive offset of every round's first item, and the total
     uint32_t warp_tot[kExtractThreads / 32];
     // staging buffers of the emit launch; the counting launch allocates the struct only up to here (kCompactCountBytes)
+    // (no hash buffer: LexHash(canon) is one pair reversal, computed when the entry leaves -- cheaper than staging it)
     alignas(16) uint64_t canon[kCompactRound];
-    uint64_t hash[kCompactRound];
     int32_t pos[kCompactRound];
 };
 constexpr size_t kCompactCountBytes = offsetof(CompactShared, canon);
@@ -110,7 +110,6 @@ struct CompactEng {
     __device__ __forceinline__ void put(uint32_t local, const Window& w, uint64_t pos) const {
         const uint32_t i = swz(local);
         sh.canon[i] = w.canon;
-        sh.hash[i] = w.hash;
         sh.pos[i] = (int32_t)pos;
     }
 
@@ -153,8 +152,9 @@ struct CompactEng {
         const uint64_t g0 = cta_base + cur_pass_base + lo;
         for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
             const uint32_t i = swz(e);
-            if (p.out.canon) p.out.canon[g0 + e] = sh.canon[i];
-            if (p.out.hash) p.out.hash[g0 + e] = sh.hash[i];
+            const uint64_t c = sh.canon[i];
+            if (p.out.canon) p.out.canon[g0 + e] = c;
+            if (p.out.hash) p.out.hash[g0 + e] = pair_reverse64(c) >> (2 * (32 - p.wc.K));  // LexHasher::write_u64, hash.rs:60-71
             if (p.out.pos) p.out.pos[g0 + e] = sh.pos[i];
         }
         __syncthreads();  // the next round re-uses the staging buffers
