@@ -1,16 +1,18 @@
-// kmb_geometry.cuh -- how a batch of reads is cut into CTA tiles and per-thread work items,
-// shared by the K <= 32 engine (kmb_extract.cuh) and the two-word engine (kmb_extract_wide.cuh).
+// kmb_geometry.cuh -- how a batch of reads is cut into CTA tiles and per-thread work items, shared by every
+// extraction-type engine: K <= 32 (kmb_extract.cuh), two-word (kmb_extract_wide.cuh), compaction (kmb_compact.cuh),
+// minimizers (kmb_minimizer.cuh).
 //
-// Work is cut in OUTPUT-slot space: item i = slots [8i, 8i+8) of the dense result arrays
-// (SURVEY.md 8d layout), so an item's stores are 64-byte (128-byte for two-word k-mers) aligned
-// whatever the read lengths are.  A slot maps back to (read, window position):
+// Work is cut in OUTPUT-slot space: an item is kRun = 8 windows of the dense result arrays (SURVEY.md 8d layout) whose
+// slots are fixed by the item's index alone (ShapeRun: 8 consecutive slots; ShapePair: two lanes interleaved over 16
+// slots), so an item's stores are aligned whatever the read lengths are.  A slot maps back to (read, window position):
 //   fixed-length reads : read = slot / W, pos = slot % W          (W = L - K + 1)
 //   ragged (CSR) reads : read = last r with win_offsets[r] <= slot, pos = slot - win_offsets[r]
-// An item lies inside one read (one span), straddles one read boundary (two spans), or -- only for
-// reads with fewer than 8 windows -- covers several reads (window-by-window path).
+// An item lies inside one read (one span), straddles one read boundary (two spans), or -- only for reads with fewer
+// windows than an item spans -- covers several reads (window-by-window path).
 //
-// A CTA first stages the stretch of the flat read stream its windows cover into shared memory
-// (2 bits/base + 1 invalid bit/base, kmb_device.cuh), then runs its items from that tile.
+// A CTA first stages the stretch of the flat read stream its windows cover into shared memory (2 bits/base + 1 invalid
+// bit/base, kmb_device.cuh), then runs its items from that tile: the common case (one clean span) in a first sweep, the
+// few two-span / dirty items densely in a second one (run_pass).
 #pragma once
 #include "kmb_device.cuh"
 
