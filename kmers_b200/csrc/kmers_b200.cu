@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -1213,8 +1214,9 @@ struct FastxSink {
     uint64_t bases_cap, reads_cap;
     uint64_t n_bases = 0, n_reads = 0;
     bool overflow = false;
+    uint64_t shift = 0;  // added to the offsets written (a chunk of a text parsed in parallel)
     void begin_read() {
-        if (offsets) { if (n_reads < reads_cap) offsets[n_reads] = n_bases; else overflow = true; }
+        if (offsets) { if (n_reads < reads_cap) offsets[n_reads] = n_bases + shift; else overflow = true; }
         ++n_reads;
     }
     void append(const char* p, size_t n) {
@@ -1272,13 +1274,81 @@ const char* parse_fastx(const char* text, uint64_t n, FastxSink& out) {
     }
     return nullptr;
 }
+
+// First record start at or after p (NULL: none before `end`).  FASTA: a line that starts with '>'.  FASTQ: a line that
+// starts with '@' AND whose second-next line starts with '+' -- a quality line may start with '@' too, but then the
+// second-next line is the following record's sequence, which never starts with '+'.
+const char* next_record(const char* text, const char* p, const char* end, char mark) {
+    if (p > text) {  // move to the start of the next line
+        p = line_end(p - 1, end);
+        if (p == end) return nullptr;
+        ++p;
+    }
+    while (p < end) {
+        if (*p == mark) {
+            if (mark == '>') return p;
+            const char* l2 = line_end(p, end);
+            const char* l3 = l2 < end ? line_end(l2 + 1, end) : end;
+            if (l3 < end && l3 + 1 < end && l3[1] == '+') return p;
+        }
+        p = line_end(p, end);
+        if (p < end) ++p;
+    }
+    return nullptr;
+}
+
+// Parse with up to n_threads threads: the text is cut at record starts, every chunk is parsed twice (count, then fill at
+// the prefix-summed positions).  Identical output to the single-threaded parse.
+const char* parse_fastx_parallel(const char* text, uint64_t n, FastxSink& out, unsigned n_threads) {
+    const char *p0 = text, *end = text + n;
+    while (p0 < end && (*p0 == '\n' || *p0 == '\r' || *p0 == ' ' || *p0 == '\t')) ++p0;
+    if (n_threads < 2 || p0 == end || (*p0 != '>' && *p0 != '@')) return parse_fastx(text, n, out);
+    const char mark = *p0;
+    std::vector<const char*> cut{p0};
+    for (unsigned t = 1; t < n_threads; ++t) {
+        const char* want = text + n / n_threads * t;
+        if (want <= cut.back()) continue;
+        const char* q = next_record(text, want, end, mark);
+        if (q && q > cut.back()) cut.push_back(q);
+    }
+    cut.push_back(end);
+    const size_t nc = cut.size() - 1;
+    if (nc < 2) return parse_fastx(text, n, out);
+    std::vector<FastxSink> part(nc, FastxSink{nullptr, nullptr, 0, 0});
+    std::vector<const char*> err(nc, nullptr);
+    auto run = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (size_t c = 1; c < nc; ++c) th.emplace_back(fn, c);
+        fn(0);
+        for (auto& t : th) t.join();
+    };
+    run([&](size_t c) { err[c] = parse_fastx(cut[c], (uint64_t)(cut[c + 1] - cut[c]), part[c]); });
+    for (size_t c = 0; c < nc; ++c)
+        if (err[c]) return err[c];
+    std::vector<uint64_t> base0(nc + 1, 0), read0(nc + 1, 0);
+    for (size_t c = 0; c < nc; ++c) { base0[c + 1] = base0[c] + part[c].n_bases; read0[c + 1] = read0[c] + part[c].n_reads; }
+    out.n_bases = base0[nc];
+    out.n_reads = read0[nc];
+    if ((out.bases && out.n_bases > out.bases_cap) || (out.offsets && out.n_reads > out.reads_cap)) { out.overflow = true; return nullptr; }
+    if (!out.bases && !out.offsets) return nullptr;  // sizing call
+    run([&](size_t c) {
+        FastxSink s{out.bases ? out.bases + base0[c] : nullptr, out.offsets ? out.offsets + read0[c] : nullptr, part[c].n_bases,
+                    part[c].n_reads};
+        s.shift = base0[c];
+        parse_fastx(cut[c], (uint64_t)(cut[c + 1] - cut[c]), s);
+    });
+    return nullptr;
+}
 }  // namespace
 
 extern "C" int32_t kmb_parse_fastx(const char* text, uint64_t n_bytes, uint8_t* bases_out, uint64_t bases_cap, uint64_t* offsets_out,
                                    uint64_t reads_cap, uint64_t* n_reads, uint64_t* n_bases) {
     if (n_bytes && !text) return fail(nullptr, KMB_ERR_INVALID_ARG, "text is NULL");
     FastxSink sink{bases_out, offsets_out, bases_cap, reads_cap};
-    const char* err = parse_fastx(text, n_bytes, sink);
+    // one thread per ~4 MiB of text, at most the hardware's; KMB_PARSE_THREADS overrides (tests)
+    unsigned n_threads = (unsigned)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), n_bytes >> 22);
+    if (const char* env = getenv("KMB_PARSE_THREADS")) n_threads = (unsigned)atoi(env);
+    const char* err = parse_fastx_parallel(text, n_bytes, sink, std::min(n_threads, 64u));
     if (err) return fail(nullptr, KMB_ERR_INVALID_ARG, "%s", err);
     if (n_reads) *n_reads = sink.n_reads;
     if (n_bases) *n_bases = sink.n_bases;

@@ -49,6 +49,29 @@ def test_parse_large_roundtrip(kb):
         assert _reads(bases, offs) == reads
 
 
+@pytest.mark.parametrize("threads", [2, 3, 7, 16])
+def test_parallel_parse_matches_serial(kb, threads, monkeypatch):
+    """The text is cut at record starts and parsed by several threads; the result must not depend on the cut points --
+    including FASTQ whose quality lines start with '@' or '+', blank lines between records, CRLF, and empty reads."""
+    rng = np.random.default_rng(threads)
+    pick = lambda alphabet, n: np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), size=n)].tobytes()
+    reads = [pick(b"ACGTN", int(n)) for n in rng.integers(0, 120, size=4000)]
+    quals = [pick(b"@+I#>", len(r)) for r in reads]
+    fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, q) + (b"\n" if i % 97 == 0 else b"") for i, (r, q) in enumerate(zip(reads, quals)))
+    fq_crlf = fq.replace(b"\n", b"\r\n")
+    fa = b"".join(b">r%d\n" % i + b"\n".join(r[j:j + 50] for j in range(0, len(r), 50)) + b"\n" for i, r in enumerate(reads))
+    for text in (fq, fq_crlf, fa, b"\n\n" + fq):
+        monkeypatch.setenv("KMB_PARSE_THREADS", "1")
+        b1, o1 = kb.parse_fastx(text)
+        monkeypatch.setenv("KMB_PARSE_THREADS", str(threads))
+        bn, on = kb.parse_fastx(text)
+        assert np.array_equal(b1, bn) and np.array_equal(o1, on)
+        assert _reads(bn, on) == reads
+    monkeypatch.setenv("KMB_PARSE_THREADS", str(threads))
+    with pytest.raises(kb.KmbError):
+        kb.parse_fastx(fq + b"@broken\nACGT\n+\nII\n")   # the error of a later chunk is reported too
+
+
 @pytest.mark.gpu
 def test_ingest_and_extract(kb):
     import oracle as ko
