@@ -5,9 +5,13 @@ import pytest
 
 @pytest.fixture(scope="module")
 def kb():
-    import __graft_entry__ as g
-    g.build()
     import kmers_b200
+    from kmers_b200 import _native
+    try:
+        _native.lib()  # the in-tree library, when it is already built (no subprocess from a process that may hold a CUDA context)
+    except Exception:
+        import __graft_entry__ as g
+        g.build()
     return kmers_b200
 
 
@@ -41,7 +45,8 @@ def test_parse_empty_and_errors(kb):
 
 def test_parse_large_roundtrip(kb):
     rng = np.random.default_rng(0)
-    reads = [bytes(rng.choice(list(b"ACGTNacgt"), size=int(n))) for n in rng.integers(0, 400, size=2000)]
+    letters = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
+    reads = [letters[rng.integers(0, 9, size=int(n))].tobytes() for n in rng.integers(0, 400, size=2000)]
     fa = b"".join(b">r%d\n" % i + b"\n".join(r[j:j + 60] for j in range(0, len(r), 60)) + b"\n" for i, r in enumerate(reads))
     fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
     for text in (fa, fq):
@@ -76,7 +81,8 @@ def test_parallel_parse_matches_serial(kb, threads, monkeypatch):
 def test_ingest_and_extract(kb):
     import oracle as ko
     rng = np.random.default_rng(1)
-    reads = [bytes(rng.choice(list(b"ACGTNacgt"), size=int(n), p=[.24, .24, .24, .24, .01, .01, .01, .005, .005]))
+    letters = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
+    reads = [letters[rng.choice(9, size=int(n), p=[.24, .24, .24, .24, .01, .01, .01, .005, .005])].tobytes()
              for n in rng.integers(0, 300, size=3000)]
     fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
     with kb.Context(0) as ctx:
@@ -88,3 +94,4 @@ def test_ingest_and_extract(kb):
     ref = ko.extract_canonical(bases, 31, offsets=offs)
     assert np.array_equal(res.canon, ref["canon"]) and np.array_equal(res.hash, ref["hash"])
     assert res.digest == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+    assert ref["n_valid"] > 100_000   # real reads: most windows are valid
