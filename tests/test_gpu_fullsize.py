@@ -157,6 +157,46 @@ def test_more_than_2_pow_32_slots():
         assert res.digest == tuple(tot)
 
 
+def test_ragged_batch_with_more_than_2_pow_32_slots():
+    """The ragged (CSR) geometry at maximum size: 4.6e7 reads of 100..160 bases cut from one generated stream, 4.6e9
+    output slots (> 2^32).  Digest vs the multi-threaded oracle; the last reads bit-exact."""
+    import torch
+    import kmers_b200 as kb
+    import oracle as ko
+    n = 46_000_000
+    rng = np.random.default_rng(9)
+    lens = rng.integers(100, 161, size=n).astype(np.int64)
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    total = int(offs[-1])
+    n_slots = int((lens - (K - 1)).sum())
+    assert n_slots > 2**32
+    with kb.Context(0, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        flat = ctx.generate(SEED, 1, total, n_thresh20=200)          # one stream of `total` bases on the device ...
+        bases_dev = torch.empty(total, dtype=torch.uint8, device="cuda")
+        ctx._ck(ctx._lib.kmb_batch_download(ctx._h, bases_dev.data_ptr(), total))
+        ctx.sync()
+        batch = ctx.attach(bases_dev, dev_offsets=torch.from_numpy(offs).cuda())   # ... read as ragged reads
+        out = kb.CanonicalKmers(k=K, n_slots=n_slots, canon=torch.empty(n_slots, dtype=torch.int64, device="cuda"), hash=None)
+        res = batch.extract_canonical(K, digest=True, out=out)
+        torch.cuda.synchronize()
+        tail = 3000
+        b0 = int(offs[n - tail])
+        bases_tail = ko.generate_bases(SEED, b0, total - b0, 200)
+        ref = ko.extract_canonical(bases_tail, K, offsets=(offs[n - tail:] - b0).astype(np.uint64))
+        assert np.array_equal(out.canon[n_slots - ref["canon"].size:].cpu().numpy().view(np.uint64), ref["canon"])
+        tot = [0, 0, 0]
+        parts = 6
+        for c in range(parts):
+            r0, r1 = n * c // parts, n * (c + 1) // parts
+            hb = ko.generate_bases(SEED, int(offs[r0]), int(offs[r1] - offs[r0]), 200)
+            d = ko.extract_canonical(hb, K, offsets=(offs[r0:r1 + 1] - offs[r0]).astype(np.uint64), n_threads=os.cpu_count() or 1,
+                                     materialize=False)
+            tot = [(a + b) % 2**64 for a, b in zip(tot, (d["n_valid"], d["checksum_canon"], d["checksum_hash"]))]
+            del hb
+        assert res.digest == tuple(tot)
+
+
 def test_histogram_exact_under_maximum_contention():
     """Shared-memory bins: every thread of every CTA hammers the two 16-bit counters of ONE 32-bit word (hist_bits = 2:
     poly-A / poly-T reads fall into bin 0, poly-G reads -- canonical poly-C -- into bin 1).  240 M increments; the
