@@ -139,36 +139,34 @@ __global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) 
         return __funnelshift_r(tile[e].x, tile[e + 1].x, o2);
     };
     auto low_bits = [](uint32_t n) -> uint32_t { return n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u); };
+    // Everything below is 32-bit and relative to the CTA (the host sends reads of 2^30 bases or more elsewhere): base x of
+    // read r_first + q sits at tile position q * L + x - s_first + mis.
+    const uint32_t L = p.L32, s_first = min(b_first * 4, L), bias = mis - s_first;
     const uint32_t n_words = (n_out + 3) / 4;
     for (uint32_t li = threadIdx.x; li < n_words; li += blockDim.x) {
         const uint32_t u = b_first + 4 * li, q = div_obr(u, p), b = u - q * p.obr;  // first byte of the word inside its read
         const uint32_t here = min(4u, n_out - 4 * li);                              // bytes of this word that exist
+        const uint32_t b0 = b * 4;
         uint32_t bits = 0;
         if (MODE == 0) {
-            const uint64_t b0 = (uint64_t)b * 4;
-            if (b0 < p.L) bits = extract((uint32_t)((r_first + q) * p.L + b0 - s_start) + mis) & low_bits(2 * (uint32_t)min((uint64_t)16, p.L - b0));
+            if (b0 < L) bits = extract(q * L + b0 + bias) & low_bits(2 * min(16u, L - b0));
         } else if (MODE == 1) {
             // A word holds bytes of at most two reads: n_a from read q (bases 4b ..), the rest from read q+1 (from its base
             // 0 on).  Both parts are one 16-base extract, masked to the bases that exist -- the same instructions for every
             // lane, whether its word straddles a region boundary or not (a branch here would cost every warp both paths).
             const uint32_t n_a = min(here, p.obr - b);
-            const uint64_t b0 = (uint64_t)b * 4;
-            const uint32_t have_a = b0 < p.L ? (uint32_t)min((uint64_t)(4 * n_a), p.L - b0) : 0u;  // bases of read q in this word
-            const uint32_t rel_a = (uint32_t)((r_first + q) * p.L + min(b0, p.L) - s_start) + mis;
+            const uint32_t have_a = b0 < L ? min(4 * n_a, L - b0) : 0u;  // bases of read q in this word
+            const uint32_t rel_a = q * L + min(b0, L) + bias;
             bits = extract(rel_a) & low_bits(2 * have_a);
             const bool two = n_a < here;
-            const uint32_t have_b = two ? (uint32_t)min((uint64_t)(4 * (here - n_a)), p.L) : 0u;
+            const uint32_t have_b = two ? min(4 * (here - n_a), L) : 0u;
             // read q+1's base 0 lands at base 4 * n_a of the word: start 4 * n_a bases early (inside the margin at worst)
-            const uint32_t rel_b = two ? (uint32_t)((r_first + q + 1) * p.L - s_start) + mis - 4 * n_a : rel_a;
+            const uint32_t rel_b = two ? (q + 1) * L + bias - 4 * n_a : rel_a;
             bits |= extract(rel_b) & (low_bits(8 * n_a + 2 * have_b) & ~low_bits(8 * n_a));
         } else {
             for (uint32_t j = 0; j < here; ++j) {  // regions of 1..3 bytes: byte by byte
-                const uint32_t uj = u + j, qj = div_obr(uj, p), bj = uj - qj * p.obr;
-                const uint64_t bj0 = (uint64_t)bj * 4;
-                if (bj0 < p.L) {
-                    const uint32_t have = (uint32_t)min((uint64_t)4, p.L - bj0);
-                    bits |= (extract((uint32_t)((r_first + qj) * p.L + bj0 - s_start) + mis) & low_bits(2 * have)) << (8 * j);
-                }
+                const uint32_t uj = u + j, qj = div_obr(uj, p), bj0 = (uj - qj * p.obr) * 4;
+                if (bj0 < L) bits |= (extract(qj * L + bj0 + bias) & low_bits(2 * min(4u, L - bj0))) << (8 * j);
             }
         }
         uint8_t* dst = p.out + byte_base + 4 * li;

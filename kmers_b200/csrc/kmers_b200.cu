@@ -1428,7 +1428,7 @@ extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, vo
         p.bases = ctx->d_bases; p.offsets = ctx->d_offsets; p.word_offsets = d_woff; p.n_reads = ctx->n_reads;
         p.L = ctx->fixed_len; p.word_bytes = word_bytes; p.bases_per_word = bpw; p.out = (uint8_t*)ob.dev;
         const uint64_t obr = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;  // bytes of one read's packed region
-        if (!ctx->d_offsets && ((uintptr_t)ob.dev & 3u) == 0 && obr <= 0xFFFFFFFFull) {
+        if (!ctx->d_offsets && ((uintptr_t)ob.dev & 3u) == 0 && ctx->fixed_len < (1ull << 30)) {
             // tiled kernel (aligned loads, coalesced 4-byte stores)
             PackTileParams t{};
             t.bases = ctx->d_bases; t.n_bytes = ctx->n_bytes; t.L = ctx->fixed_len; t.L32 = (uint32_t)ctx->fixed_len;
