@@ -245,10 +245,10 @@ struct NarrowEng {
     using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;  // tile entries one span reads
-    // resident CTAs per SM the register allocation must allow (an explicit 1 would let the compiler take ~80-90
-    // registers and halve the occupancy): 4 = 64 registers; the canonical-words-only variant is ALU-bound and fits 5, the four-array
-    // variant needs ~100 registers
-    static constexpr int kMinCtas = FWRC ? 2 : ((!HASH && !DIGEST && MODE == 0) ? 5 : 4), kMinCtasCsr = FWRC ? 2 : 4;
+    // Resident CTAs per SM the register allocation must allow; 0 = left to the compiler, which lands on 40-63 registers for
+    // the fixed-length kernels (an explicit 1 made it take 80-90 and halve the occupancy; an explicit 6 for the
+    // canonical-words-only variant made it spill).  The ragged kernels need the cap: 73 registers -> 64 took them 86 % -> 95 %.
+    static constexpr int kMinCtas = 0, kMinCtasCsr = FWRC ? 2 : 4;
     const NarrowParams& p;
     Acc acc;
     __device__ explicit NarrowEng(const NarrowParams& params) : p(params) {}

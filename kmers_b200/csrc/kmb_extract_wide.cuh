@@ -224,7 +224,7 @@ struct WideEng {
     using Shape = ShapePair;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = NW32 + 2;  // tile entries one span reads
-    static constexpr int kMinCtas = DIGEST ? 3 : 4, kMinCtasCsr = DIGEST ? 3 : 4;  // resident CTAs/SM the register allocation must allow
+    static constexpr int kMinCtas = 0, kMinCtasCsr = DIGEST ? 3 : 4;  // resident CTAs/SM the register allocation must allow (0: compiler's choice)
     const WideParams& p;
     WideAcc acc;
     __device__ explicit WideEng(const WideParams& params) : p(params) {}
