@@ -153,7 +153,11 @@ __device__ __forceinline__ void span_minimizers32(const Span& s, const MinConst&
         // common part [kRun-1, m-1], right to left: position m-1-t sits at bit 2*(kRun-1) + 2t
         Key c = Key::worst();
         const uint32_t tmax = m - (uint32_t)kRun;  // <= 24
-        for (uint32_t t = 0; t <= min(tmax, 8u); ++t) c.take_left(Key::make(__funnelshift_r(p0, p1, 2 * (kRun - 1) + 2 * t), m - 1 - t, mc));
+#pragma unroll
+        for (uint32_t t = 0; t <= 8u; ++t) {  // compile-time shifts; the kernel-uniform guard becomes a uniform branch
+            if (t > tmax) break;
+            c.take_left(Key::make(__funnelshift_r(p0, p1, 2 * (kRun - 1) + 2 * t), m - 1 - t, mc));
+        }
         for (uint32_t t = 9; t <= tmax; ++t) c.take_left(Key::make(__funnelshift_r(p1, p2, 2 * t - 18), m - 1 - t, mc));
         // suffixes of [0, kRun-2]: Q = P >> 2m puts position p at bit 2*(kRun-2-p)
         uint32_t q0, q1, q2;
