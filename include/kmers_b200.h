@@ -58,6 +58,10 @@ extern "C" {
 
 /* flags for kmb_extract_canonical* */
 #define KMB_F_NO_VALIDATE 0x1u /* Path-E semantics: every window is kept, bytes map by (c>>1)&3 */
+/* kmb_histogram only: accumulate {n_valid, checksum_canon, checksum_hash} into hist_out[n_bins .. n_bins + 2] instead of
+ * reading a digest back: [bins | digest] is then one buffer of n_bins + 3 words that the ranks all-reduce in place
+ * (SURVEY 8e), and the call stays asynchronous. */
+#define KMB_F_DIGEST_IN_HIST 0x2u
 
 /* MatchType, naive_impl/canonical_kmer.rs:7-12 */
 #define KMB_NO_MATCH 0
@@ -165,17 +169,44 @@ int32_t kmb_extract_canonical_wide(kmb_ctx *ctx, uint32_t k, int32_t enc, uint32
 /* Fused, nothing materialised: histogram of emitted windows by the top
  * hist_bits of the 2k-bit LexHash (1 << hist_bits u64 bins, device or host
  * dst, ACCUMULATED into when accumulate != 0) + digest.  Config 5 of
- * BASELINE.json; the bins are what ranks all-reduce. */
+ * BASELINE.json; the bins are what ranks all-reduce.  With KMB_F_DIGEST_IN_HIST hist_out has 3 more words, which
+ * receive the digest (digest must be NULL). */
 int32_t kmb_histogram(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint32_t hist_bits, uint64_t *hist_out,
                       int32_t accumulate, kmb_digest *digest);
 
-/* One-shot end-to-end form with HOST buffers: chunks the reads, and overlaps
- * pinned-staged H2D, the extraction kernel and (when host outputs are given)
- * the D2H of results.  host_canon / host_hash may be NULL (digest only; the
- * outputs then stay in device scratch).  Fixed-length reads only. */
+/* One-shot end-to-end form for reads that live in HOST memory (pinned or pageable; fixed-length reads): the same
+ * outputs as kmb_extract_canonical for n_reads reads of fixed_len bases at host_bases.
+ *   out_canon / out_hash: DEVICE arrays for the whole batch (n_reads * (fixed_len - k + 1) words each; written in place,
+ *   the results stay resident), HOST arrays of that size (copied back chunk by chunk on a stream of their own while
+ *   later chunks upload and compute), or NULL (that array is not produced; both NULL = digest only).
+ * The call chunks the reads and overlaps, on three streams: host-side packing of the ASCII bytes to 2 bits + 1 validity
+ * bit per base by a pool of worker threads (3 bits/base cross PCIe instead of 8; for pageable input this doubles as the
+ * staging copy), H2D, the extraction kernel, and the D2H of results.  When the input is pinned, chunks the packers have
+ * not reached are also sent as raw ASCII whenever the link would otherwise idle.  Only format conversion and copies run
+ * on the host: every k-mer is computed by the GPU kernel.  Synchronous.  This is the device-resident read-batch buffer
+ * with pinned-host staging that BASELINE.json's north_star names. */
 int32_t kmb_extract_canonical_host(kmb_ctx *ctx, const uint8_t *host_bases, uint64_t n_reads,
-                                   uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t *host_canon,
-                                   uint64_t *host_hash, kmb_digest *digest);
+                                   uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t *out_canon,
+                                   uint64_t *out_hash, kmb_digest *digest);
+/* The same for reads the caller already holds 2-bit packed in host memory: host_bits[i] = bases 16i .. 16i+15 of the
+ * concatenated reads (base j at bits 2j+1:2j, A0 C1 G2 T3 -- SeqVector's bit layout, naive_impl/seq_vector.rs:230-242,
+ * without per-read padding), host_inv[i] bit j = base 16i+j is not one of ACGTacgt (NULL: no invalid base, as in a
+ * SeqVector).  kmb_host_pack writes both.  0.25 - 0.375 B/base cross PCIe and no host thread touches the data. */
+int32_t kmb_extract_canonical_host_packed(kmb_ctx *ctx, const uint32_t *host_bits, const uint16_t *host_inv,
+                                          uint64_t n_reads, uint64_t fixed_len, uint32_t k, uint32_t flags,
+                                          uint64_t *out_canon, uint64_t *out_hash, kmb_digest *digest);
+/* ASCII -> the packed staging format above, on the host (SIMD, single-threaded; needs no GPU): the host twin of
+ * SeqVector::from(&[u8]) (seq_vector.rs:230-242) plus the validity mask a SeqVector cannot hold (naive_impl/mod.rs:40-50).
+ * bits_out / inv_out receive ceil(n_bases / 16) entries; bytes outside ACGTacgt encode by (c >> 1) & 3 like
+ * Encoding::encode and set their invalid bit. */
+int32_t kmb_host_pack(const uint8_t *bases, uint64_t n_bases, uint32_t *bits_out, uint16_t *inv_out);
+/* which implementation kmb_host_pack runs on this CPU: "avx512bw", "avx2" or "swar" */
+const char *kmb_host_pack_isa(void);
+/* worker threads of the host pipeline (0 = default: the CPUs the process may run on, at most 32; one process per GPU on
+ * a shared host should divide the cores between the ranks) */
+int32_t kmb_ctx_set_host_threads(kmb_ctx *ctx, uint32_t n_threads);
+/* what the last kmb_extract_canonical_host* call did: stats4 = {chunks, chunks sent as raw ASCII, H2D bytes, D2H bytes} */
+int32_t kmb_ctx_host_stats(const kmb_ctx *ctx, uint64_t *stats4);
 
 /* ---- "next" row N1: minimizers ------------------------------------------ */
 /* One (lmer, pos) per k-mer window of every read, dense slots as kmb_extract_canonical: the LEFTMOST w-mer of

@@ -17,6 +17,7 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_PANIC, ERR_NOMEM = -1, 
 SENTINEL = 0xFFFFFFFFFFFFFFFF
 ENC_ACGT, ENC_ACTG, ENC_XOR10 = 0x1E, 0x1B, 0x100
 F_NO_VALIDATE = 0x1
+F_DIGEST_IN_HIST = 0x2
 NO_MATCH, IDENTITY_MATCH, TWIN_MATCH = 0, 1, 2
 
 
@@ -68,6 +69,11 @@ SIGNATURES = {
     "kmb_extract_canonical_wide": (_i32, [_vp, _u32, _i32, _u32, _vp, _vp, _pd]),
     "kmb_histogram": (_i32, [_vp, _u32, _u32, _u32, _vp, _i32, _pd]),
     "kmb_extract_canonical_host": (_i32, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _pd]),
+    "kmb_extract_canonical_host_packed": (_i32, [_vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _pd]),
+    "kmb_host_pack": (_i32, [_vp, _u64, _vp, _vp]),
+    "kmb_host_pack_isa": (C.c_char_p, []),
+    "kmb_ctx_set_host_threads": (_i32, [_vp, _u32]),
+    "kmb_ctx_host_stats": (_i32, [_vp, _pu64]),
     "kmb_minimizers": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "kmb_minimizer_words": (_i32, [_vp, _u32, _u32, _u32, _vp, _u64, _vp, _vp]),
     "kmb_batch_repack": (_i32, [_vp, _i32]),

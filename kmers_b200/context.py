@@ -105,6 +105,44 @@ class Context:
     def sync(self):
         self._ck(self._lib.kmb_ctx_sync(self._h))
 
+    # ---- stream ordering against torch (the owner of the device tensors handed in / out)
+    # Async contract: calls that write DEVICE outputs return once the work is enqueued on the context's stream.  The
+    # tensors are allocated by torch on ITS current stream, so when the two streams differ (the default: a context owns a
+    # private non-blocking stream) `_order_in` makes the context's stream wait for torch's pending work before the call and
+    # `_order_out` makes torch's current stream wait for the kernels after it (+ record_stream, so the caching allocator
+    # does not hand the memory out again while a kernel still writes it).  Any torch op on the results -- `.cpu()`,
+    # `CanonicalKmers.host()`, dropping the tensor -- is then ordered after the kernels.
+    def _streams(self):
+        t = _torch()
+        if not t.cuda.is_available():
+            return None
+        cur = t.cuda.current_stream()
+        mine = self.stream
+        if mine in (0, 1):  # legacy default stream: synchronises with torch's default stream implicitly
+            mine = 0
+        if int(cur.cuda_stream) == mine:
+            return None
+        return t, cur, t.cuda.ExternalStream(self.stream if self.stream not in (0, 1) else 0)
+
+    def _order_in(self, *xs):
+        if not any(_is_tensor(x) and x.is_cuda for x in xs if x is not None):
+            return
+        st = self._streams()
+        if st is not None:
+            _, cur, ext = st
+            ext.wait_stream(cur)
+
+    def _order_out(self, *xs):
+        ts = [x for x in xs if x is not None and _is_tensor(x) and x.is_cuda]
+        if not ts:
+            return
+        st = self._streams()
+        if st is not None:
+            _, cur, ext = st
+            cur.wait_stream(ext)
+            for x in ts:
+                x.record_stream(ext)
+
     @property
     def stream(self) -> int:
         return int(self._lib.kmb_ctx_stream(self._h) or 0)
@@ -135,6 +173,7 @@ class Context:
             n_reads = dev_offsets.numel() - 1
         elif n_reads is None:
             n_reads = n_bytes // fixed_len if fixed_len else 0
+        self._order_in(dev_bases, dev_offsets)
         self._ck(self._lib.kmb_batch_attach(self._h, _ptr(dev_bases), n_bytes, _ptr(dev_offsets), n_reads, fixed_len))
         self._keep = [dev_bases, dev_offsets]
         return ReadBatch(self, n_bytes, n_reads, fixed_len, dev_offsets is not None)
@@ -152,16 +191,48 @@ class Context:
         self._keep = []
         return ReadBatch(self, int(nb.value), int(nr.value), 0, True)
 
-    # ---- one-shot host path (e2e): chunked, H2D / kernel / D2H overlapped
+    # ---- one-shot host path (e2e): chunked; host packing, H2D, kernel and D2H overlapped
     def extract_canonical_host(self, host_bases: np.ndarray, n_reads: int, fixed_len: int, k: int, *,
-                               host_canon: Optional[np.ndarray] = None, host_hash: Optional[np.ndarray] = None,
+                               out_canon=None, out_hash=None, host_canon=None, host_hash=None,
                                validate: bool = True, digest: bool = True):
+        """kmb_extract_canonical_host: reads in HOST memory -> canonical words / LexHashes.
+
+        out_canon / out_hash: torch int64 CUDA tensors for the whole batch (results stay resident on the device), numpy
+        uint64 / pinned torch arrays (results copied back), or None (not produced).  host_canon / host_hash are the
+        round-1 names of the same arguments.  Returns the digest tuple (or None)."""
+        out_canon = host_canon if out_canon is None else out_canon
+        out_hash = host_hash if out_hash is None else out_hash
         d = Digest()
         flags = 0 if validate else nv.F_NO_VALIDATE
+        self._order_in(out_canon, out_hash)
         self._ck(self._lib.kmb_extract_canonical_host(self._h, _ptr(host_bases), n_reads, fixed_len, k, flags,
-                                                      _ptr(host_canon), _ptr(host_hash),
+                                                      _ptr(out_canon), _ptr(out_hash),
                                                       C.byref(d) if digest else None))
+        self._order_out(out_canon, out_hash)
         return d.astuple() if digest else None
+
+    def extract_canonical_host_packed(self, host_bits: np.ndarray, host_inv: Optional[np.ndarray], n_reads: int,
+                                      fixed_len: int, k: int, *, out_canon=None, out_hash=None, validate: bool = True,
+                                      digest: bool = True):
+        """kmb_extract_canonical_host_packed: reads already 2-bit packed on the host (`host_pack`)."""
+        d = Digest()
+        flags = 0 if validate else nv.F_NO_VALIDATE
+        self._order_in(out_canon, out_hash)
+        self._ck(self._lib.kmb_extract_canonical_host_packed(self._h, _ptr(host_bits), _ptr(host_inv), n_reads, fixed_len,
+                                                             k, flags, _ptr(out_canon), _ptr(out_hash),
+                                                             C.byref(d) if digest else None))
+        self._order_out(out_canon, out_hash)
+        return d.astuple() if digest else None
+
+    def set_host_threads(self, n: int):
+        """Worker threads of the host pipeline (0 = default)."""
+        self._ck(self._lib.kmb_ctx_set_host_threads(self._h, n))
+
+    def host_stats(self) -> dict:
+        """What the last extract_canonical_host* call did."""
+        st = (C.c_uint64 * 4)()
+        self._ck(self._lib.kmb_ctx_host_stats(self._h, st))
+        return {"chunks": int(st[0]), "raw_chunks": int(st[1]), "h2d_bytes": int(st[2]), "d2h_bytes": int(st[3])}
 
     # ---- element-wise word ops (naive_impl::Kmer in batch)
     @staticmethod
@@ -182,6 +253,7 @@ class Context:
         """Kmer::get_reverse_complement_word (naive_impl/kmer.rs:138-147) on every word."""
         n, w, to = self._words_in(words, to)
         out = self._alloc(n, to, np.uint64)
+        self._order_in(w, out)
         self._ck(self._lib.kmb_reverse_complement_words(self._h, k, _ptr(w), _ptr(out), n))
         self.sync()
         return out
@@ -191,6 +263,7 @@ class Context:
         n, w, to = self._words_in(words, to)
         out = self._alloc(n, to, np.uint64)
         flag = self._alloc(n, to, np.uint8)
+        self._order_in(w, out, flag)
         self._ck(self._lib.kmb_canonical_words(self._h, k, _ptr(w), _ptr(out), _ptr(flag), n))
         self.sync()
         return out, flag
@@ -199,6 +272,7 @@ class Context:
         """hash_one(&LexHasherState::new(k), kmer) (naive_impl/hash.rs:10-20, 60-71) on every word."""
         n, w, to = self._words_in(words, to)
         out = self._alloc(n, to, np.uint64)
+        self._order_in(w, out)
         self._ck(self._lib.kmb_lexhash_words(self._h, k, _ptr(w), _ptr(out), n))
         self.sync()
         return out
@@ -208,6 +282,7 @@ class Context:
         n, w, to = self._words_in(words, to)
         o = others if _is_tensor(others) else np.ascontiguousarray(others, dtype=np.uint64)
         out = self._alloc(n, to, np.uint8)
+        self._order_in(w, o, out)
         self._ck(self._lib.kmb_match_words(self._h, k, _ptr(w), _ptr(o), _ptr(out), n))
         self.sync()
         return out
@@ -222,6 +297,7 @@ class Context:
             off = t.empty(n, dtype=t.int32, device="cuda")
         else:
             off = np.empty(n, dtype=np.uint32)
+        self._order_in(wd, mm, off)
         self._ck(self._lib.kmb_minimizer_words(self._h, k, w, hash_k, _ptr(wd), n, _ptr(mm), _ptr(off)))
         self.sync()
         return mm, off
@@ -302,8 +378,10 @@ class ReadBatch:
                 out.fw, out.rc = self._alloc(n, to), self._alloc(n, to)
         d = Digest()
         flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._order_in(out.canon, out.hash, out.fw, out.rc)
         self.ctx._ck(self.ctx._lib.kmb_extract_canonical(self.ctx._h, k, flags, _ptr(out.canon), _ptr(out.hash),
                                                          _ptr(out.fw), _ptr(out.rc), C.byref(d) if digest else None))
+        self.ctx._order_out(out.canon, out.hash, out.fw, out.rc)
         out.digest = d.astuple() if digest else None
         return out
 
@@ -333,6 +411,7 @@ class ReadBatch:
         else:
             mm, pos = np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.uint32)
         flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._order_in(mm, pos)
         self.ctx._ck(self.ctx._lib.kmb_minimizers(self.ctx._h, k, w, hash_k, flags, _ptr(mm), _ptr(pos)))
         self.ctx.sync()
         return mm, pos
@@ -353,6 +432,7 @@ class ReadBatch:
             canon, hsh = np.empty(m, dtype=np.uint64), np.empty(m, dtype=np.uint64)
             pos = np.empty(m, dtype=np.int32)
             offs = np.empty(self.n_reads + 1, dtype=np.uint64)
+        self.ctx._order_in(canon, hsh, pos, offs)
         self.ctx._ck(self.ctx._lib.kmb_extract_compact(self.ctx._h, k, flags, _ptr(canon), _ptr(hsh), _ptr(pos), _ptr(offs), m,
                                                        C.byref(n)))
         return dict(pos=pos, canon=canon, hash=hsh, emit_offsets=offs, n=int(n.value))
@@ -366,22 +446,31 @@ class ReadBatch:
         out.hash = self._alloc(2 * n, to) if want_hash else None
         d = Digest()
         flags = 0 if validate else nv.F_NO_VALIDATE
+        self.ctx._order_in(out.canon, out.hash)
         self.ctx._ck(self.ctx._lib.kmb_extract_canonical_wide(self.ctx._h, k, enc, flags, _ptr(out.canon), _ptr(out.hash),
                                                               C.byref(d) if digest else None))
+        self.ctx._order_out(out.canon, out.hash)
         out.digest = d.astuple() if digest else None
         return out
 
     def histogram(self, k: int, hist_bits: int, *, hist=None, accumulate: bool = False, digest: bool = True,
-                  validate: bool = True, to: str = "device"):
-        """Fused extraction -> LexHash-prefix histogram + digest, nothing materialised (kmb_histogram)."""
+                  validate: bool = True, to: str = "device", digest_in_hist: bool = False):
+        """Fused extraction -> LexHash-prefix histogram + digest, nothing materialised (kmb_histogram).
+
+        digest_in_hist: `hist` has 2^hist_bits + 3 words and the digest is accumulated into the last three on the
+        device (KMB_F_DIGEST_IN_HIST): one buffer to all-reduce in place, no read-back, the call stays asynchronous."""
+        n = (1 << hist_bits) + (3 if digest_in_hist else 0)
         if hist is None:
-            hist = self._alloc(1 << hist_bits, to)
+            hist = self._alloc(n, to)
             accumulate = False
         d = Digest()
-        flags = 0 if validate else nv.F_NO_VALIDATE
+        flags = (0 if validate else nv.F_NO_VALIDATE) | (nv.F_DIGEST_IN_HIST if digest_in_hist else 0)
+        want = digest and not digest_in_hist
+        self.ctx._order_in(hist)
         self.ctx._ck(self.ctx._lib.kmb_histogram(self.ctx._h, k, flags, hist_bits, _ptr(hist), int(accumulate),
-                                                 C.byref(d) if digest else None))
-        return hist, (d.astuple() if digest else None)
+                                                 C.byref(d) if want else None))
+        self.ctx._order_out(hist)
+        return hist, (d.astuple() if want else None)
 
     def pack(self, enc: int = nv.ENC_ACGT, word_bits: int = 64, to: str = "host"):
         """Encoding::encode of every read (kmb_pack).  Returns (byte image, word offsets or None)."""
@@ -394,8 +483,27 @@ class ReadBatch:
         else:
             out = np.empty(nbytes, dtype=np.uint8)
         woff = np.empty(self.n_reads + 1, dtype=np.uint64) if self.ragged else None
+        self.ctx._order_in(out)
         self.ctx._ck(self.ctx._lib.kmb_pack(self.ctx._h, enc, word_bits, _ptr(out), _ptr(woff)))
         return out, woff
+
+
+def host_pack(bases, bits: Optional[np.ndarray] = None, inv: Optional[np.ndarray] = None):
+    """ASCII bases -> (bits uint32, inv uint16), 16 bases per entry: the flat 2-bit + validity staging format
+    (kmb_host_pack; host SIMD code, needs no GPU).  `bits` / `inv` may be preallocated (e.g. pinned) arrays."""
+    lib = nv.lib()
+    b = np.ascontiguousarray(np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else bases,
+                             dtype=np.uint8)
+    nw = (b.size + 15) // 16
+    bits = np.empty(nw, dtype=np.uint32) if bits is None else bits
+    inv = np.empty(nw, dtype=np.uint16) if inv is None else inv
+    assert bits.size >= nw and inv.size >= nw
+    check(None, lib.kmb_host_pack(_ptr(b), b.size, _ptr(bits), _ptr(inv)))
+    return bits, inv
+
+
+def host_pack_isa() -> str:
+    return nv.lib().kmb_host_pack_isa().decode()
 
 
 def parse_fastx(text: bytes):

@@ -127,24 +127,29 @@ __device__ __forceinline__ uint32_t count_valid_windows(const uint2* tile, uint3
 // 2-bit packed input (the layout kmb_pack writes with Naive::ACGT and u64 words = SeqVector's words,
 // naive_impl/seq_vector.rs:230-242): the tile entries are the packed 32-bit words themselves.
 // A packed store cannot hold an invalid base, so the invalid masks are zero.
-__device__ __forceinline__ void stage_packed(const uint32_t* words, uint64_t n_words32, uint64_t first_word,
+// With `inv` (the flat packed staging format the host packer writes, kmb_hostpack.h): one 16-bit invalid mask per
+// word travels with the bits, so validation works as on ASCII input; words past the end read as invalid.
+__device__ __forceinline__ void stage_packed(const uint32_t* words, const uint16_t* inv, uint64_t n_words32, uint64_t first_word,
                                              uint32_t n_entries, const EncDesc& enc, uint2* tile) {
     for (uint32_t v = threadIdx.x; v < n_entries; v += blockDim.x) {
         const uint64_t i = first_word + v;
         uint32_t w = i < n_words32 ? __ldg(words + i) : 0u;
         // the store holds A0 C1 G2 T3; x ^ (x >> 1) per field is its own inverse and leads back to the internal code
         if (!enc.is_acgt) w = apply_encoding(w ^ ((w >> 1) & 0x55555555u), enc);
-        tile[v] = make_uint2(w, 0u);
+        uint32_t m = 0u;
+        if (inv) m = i < n_words32 ? (uint32_t)__ldg(inv + i) : 0xFFFFu;
+        tile[v] = make_uint2(w, m);
     }
 }
 
 // Stage the stretch that starts at flat base index g_start; returns the offset of that base inside tile entry 0.
 template <bool VALIDATE>
 __device__ __forceinline__ uint32_t stage_stretch(const uint8_t* bases, uint64_t n_bytes, uint32_t packed, uint64_t g_start,
-                                                  uint32_t span, uint32_t span_entries, const EncDesc& enc, uint2* tile) {
+                                                  uint32_t span, uint32_t span_entries, const EncDesc& enc, uint2* tile,
+                                                  const uint16_t* inv = nullptr) {
     if (packed) {
         const uint32_t mis = (uint32_t)(g_start & 15u);
-        stage_packed(reinterpret_cast<const uint32_t*>(bases), n_bytes >> 2, g_start >> 4, ((span + mis + 15) >> 4) + span_entries - 1, enc, tile);
+        stage_packed(reinterpret_cast<const uint32_t*>(bases), inv, n_bytes >> 2, g_start >> 4, ((span + mis + 15) >> 4) + span_entries - 1, enc, tile);
         return mis;
     }
     const uint8_t* first = bases + g_start;
@@ -167,7 +172,8 @@ struct FixedGeom {
     uint32_t W32;           // W (< 2^32, checked on the host)
     uint32_t w_magic;       // floor(2^32 / W) + 1
     uint32_t items_per_cta; // host-chosen so the staged stretch fits shared memory
-    uint32_t packed;        // bases = 2-bit packed words (SeqVector layout) instead of ASCII
+    uint32_t packed;        // 0: ASCII; 1: 2-bit packed words, SeqVector layout; 2: flat 2-bit stream + invalid masks (`inv`)
+    const uint16_t* inv;    // packed == 2: one 16-bit invalid mask per 32-bit word of `bases`
 };
 
 // u / W for a small u (u < W + slots per CTA): 0/1 when W is large, else multiply-high
@@ -294,7 +300,7 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     const uint32_t q_last = div_w(u_last, g, slots_per_cta);
     // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
     const uint32_t span = q_last * g.L32 + (u_last - q_last * g.W32) - p_first + K;
-    const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile);
+    const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile, g.inv);
     if constexpr (!Eng::kTwoPhase) deferred_reset();
     __syncthreads();
 

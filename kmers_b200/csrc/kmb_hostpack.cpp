@@ -1,0 +1,198 @@
+// kmb_hostpack.cpp -- see kmb_hostpack.h.  Compiled by g++ (no CUDA); the SIMD variants carry their own target
+// attributes and are selected at run time, so the object itself needs no -m flags.
+#include "kmb_hostpack.h"
+
+#include <immintrin.h>
+#include <sched.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace kmbhost {
+namespace {
+
+// ---------------------------------------------------------------- portable path
+// lut[c] = 2-bit code | invalid << 2.  code = x ^ (x >> 1) with x = (c >> 1) & 3: A0 C1 G2 T3 for the letters
+// (naive_impl/mod.rs:40-50), the Path-E field permuted the same way for every other byte (encoding/naive.rs:14-16).
+struct Lut {
+    uint8_t v[256];
+    Lut() {
+        for (int c = 0; c < 256; ++c) {
+            const unsigned x = ((unsigned)c >> 1) & 3u;
+            const unsigned u = (unsigned)c & 0xDFu;
+            const bool ok = u == 'A' || u == 'C' || u == 'G' || u == 'T';
+            v[c] = (uint8_t)((x ^ (x >> 1)) | (ok ? 0u : 4u));
+        }
+    }
+};
+const Lut g_lut;
+
+// one entry (<= 16 bases); bases that do not exist read as code 0 / invalid
+inline void pack_entry(const uint8_t* src, size_t n, uint32_t* bits, uint16_t* inv) {
+    uint32_t b = 0, m = n < 16 ? (0xFFFFu << n) & 0xFFFFu : 0u;
+    for (size_t j = 0; j < n; ++j) {
+        const unsigned t = g_lut.v[src[j]];
+        b |= (t & 3u) << (2 * j);
+        m |= (t >> 2) << j;
+    }
+    *bits = b;
+    *inv = (uint16_t)m;
+}
+
+void pack_swar(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
+    const size_t full = n_bases / 16;
+    for (size_t e = 0; e < full; ++e) pack_entry(src + 16 * e, 16, bits + e, inv + e);
+    if (n_bases % 16) pack_entry(src + 16 * full, n_bases % 16, bits + full, inv + full);
+}
+
+// ---------------------------------------------------------------- AVX2 + BMI2: 32 bases per iteration
+// bit 1 / bit 2 of every byte through movemask (a 16-bit lane shift brings them to bit 7 of their own byte), the two
+// bit planes interleaved by pdep; validity = the byte, case-folded, equals the letter its low nibble claims (pshufb LUT).
+__attribute__((target("avx2,bmi2"))) void pack_avx2(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
+    const __m256i table = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,
+                                           -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i m0f = _mm256_set1_epi8(0x0F), mdf = _mm256_set1_epi8((char)0xDF);
+    const size_t blocks = n_bases / 32;
+    for (size_t b = 0; b < blocks; ++b) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 32 * b));
+        const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
+        const uint32_t m2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
+        const uint64_t w = _pdep_u64(m1 ^ m2, 0x5555555555555555ull) | _pdep_u64(m2, 0xAAAAAAAAAAAAAAAAull);
+        const __m256i expect = _mm256_shuffle_epi8(table, _mm256_and_si256(v, m0f));
+        const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, _mm256_and_si256(v, mdf)));
+        std::memcpy(bits + 2 * b, &w, 8);
+        std::memcpy(inv + 2 * b, &bad, 4);
+    }
+    if (n_bases % 32) pack_swar(src + 32 * blocks, n_bases % 32, bits + 2 * blocks, inv + 2 * blocks);
+}
+
+// ---------------------------------------------------------------- AVX-512BW + BMI2: 64 bases per iteration
+__attribute__((target("avx512f,avx512bw,bmi2"))) void pack_avx512(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
+    const __m512i table = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
+    const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04);
+    const __m512i m0f = _mm512_set1_epi8(0x0F), mdf = _mm512_set1_epi8((char)0xDF);
+    const size_t blocks = n_bases / 64;
+    for (size_t b = 0; b < blocks; ++b) {
+        const __m512i v = _mm512_loadu_si512(src + 64 * b);
+        const uint64_t m1 = _mm512_test_epi8_mask(v, b1), m2 = _mm512_test_epi8_mask(v, b2);
+        const uint64_t lo = m1 ^ m2;
+        const uint64_t w0 = _pdep_u64(lo, 0x5555555555555555ull) | _pdep_u64(m2, 0xAAAAAAAAAAAAAAAAull);
+        const uint64_t w1 = _pdep_u64(lo >> 32, 0x5555555555555555ull) | _pdep_u64(m2 >> 32, 0xAAAAAAAAAAAAAAAAull);
+        const __m512i expect = _mm512_shuffle_epi8(table, _mm512_and_si512(v, m0f));
+        const uint64_t bad = ~(uint64_t)_mm512_cmpeq_epi8_mask(expect, _mm512_and_si512(v, mdf));
+        std::memcpy(bits + 4 * b, &w0, 8);
+        std::memcpy(bits + 4 * b + 2, &w1, 8);
+        std::memcpy(inv + 4 * b, &bad, 8);
+    }
+    if (n_bases % 64) pack_swar(src + 64 * blocks, n_bases % 64, bits + 4 * blocks, inv + 4 * blocks);
+}
+
+using PackFn = void (*)(const uint8_t*, size_t, uint32_t*, uint16_t*);
+struct Choice {
+    PackFn fn;
+    const char* name;
+};
+
+Choice choose(int which) {
+    __builtin_cpu_init();
+    const bool bmi2 = __builtin_cpu_supports("bmi2");
+    const bool avx2 = bmi2 && __builtin_cpu_supports("avx2");
+    const bool avx512 = bmi2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    if ((which == 0 || which == 3) && avx512) return {pack_avx512, "avx512bw"};
+    if ((which == 0 || which == 2 || which == 3) && avx2) return {pack_avx2, "avx2"};
+    return {pack_swar, "swar"};
+}
+std::atomic<int> g_forced{0};
+int env_isa() {  // KMB_HOST_PACK_ISA=swar|avx2|avx512bw caps the implementation (tests run every variant)
+    const char* e = getenv("KMB_HOST_PACK_ISA");
+    if (!e) return 0;
+    return !strcmp(e, "swar") ? 1 : (!strcmp(e, "avx2") ? 2 : (!strcmp(e, "avx512bw") ? 3 : 0));
+}
+Choice current() {
+    static const Choice best = choose(env_isa());
+    const int f = g_forced.load(std::memory_order_relaxed);
+    return f == 0 ? best : choose(f);
+}
+
+}  // namespace
+
+void pack_ascii(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
+    if (n_bases) current().fn(src, n_bases, bits, inv);
+}
+const char* pack_isa() { return current().name; }
+void pack_force_isa(int which) { g_forced.store(which < 0 || which > 3 ? 0 : which, std::memory_order_relaxed); }
+
+unsigned usable_cpus() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return (unsigned)n;
+    }
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? h : 1u;
+}
+
+// ---------------------------------------------------------------- worker pool
+struct Pool::Impl {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    std::vector<std::thread> threads;
+    bool stop = false;
+    void loop() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;  // stop requested and nothing left
+                job = std::move(q.front());
+                q.pop_front();
+            }
+            job();
+        }
+    }
+};
+
+Pool::Pool(unsigned n_threads) : impl_(new Impl) {
+    if (n_threads < 1) n_threads = 1;
+    impl_->threads.reserve(n_threads);
+    try {
+        for (unsigned i = 0; i < n_threads; ++i) impl_->threads.emplace_back([this] { impl_->loop(); });
+    } catch (...) {
+        // fewer threads than asked for is fine as long as there is one; with none, jobs run inline in submit()
+    }
+}
+
+Pool::~Pool() {
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv.notify_all();
+    for (auto& t : impl_->threads) t.join();
+    delete impl_;
+}
+
+unsigned Pool::size() const { return (unsigned)impl_->threads.size(); }
+
+void Pool::submit(std::function<void()> job) {
+    if (impl_->threads.empty()) {  // thread creation failed altogether
+        job();
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->q.push_back(std::move(job));
+    }
+    impl_->cv.notify_one();
+}
+
+}  // namespace kmbhost

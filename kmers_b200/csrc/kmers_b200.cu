@@ -21,77 +21,15 @@
 #include <cub/device/device_scan.cuh>
 
 #include "kmb_encoding.cuh"
+#include "kmb_internal.h"
 #include "kmb_launch.h"
 
 using namespace kmb;
 
-// ======================================================================= ctx
-struct kmb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;  // H2D / D2H leg of the pipelined host path
-    std::string err;
-    uint64_t launches = 0;
-
-    // resident batch
-    const uint8_t* d_bases = nullptr;
-    const uint64_t* d_offsets = nullptr;
-    uint8_t* own_bases = nullptr;
-    size_t own_bases_cap = 0;
-    uint64_t* own_offsets = nullptr;
-    size_t own_offsets_cap = 0;
-    uint64_t n_bytes = 0, n_reads = 0, fixed_len = 0;
-    bool have_batch = false;
-    // 2-bit packed batch (SeqVector layout): d_bases points at u64 words; reads start on word boundaries
-    bool packed = false;
-    uint64_t stride_len = 0;                  // fixed-length: bases between read starts (fixed_len padded to 32)
-    const uint64_t* d_base_starts = nullptr;  // ragged: flat (padded) base index of every read's first base, n_reads + 1
-    uint64_t n_bases_flat = 0;                // size of the flat base index space
-    uint64_t* own_packed = nullptr;
-    size_t own_packed_cap = 0;
-    uint64_t* own_base_starts = nullptr;
-    size_t own_base_starts_cap = 0;
-
-    // CSR window-offset cache (per k)
-    uint64_t* d_win_offsets = nullptr;
-    size_t win_cap = 0;
-    uint32_t win_k = 0;
-    uint64_t win_total = 0;
-    bool win_valid = false;
-
-    uint64_t* d_first_read = nullptr;  // per-CTA first read of the CSR kernels
-    size_t first_read_cap = 0;
-    unsigned long long* d_cta_counts = nullptr;  // compaction: valid windows per CTA / their scan
-    size_t cta_counts_cap = 0;
-    // a counting call (all outputs NULL) leaves its scan for the emit call that follows it (same k / flags, batch owned
-    // by the context so that nobody can have changed the bases in between); used once
-    bool compact_ready = false;
-    uint32_t compact_k = 0, compact_flags = 0;
-    unsigned compact_grid = 0;
-    uint64_t compact_total = 0;
-
-    // scratch
-    unsigned long long* d_digest = nullptr;  // 3 words
-    unsigned long long* h_digest = nullptr;  // pinned, 4 words
-    void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_cap[4] = {0, 0, 0, 0};
-    void* d_cub = nullptr;
-    size_t cub_cap = 0;
-    uint8_t* h_stage[2] = {nullptr, nullptr};
-    size_t stage_cap = 0;
-    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
-    // pipelined host path
-    uint8_t* pipe_in[2] = {nullptr, nullptr};
-    uint64_t* pipe_canon[2] = {nullptr, nullptr};
-    uint64_t* pipe_hash[2] = {nullptr, nullptr};
-    size_t pipe_in_cap = 0, pipe_out_cap = 0;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-};
-
+// ======================================================================= ctx (struct kmb_ctx: kmb_internal.h)
 static thread_local std::string g_err;
 
-static int32_t fail(kmb_ctx* ctx, int32_t code, const char* fmt, ...) {
+int32_t kmb_i_fail(kmb_ctx* ctx, int32_t code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -100,35 +38,24 @@ static int32_t fail(kmb_ctx* ctx, int32_t code, const char* fmt, ...) {
     if (ctx) ctx->err = buf; else g_err = buf;
     return code;
 }
+#define fail kmb_i_fail
 
-#define CK(ctx, call)                                                                              \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            cudaGetLastError();                                                                    \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMB_ERR_NOMEM : KMB_ERR_CUDA,       \
-                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-        }                                                                                          \
-    } while (0)
+int32_t kmb_i_bind(kmb_ctx* ctx) { CK(ctx, cudaSetDevice(ctx->device)); return KMB_OK; }
 
-#define NEED_CTX(ctx) \
-    do { if (!(ctx)) return fail(nullptr, KMB_ERR_INVALID_ARG, "ctx is NULL"); } while (0)
-
-static int32_t bind(kmb_ctx* ctx) { CK(ctx, cudaSetDevice(ctx->device)); return KMB_OK; }
-#define BIND(ctx) do { int32_t b_ = bind(ctx); if (b_ != KMB_OK) return b_; } while (0)
-
-static bool is_device_ptr(const void* p) {
+bool kmb_i_is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
-static bool is_pinned_ptr(const void* p) {
+bool kmb_i_is_pinned_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
+#define is_device_ptr kmb_i_is_device_ptr
+#define is_pinned_ptr kmb_i_is_pinned_ptr
 
-static int32_t grow(kmb_ctx* ctx, void** ptr, size_t* cap, size_t need) {
+int32_t kmb_i_grow(kmb_ctx* ctx, void** ptr, size_t* cap, size_t need) {
     if (*cap >= need && *ptr) return KMB_OK;
     if (*ptr) { CK(ctx, cudaStreamSynchronize(ctx->stream)); CK(ctx, cudaFree(*ptr)); *ptr = nullptr; *cap = 0; }
     size_t bytes = need + 256;
@@ -136,6 +63,7 @@ static int32_t grow(kmb_ctx* ctx, void** ptr, size_t* cap, size_t need) {
     *cap = need;
     return KMB_OK;
 }
+#define grow kmb_i_grow
 
 extern "C" int32_t kmb_version(void) { return KMB_VERSION; }
 
@@ -163,14 +91,10 @@ extern "C" int32_t kmb_ctx_create(int32_t device, void* cuda_stream, kmb_ctx** o
         if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
         else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
     }
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_digest, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_digest, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         int32_t rc = fail(nullptr, KMB_ERR_CUDA, "ctx creation failed: %s", cudaGetErrorString(e));
@@ -186,7 +110,7 @@ extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
     if (!ctx) return KMB_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    kmb_i_hostpipe_destroy(ctx);
     cudaFree(ctx->own_bases);
     cudaFree(ctx->own_offsets);
     cudaFree(ctx->own_packed);
@@ -200,13 +124,7 @@ extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
     cudaFree(ctx->d_cub);
     for (int i = 0; i < 2; ++i) {
         cudaFreeHost(ctx->h_stage[i]);
-        cudaFree(ctx->pipe_in[i]);
-        cudaFree(ctx->pipe_canon[i]);
-        cudaFree(ctx->pipe_hash[i]);
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
-        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
-        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
-        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
@@ -344,13 +262,19 @@ extern "C" int32_t kmb_batch_upload(kmb_ctx* ctx, const uint8_t* bases, uint64_t
     int32_t rc = check_shape(ctx, n_bytes, offsets != nullptr, n_reads, fixed_len);
     if (rc) return rc;
     if (n_bytes && !bases) return fail(ctx, KMB_ERR_INVALID_ARG, "bases is NULL");
+    if (offsets) {  // checked before any state changes: a bad table leaves the resident batch as it was
+        if (offsets[0] != 0 || offsets[n_reads] != n_bytes)
+            return fail(ctx, KMB_ERR_INVALID_ARG, "offsets must start at 0 and end at n_bytes");
+        for (uint64_t r = 0; r < n_reads; ++r)
+            if (offsets[r + 1] < offsets[r])
+                return fail(ctx, KMB_ERR_INVALID_ARG, "offsets must be ascending (offsets[%llu] > offsets[%llu])", (unsigned long long)r,
+                            (unsigned long long)(r + 1));
+    }
     drop_batch(ctx);
     if ((rc = grow(ctx, (void**)&ctx->own_bases, &ctx->own_bases_cap, n_bytes + 64))) return rc;
     if ((rc = stage_h2d(ctx, ctx->own_bases, bases, n_bytes))) return rc;
     ctx->d_bases = ctx->own_bases;
     if (offsets) {
-        if (offsets[0] != 0 || offsets[n_reads] != n_bytes)
-            return fail(ctx, KMB_ERR_INVALID_ARG, "offsets must start at 0 and end at n_bytes");
         if ((rc = grow(ctx, (void**)&ctx->own_offsets, &ctx->own_offsets_cap, (n_reads + 1) * 8))) return rc;
         if ((rc = stage_h2d(ctx, ctx->own_offsets, offsets, (n_reads + 1) * 8))) return rc;
         ctx->d_offsets = ctx->own_offsets;
@@ -358,6 +282,41 @@ extern "C" int32_t kmb_batch_upload(kmb_ctx* ctx, const uint8_t* bases, uint64_t
     ctx->n_bytes = n_bytes; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
     ctx->stride_len = ctx->fixed_len; ctx->n_bases_flat = ctx->n_bytes;
     ctx->have_batch = true;
+    return KMB_OK;
+}
+
+// borrowed CSR tables live in device memory: one cheap pass flags a table that is not ascending from 0 to `last`
+// (and, for packed batches, word offsets too small for their reads)
+__global__ void __launch_bounds__(256) check_offsets_kernel(const uint64_t* offsets, const uint64_t* word_offsets, uint64_t n_reads,
+                                                            uint64_t last, unsigned long long* bad) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    bool ok = true;
+    if (r == 0) ok = offsets[0] == 0 && (!word_offsets || word_offsets[0] == 0);
+    if (r == n_reads) ok = ok && offsets[r] == last;
+    if (r < n_reads) {
+        ok = ok && offsets[r + 1] >= offsets[r];
+        if (word_offsets && ok)
+            ok = word_offsets[r + 1] >= word_offsets[r] && (word_offsets[r + 1] - word_offsets[r]) >= (offsets[r + 1] - offsets[r] + 31) / 32;
+    }
+    if (!ok) atomicAdd(bad, 1ull);
+}
+
+static int32_t check_device_offsets(kmb_ctx* ctx, const uint64_t* d_offsets, const uint64_t* d_word_offsets, uint64_t n_reads, uint64_t last,
+                                    bool check_last) {
+    CK(ctx, cudaMemsetAsync(ctx->d_digest + 3, 0, 8, ctx->stream));
+    if (!check_last) {  // the last entry is whatever it is: read it back instead of comparing
+        CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        last = ctx->h_digest[3];
+    }
+    check_offsets_kernel<<<(unsigned)((n_reads + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_offsets, d_word_offsets, n_reads, last, ctx->d_digest + 3);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_digest + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_digest[3] != 0)
+        return fail(ctx, KMB_ERR_INVALID_ARG, "offsets must ascend from 0 to the batch size (%llu entries violate that)", ctx->h_digest[3]);
     return KMB_OK;
 }
 
@@ -369,6 +328,7 @@ extern "C" int32_t kmb_batch_attach(kmb_ctx* ctx, const uint8_t* dev_bases, uint
     if (rc) return rc;
     if (n_bytes && !is_device_ptr(dev_bases)) return fail(ctx, KMB_ERR_INVALID_ARG, "dev_bases is not device memory");
     if (dev_offsets && !is_device_ptr(dev_offsets)) return fail(ctx, KMB_ERR_INVALID_ARG, "dev_offsets is not device memory");
+    if (dev_offsets && (rc = check_device_offsets(ctx, dev_offsets, nullptr, n_reads, n_bytes, true))) return rc;
     drop_batch(ctx);
     ctx->d_bases = dev_bases; ctx->d_offsets = dev_offsets;
     ctx->n_bytes = n_bytes; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
@@ -516,11 +476,11 @@ static int32_t out_finish(kmb_ctx* ctx, const OutBuf& ob) {
     return KMB_OK;
 }
 
-static int32_t digest_begin(kmb_ctx* ctx) {
+int32_t kmb_i_digest_begin(kmb_ctx* ctx) {
     CK(ctx, cudaMemsetAsync(ctx->d_digest, 0, 3 * sizeof(unsigned long long), ctx->stream));
     return KMB_OK;
 }
-static int32_t digest_end(kmb_ctx* ctx, kmb_digest* digest) {
+int32_t kmb_i_digest_end(kmb_ctx* ctx, kmb_digest* digest) {
     CK(ctx, cudaMemcpyAsync(ctx->h_digest, ctx->d_digest, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     digest->n_valid = ctx->h_digest[0];
@@ -529,15 +489,18 @@ static int32_t digest_end(kmb_ctx* ctx, kmb_digest* digest) {
     return KMB_OK;
 }
 
+#define digest_begin kmb_i_digest_begin
+#define digest_end kmb_i_digest_end
+
 // ======================================================================= geometry (shared by both engines)
 static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
 
 // fixed-length reads: slot-space geometry of fixed_kernel
 static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
-                            uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, bool packed = false,
-                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 36 * 1024) {
+                            uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, uint32_t layout = KMB_I_ASCII,
+                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 36 * 1024, const uint16_t* d_inv = nullptr) {
     if (stride == 0) stride = L;
-    g->bases = d_bases; g->n_bytes = n_bytes; g->L = stride; g->L32 = (uint32_t)stride; g->packed = packed ? 1u : 0u;
+    g->bases = d_bases; g->n_bytes = n_bytes; g->L = stride; g->L32 = (uint32_t)stride; g->packed = layout; g->inv = d_inv;
     g->W = L - k + 1;
     if (g->W > 0xFFFF0000ull) return false;  // one read of > 4.29 Gbases: split it (window positions are 32-bit inside a CTA)
     g->W32 = (uint32_t)g->W;
@@ -604,19 +567,20 @@ static WinConst make_winconst(uint32_t k, const EncDesc& enc) {
 }
 
 // One extraction launch over (d_bases, fixed_len) -- or over the ctx's resident CSR batch when fixed_len == 0.
-static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint64_t n_bytes, uint64_t n_reads,
-                           uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* canon, uint64_t* hash, uint64_t* fw,
-                           uint64_t* rc, bool want_digest, unsigned long long* hist, uint32_t hist_bits, cudaStream_t st,
-                           uint64_t stride = 0, bool packed = false) {
+int32_t kmb_i_run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint64_t n_bytes, uint64_t n_reads,
+                          uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* canon, uint64_t* hash, uint64_t* fw,
+                          uint64_t* rc, bool want_digest, unsigned long long* hist, uint32_t hist_bits, cudaStream_t st,
+                          uint64_t stride, uint32_t layout, const uint16_t* d_inv, unsigned long long* d_digest) {
     EncDesc enc;
     make_enc(KMB_ENC_ACGT, &enc, nullptr);
-    const bool validate = !(flags & KMB_F_NO_VALIDATE) && !packed;  // a packed store holds no invalid base
+    // a SeqVector-packed store holds no invalid base; the flat packed staging format carries its invalid masks
+    const bool validate = !(flags & KMB_F_NO_VALIDATE) && layout != KMB_I_SEQVECTOR;
     const bool fwrc = fw || rc;
     const bool khi = k > 16;
     NarrowParams ep{};
     ep.wc = make_winconst(k, enc);
     ep.out.canon = canon; ep.out.hash = hash; ep.out.fw = fw; ep.out.rc = rc;
-    ep.out.digest = ctx->d_digest; ep.out.hist = hist; ep.out.hist_shift = 2 * k - hist_bits;
+    ep.out.digest = d_digest ? d_digest : ctx->d_digest; ep.out.hist = hist; ep.out.hist_shift = 2 * k - hist_bits;
     ep.out.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
     FixedGeom fg{};
     CsrGeom cg{};
@@ -625,8 +589,8 @@ static int32_t run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint6
     const bool big = hist && hist_bits <= 16 && !getenv("KMB_HIST_GLOBAL");
     if (!csr) {
         if (fixed_len < k || n_reads == 0) return KMB_OK;
-        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l, stride, packed, big ? kMaxItemsPerCta : kItemsPerCta,
-                             big ? 64 * 1024 : 36 * 1024))
+        if (!make_fixed_geom(d_bases, n_bytes, n_reads, fixed_len, k, 4, &fg, &l, stride, layout, big ? kMaxItemsPerCta : kItemsPerCta,
+                             big ? 64 * 1024 : 36 * 1024, d_inv))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else {
         if (n_bytes == 0 || n_reads == 0) return KMB_OK;
@@ -677,9 +641,9 @@ extern "C" int32_t kmb_extract_canonical(kmb_ctx* ctx, uint32_t k, uint32_t flag
         if ((rc = out_prepare(ctx, i, user[i], n_slots * 8, &ob[i]))) return rc;
     if (digest && (rc = digest_begin(ctx))) return rc;
     if (n_slots) {
-        rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags,
+        rc = kmb_i_run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags,
                          (uint64_t*)ob[0].dev, (uint64_t*)ob[1].dev, (uint64_t*)ob[2].dev, (uint64_t*)ob[3].dev,
-                         digest != nullptr, nullptr, 0, ctx->stream, ctx->stride_len, ctx->packed);
+                         digest != nullptr, nullptr, 0, ctx->stream, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII, nullptr);
         if (rc) return rc;
     }
     bool any_host = false;
@@ -697,15 +661,22 @@ extern "C" int32_t kmb_histogram(kmb_ctx* ctx, uint32_t k, uint32_t flags, uint3
     if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
     if (hist_bits < 1 || hist_bits > 2 * k || hist_bits > 28 || !hist_out)
         return fail(ctx, KMB_ERR_INVALID_ARG, "hist_bits must be in [1, min(2k, 28)] and hist_out non-NULL");
-    const size_t bytes = ((size_t)1 << hist_bits) * 8;
+    // KMB_F_DIGEST_IN_HIST: the three digest words are accumulated behind the bins (hist_out[n_bins .. n_bins + 2]) instead of
+    // being read back, so that [bins | digest] is ONE buffer the ranks all-reduce in place, and the call stays asynchronous
+    const bool tail = (flags & KMB_F_DIGEST_IN_HIST) != 0;
+    if (tail && digest) return fail(ctx, KMB_ERR_INVALID_ARG, "KMB_F_DIGEST_IN_HIST: the digest goes to hist_out, pass digest = NULL");
+    const size_t n_bins = (size_t)1 << hist_bits;
+    const size_t bytes = (n_bins + (tail ? 3 : 0)) * 8;
     OutBuf ob;
     int32_t rc = out_prepare(ctx, 0, hist_out, bytes, &ob);
     if (rc) return rc;
     if (ob.host && accumulate) CK(ctx, cudaMemcpyAsync(ob.dev, hist_out, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (!accumulate) CK(ctx, cudaMemsetAsync(ob.dev, 0, bytes, ctx->stream));
     if (digest && (rc = digest_begin(ctx))) return rc;
-    rc = run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags, nullptr,
-                     nullptr, nullptr, nullptr, digest != nullptr, (unsigned long long*)ob.dev, hist_bits, ctx->stream, ctx->stride_len, ctx->packed);
+    rc = kmb_i_run_extract(ctx, ctx->d_bases, ctx->d_offsets != nullptr, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, flags, nullptr,
+                           nullptr, nullptr, nullptr, digest != nullptr || tail, (unsigned long long*)ob.dev, hist_bits, ctx->stream,
+                           ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII, nullptr,
+                           tail ? (unsigned long long*)ob.dev + n_bins : nullptr);
     if (rc) return rc;
     if ((rc = out_finish(ctx, ob))) return rc;
     if (digest) return digest_end(ctx, digest);
@@ -742,7 +713,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     CsrGeom cg{};
     Launch l;
     if (!csr) {
-        if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed))
+        if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
         return rc;
@@ -756,7 +727,8 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     const bool counting_call = !canon_out && !hash_out && !pos_out && !emit_offsets_out;
     const bool owned = ctx->d_bases == ctx->own_bases || ctx->d_bases == (const uint8_t*)ctx->own_packed;
     uint64_t total;
-    if (!counting_call && ctx->compact_ready && ctx->compact_k == k && ctx->compact_flags == flags && ctx->compact_grid == l.grid) {
+    if (!counting_call && ctx->compact_ready && ctx->compact_k == k && ctx->compact_flags == flags && ctx->compact_grid == l.grid &&
+        ctx->compact_packed == ctx->packed) {
         total = ctx->compact_total;  // the counting call just before this one already left the scan in d_cta_counts
     } else {
         CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 1) * 8, ctx->stream));
@@ -777,6 +749,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     if (counting_call) {
         if (owned) {
             ctx->compact_ready = true; ctx->compact_k = k; ctx->compact_flags = flags; ctx->compact_grid = l.grid; ctx->compact_total = total;
+            ctx->compact_packed = ctx->packed;
         }
         return KMB_OK;
     }
@@ -841,7 +814,7 @@ extern "C" int32_t kmb_minimizers(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t
         Launch l;
         const bool csr = ctx->d_offsets != nullptr, validate = !(flags & KMB_F_NO_VALIDATE) && !ctx->packed;
         if (!csr) {
-            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed))
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
         } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
             return rc;
@@ -912,7 +885,7 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
         Launch l;
         const bool csr = ctx->d_offsets != nullptr;
         if (!csr) {
-            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, nw32 + 2, &fg, &l, ctx->stride_len, ctx->packed))
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, nw32 + 2, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
         } else if ((rc = make_csr_geom(ctx, k, nw32 + 2, &cg, &l))) {
             return rc;
@@ -927,87 +900,6 @@ extern "C" int32_t kmb_extract_canonical_wide(kmb_ctx* ctx, uint32_t k, int32_t 
     if ((rc = out_finish(ctx, oh))) return rc;
     if (digest) return digest_end(ctx, digest);
     if (oc.host || oh.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return KMB_OK;
-}
-
-// ======================================================================= pipelined host path
-// Chunks of reads: H2D on the copy stream, kernel on the compute stream, D2H
-// (when host outputs are wanted) back on the copy stream; two buffers in flight.
-extern "C" int32_t kmb_extract_canonical_host(kmb_ctx* ctx, const uint8_t* host_bases, uint64_t n_reads,
-                                              uint64_t fixed_len, uint32_t k, uint32_t flags, uint64_t* host_canon,
-                                              uint64_t* host_hash, kmb_digest* digest) {
-    NEED_CTX(ctx);
-    BIND(ctx);
-    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
-    if (fixed_len == 0) return fail(ctx, KMB_ERR_INVALID_ARG, "fixed_len must be > 0");
-    if (n_reads && !host_bases) return fail(ctx, KMB_ERR_INVALID_ARG, "host_bases is NULL");
-    int32_t rc;
-    if (digest && (rc = digest_begin(ctx))) return rc;
-    const uint64_t W = fixed_len >= k ? fixed_len - k + 1 : 0;
-    if (W && n_reads) {
-        // chunk ~64 MiB of output per array so both directions stay busy
-        uint64_t reads_per_chunk = ((uint64_t)64 << 20) / (W * 8);
-        if (reads_per_chunk < 1) reads_per_chunk = 1;
-        // keep chunk slot starts 32-byte aligned for the vector stores
-        reads_per_chunk = (reads_per_chunk + 3) & ~3ull;
-        if (reads_per_chunk > n_reads) reads_per_chunk = n_reads;
-        const size_t in_cap = reads_per_chunk * fixed_len, out_cap = reads_per_chunk * W * 8;
-        const bool want_out = host_canon || host_hash;
-        const bool pinned_in = is_pinned_ptr(host_bases);
-        for (int i = 0; i < 2; ++i) {
-            size_t c0 = ctx->pipe_in_cap, c1 = ctx->pipe_out_cap, c2 = ctx->pipe_out_cap;
-            if ((rc = grow(ctx, (void**)&ctx->pipe_in[i], &c0, in_cap + 64))) return rc;
-            if ((rc = grow(ctx, (void**)&ctx->pipe_canon[i], &c1, out_cap))) return rc;
-            if ((rc = grow(ctx, (void**)&ctx->pipe_hash[i], &c2, out_cap))) return rc;
-            if (i == 1) { ctx->pipe_in_cap = c0; ctx->pipe_out_cap = c1; }
-        }
-        if (!pinned_in && ctx->stage_cap < in_cap) {
-            for (int i = 0; i < 2; ++i) {
-                if (ctx->h_stage[i]) { CK(ctx, cudaFreeHost(ctx->h_stage[i])); ctx->h_stage[i] = nullptr; }
-                CK(ctx, cudaHostAlloc((void**)&ctx->h_stage[i], in_cap, cudaHostAllocDefault));
-            }
-            ctx->stage_cap = in_cap;
-        }
-        // compute stream must not overtake earlier work queued on it by the caller
-        CK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
-        CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[0], 0));
-        uint64_t done = 0;
-        int buf = 0;
-        uint64_t chunk_idx = 0;
-        while (done < n_reads) {
-            const uint64_t nr = n_reads - done < reads_per_chunk ? n_reads - done : reads_per_chunk;
-            const size_t in_bytes = nr * fixed_len, out_bytes = nr * W * 8;
-            if (chunk_idx >= 2) {
-                // buffer reuse: its kernel (reads pipe_in) and its D2H (reads pipe_out) must be done
-                CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[buf], 0));
-                if (!pinned_in) CK(ctx, cudaEventSynchronize(ctx->ev_in[buf]));
-            }
-            const uint8_t* src = host_bases + done * fixed_len;
-            if (!pinned_in) { memcpy(ctx->h_stage[buf], src, in_bytes); src = ctx->h_stage[buf]; }
-            CK(ctx, cudaMemcpyAsync(ctx->pipe_in[buf], src, in_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CK(ctx, cudaEventRecord(ctx->ev_in[buf], ctx->copy_stream));
-            CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
-            if (chunk_idx >= 2 && want_out) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[buf], 0));
-            rc = run_extract(ctx, ctx->pipe_in[buf], false, in_bytes, nr, fixed_len, k, flags, ctx->pipe_canon[buf],
-                             ctx->pipe_hash[buf], nullptr, nullptr, digest != nullptr, nullptr, 0, ctx->stream);
-            if (rc) return rc;
-            CK(ctx, cudaEventRecord(ctx->ev_k[buf], ctx->stream));
-            if (want_out) {
-                CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k[buf], 0));
-                if (host_canon)
-                    CK(ctx, cudaMemcpyAsync(host_canon + done * W, ctx->pipe_canon[buf], out_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                if (host_hash)
-                    CK(ctx, cudaMemcpyAsync(host_hash + done * W, ctx->pipe_hash[buf], out_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                CK(ctx, cudaEventRecord(ctx->ev_out[buf], ctx->copy_stream));
-            }
-            done += nr;
-            buf ^= 1;
-            ++chunk_idx;
-        }
-        CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    }
-    if (digest) return digest_end(ctx, digest);
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return KMB_OK;
 }
 
@@ -1028,7 +920,7 @@ __global__ void __launch_bounds__(256) packed_get_kmers_kernel(const uint64_t* w
     uint64_t v = ~0ull;
     if (r < n_reads) {
         const uint64_t len = offsets ? offsets[r + 1] - offsets[r] : fixed_len;
-        if (p + k <= len) {
+        if (p <= len && k <= len - p) {  // p + k <= len without the wrap-around of a huge p
             const uint64_t bit = ((base_starts ? base_starts[r] : r * stride) + p) * 2;
             const uint64_t wi = bit >> 6, sh = bit & 63;
             v = words[wi] >> sh;
@@ -1049,6 +941,9 @@ static int32_t set_packed(kmb_ctx* ctx, const uint64_t* d_words, uint64_t n_word
         ctx->launches++;
         ctx->d_base_starts = ctx->own_base_starts;
     }
+    // the batch changes representation: cached per-CTA compaction counts (taken with validation on the ASCII bytes) and the
+    // window-offset geometry they belong to no longer describe it
+    ctx->compact_ready = false;
     ctx->d_bases = (const uint8_t*)d_words;
     ctx->n_bytes = n_words * 8;
     ctx->n_bases_flat = n_words * 32;
@@ -1091,6 +986,12 @@ extern "C" int32_t kmb_batch_attach_packed(kmb_ctx* ctx, const uint64_t* dev_wor
     if ((dev_offsets != nullptr) != (dev_word_offsets != nullptr)) return fail(ctx, KMB_ERR_INVALID_ARG, "ragged packed batches need offsets and word_offsets");
     if (n_words && !is_device_ptr(dev_words)) return fail(ctx, KMB_ERR_INVALID_ARG, "dev_words is not device memory");
     if (!dev_offsets && n_reads * ((fixed_len + 31) / 32) != n_words) return fail(ctx, KMB_ERR_INVALID_ARG, "n_words != n_reads * ceil(fixed_len / 32)");
+    if (dev_offsets) {
+        if (!is_device_ptr(dev_offsets) || !is_device_ptr(dev_word_offsets)) return fail(ctx, KMB_ERR_INVALID_ARG, "offsets are not device memory");
+        int32_t rc = check_device_offsets(ctx, dev_word_offsets, nullptr, n_reads, n_words, true);  // word offsets: 0 .. n_words
+        if (rc == KMB_OK) rc = check_device_offsets(ctx, dev_offsets, dev_word_offsets, n_reads, 0, false);
+        if (rc) return rc;
+    }
     drop_batch(ctx);
     ctx->d_offsets = dev_offsets; ctx->n_reads = n_reads; ctx->fixed_len = fixed_len;
     ctx->have_batch = true;
@@ -1316,10 +1217,19 @@ const char* parse_fastx_parallel(const char* text, uint64_t n, FastxSink& out, u
     if (nc < 2) return parse_fastx(text, n, out);
     std::vector<FastxSink> part(nc, FastxSink{nullptr, nullptr, 0, 0});
     std::vector<const char*> err(nc, nullptr);
+    // A std::thread constructor can throw (std::system_error) after others have started: whatever happens, every started
+    // thread is joined before the vector goes away (a joinable thread's destructor would call std::terminate); the chunks
+    // whose thread never started run here.
     auto run = [&](auto&& fn) {
         std::vector<std::thread> th;
-        for (size_t c = 1; c < nc; ++c) th.emplace_back(fn, c);
+        th.reserve(nc);
+        size_t started = 1;
+        try {
+            for (; started < nc; ++started) th.emplace_back(fn, started);
+        } catch (...) {
+        }
         fn(0);
+        for (size_t c = started; c < nc; ++c) fn(c);
         for (auto& t : th) t.join();
     };
     run([&](size_t c) { err[c] = parse_fastx(cut[c], (uint64_t)(cut[c + 1] - cut[c]), part[c]); });
@@ -1348,7 +1258,14 @@ extern "C" int32_t kmb_parse_fastx(const char* text, uint64_t n_bytes, uint8_t* 
     // one thread per ~4 MiB of text, at most the hardware's; KMB_PARSE_THREADS overrides (tests)
     unsigned n_threads = (unsigned)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), n_bytes >> 22);
     if (const char* env = getenv("KMB_PARSE_THREADS")) n_threads = (unsigned)atoi(env);
-    const char* err = parse_fastx_parallel(text, n_bytes, sink, std::min(n_threads, 64u));
+    const char* err = nullptr;
+    try {  // nothing may unwind across the C ABI (std::bad_alloc from the bookkeeping vectors)
+        err = parse_fastx_parallel(text, n_bytes, sink, std::min(n_threads, 64u));
+    } catch (const std::bad_alloc&) {
+        return fail(nullptr, KMB_ERR_NOMEM, "out of host memory while parsing");
+    } catch (...) {
+        return fail(nullptr, KMB_ERR_INVALID_ARG, "unexpected failure while parsing");
+    }
     if (err) return fail(nullptr, KMB_ERR_INVALID_ARG, "%s", err);
     if (n_reads) *n_reads = sink.n_reads;
     if (n_bases) *n_bases = sink.n_bases;

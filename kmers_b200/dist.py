@@ -65,6 +65,19 @@ def sharded_histogram(ctx, seed: int, n_bases: int, k: int, hist_bits: int, rank
     return g_hist, g_digest, max(0, n - k + 1)
 
 
+def sharded_histogram_fused(ctx, batch, k: int, hist_bits: int, buf, group=None):
+    """One timed step of config 5 on this rank: the fused histogram kernel accumulates [bins | n_valid | checksum_canon |
+    checksum_hash] into `buf` (int64 CUDA tensor of 2^hist_bits + 3 words, zeroed by the call), then ONE in-place
+    all-reduce sums it over the ranks -- nothing is read back to the host in between ("the histogram kernel
+    writes straight into the send buffer, in-place all-reduce on the same stream").  Returns buf."""
+    import torch.distributed as dist
+
+    batch.histogram(k, hist_bits, hist=buf, accumulate=False, digest_in_hist=True)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
 def allreduce_single_process(ctxs, bufs):
     """The same reduction for ONE process that drives several GPUs (the shape a Rust host has): in-place wrapping-u64
     sum of the int64 CUDA tensors `bufs[i]` (one per context / GPU) through the C ABI's kmb_allreduce_u64 (NCCL)."""

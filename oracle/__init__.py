@@ -17,7 +17,31 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libkmers_oracle.so")
+_SO = os.path.join(_HERE, "libkmers_oracle.so")  # portable build (-march=x86-64-v2): travels to any box
+
+
+def use_native_build() -> str:
+    """Switch this process to a `-O3 -march=native` build of the oracle, compiled ON THE MACHINE THAT RUNS IT (the
+    shipped library is built portable because it travels to another host).  Used by bench.py's CPU legs so that the
+    reported CPU baseline is not handicapped.  Must be called before the first `lib()`.  Returns the
+    flags in effect ("-march=native", or the portable ones if the native build is not possible here)."""
+    global _SO
+    import hashlib
+    assert _lib is None, "use_native_build() must come before the first oracle call"
+    try:
+        with open("/proc/cpuinfo") as f:
+            ident = "".join(l for l in f if l.startswith(("model name", "flags")))[:20000]
+        tag = hashlib.sha1(ident.encode()).hexdigest()[:10]
+        so = os.path.join(_HERE, f"libkmers_oracle_native_{tag}.so")
+        src, hdr = os.path.join(_HERE, "kmers_oracle.c"), os.path.join(_HERE, "kmers_oracle.h")
+        if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr)):
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-fno-semantic-interposition", "-std=c11", "-pthread",
+                                   "-shared", "-o", so + ".tmp", src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            os.replace(so + ".tmp", so)
+        _SO = so
+        return "-O3 -march=native (built on this host)"
+    except Exception:
+        return "-O3 -march=x86-64-v2 (portable build; native build failed here)"
 
 OK = 0
 PANIC = -1
@@ -74,7 +98,8 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    build()
+    if _SO.endswith("libkmers_oracle.so"):
+        build()
     L = C.CDLL(_SO)
     u8, u64, sz, i32, u32 = C.c_uint8, C.c_uint64, C.c_size_t, C.c_int, C.c_uint
     P = C.POINTER
@@ -137,6 +162,7 @@ def lib() -> C.CDLL:
     sig("ko_extract_canonical", i32, vp, vp, sz, u64, u32, i32, vp, vp, vp, vp, vp, u32, P(Digest), i32)
     sig("ko_bench_windows", i32, vp, vp, sz, u64, u32, vp, vp, P(Digest), i32)
     sig("ko_extract_canonical_wide", i32, vp, vp, sz, u64, u32, i32, i32, vp, vp, P(Digest))
+    sig("ko_extract_canonical_wide_mt", i32, vp, vp, sz, u64, u32, i32, i32, vp, vp, P(Digest), i32)
     sig("ko_minimizer_word", i32, u64, sz, sz, u32, i32, P(u64), P(sz))
     sig("ko_sv_from_bytes", i32, vp, sz, vp)
     sig("ko_sv_get_kmer_u64", i32, vp, sz, sz, sz, P(u64))
@@ -306,7 +332,7 @@ def bench_windows(bases: np.ndarray, k: int, *, offsets=None, n_reads=None, fixe
 
 
 def extract_canonical_wide(bases: np.ndarray, k: int, *, enc=NAIVE["ACGT"], validate=True, offsets=None,
-                           n_reads=None, fixed_len=0, want_hash=True):
+                           n_reads=None, fixed_len=0, want_hash=True, n_threads=1):
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     o, op = _offs_ptr(offsets)
     if o is not None:
@@ -315,9 +341,9 @@ def extract_canonical_wide(bases: np.ndarray, k: int, *, enc=NAIVE["ACGT"], vali
     canon = np.empty(2 * n_slots, dtype=np.uint64)
     hsh = np.empty(2 * n_slots, dtype=np.uint64) if want_hash else None
     d = Digest()
-    st = lib().ko_extract_canonical_wide(bases.ctypes.data, op, n_reads, fixed_len, k, enc, int(validate),
-                                         canon.ctypes.data, hsh.ctypes.data if want_hash else None,
-                                         C.byref(d))
+    st = lib().ko_extract_canonical_wide_mt(bases.ctypes.data, op, n_reads, fixed_len, k, enc, int(validate),
+                                            canon.ctypes.data, hsh.ctypes.data if want_hash else None,
+                                            C.byref(d), n_threads)
     if st != OK:
         raise RuntimeError("panic: extract_canonical_wide")
     return dict(canon=canon.reshape(-1, 2), hash=hsh.reshape(-1, 2) if want_hash else None,

@@ -713,6 +713,64 @@ int ko_extract_canonical_wide(const uint8_t *bases, const uint64_t *offsets, siz
     return KO_OK;
 }
 
+/* the same over n_threads threads: reads are cut into contiguous ranges, every range runs the function above
+ * on its own slice of the outputs (test infrastructure: gives config 3 a CPU figure on all cores) */
+typedef struct {
+    const uint8_t *bases; const uint64_t *offsets; size_t r0, r1; uint64_t fixed_len; unsigned k; int enc, validate;
+    uint64_t *canon_out, *hash_out; uint64_t slot0; ko_digest d; int status;
+} wide_job_t;
+
+static void *wide_job_main(void *arg) {
+    wide_job_t *jb = (wide_job_t *)arg;
+    /* a range of a CSR batch is a CSR batch again once its offsets are rebased; fixed-length ranges just shift */
+    const size_t n = jb->r1 - jb->r0;
+    uint64_t *canon = jb->canon_out ? jb->canon_out + 2 * jb->slot0 : NULL;
+    uint64_t *hash = jb->hash_out ? jb->hash_out + 2 * jb->slot0 : NULL;
+    if (!jb->offsets) {
+        jb->status = ko_extract_canonical_wide(jb->bases + jb->r0 * jb->fixed_len, NULL, n, jb->fixed_len, jb->k, jb->enc,
+                                               jb->validate, canon, hash, &jb->d);
+        return NULL;
+    }
+    uint64_t *offs = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    if (!offs) { jb->status = KO_PANIC; return NULL; }
+    for (size_t i = 0; i <= n; ++i) offs[i] = jb->offsets[jb->r0 + i] - jb->offsets[jb->r0];
+    jb->status = ko_extract_canonical_wide(jb->bases + jb->offsets[jb->r0], offs, n, 0, jb->k, jb->enc, jb->validate, canon, hash, &jb->d);
+    free(offs);
+    return NULL;
+}
+
+int ko_extract_canonical_wide_mt(const uint8_t *bases, const uint64_t *offsets, size_t n_reads, uint64_t fixed_len, unsigned k,
+                                 int enc, int validate, uint64_t *canon_out, uint64_t *hash_out, ko_digest *digest, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if ((size_t)n_threads > n_reads) n_threads = n_reads ? (int)n_reads : 1;
+    if (n_threads == 1) return ko_extract_canonical_wide(bases, offsets, n_reads, fixed_len, k, enc, validate, canon_out, hash_out, digest);
+    wide_job_t *jobs = (wide_job_t *)calloc((size_t)n_threads, sizeof(wide_job_t));
+    pthread_t *tids = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    if (!jobs || !tids) { free(jobs); free(tids); return KO_PANIC; }
+    uint64_t slot = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        wide_job_t *jb = &jobs[t];
+        jb->bases = bases; jb->offsets = offsets; jb->fixed_len = fixed_len; jb->k = k; jb->enc = enc; jb->validate = validate;
+        jb->canon_out = canon_out; jb->hash_out = hash_out;
+        jb->r0 = n_reads * (size_t)t / (size_t)n_threads;
+        jb->r1 = n_reads * (size_t)(t + 1) / (size_t)n_threads;
+        jb->slot0 = slot;
+        for (size_t r = jb->r0; r < jb->r1; ++r) slot += n_windows(read_begin(offsets, fixed_len, r + 1) - read_begin(offsets, fixed_len, r), k);
+    }
+    for (int t = 0; t < n_threads; ++t) pthread_create(&tids[t], NULL, wide_job_main, &jobs[t]);
+    for (int t = 0; t < n_threads; ++t) pthread_join(tids[t], NULL);
+    ko_digest d = {0, 0, 0};
+    int status = KO_OK;
+    for (int t = 0; t < n_threads; ++t) {
+        if (jobs[t].status != KO_OK) status = jobs[t].status;
+        d.n_valid += jobs[t].d.n_valid; d.checksum_canon += jobs[t].d.checksum_canon; d.checksum_hash += jobs[t].d.checksum_hash;
+    }
+    free(jobs);
+    free(tids);
+    if (digest) *digest = d;
+    return status;
+}
+
 /* ======================================================================= */
 /* "next" rows: minimizers + SeqVector                                      */
 /* ======================================================================= */

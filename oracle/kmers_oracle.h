@@ -229,6 +229,9 @@ int ko_extract_canonical_wide(const uint8_t *bases, const uint64_t *offsets, siz
                               uint64_t *canon_out /* 2 words per slot */,
                               uint64_t *hash_out /* 2 words per slot, may be NULL */,
                               ko_digest *digest);
+/* the same on n_threads threads (reads cut into contiguous ranges) */
+int ko_extract_canonical_wide_mt(const uint8_t *bases, const uint64_t *offsets, size_t n_reads, uint64_t fixed_len, unsigned k,
+                                 int enc, int validate, uint64_t *canon_out, uint64_t *hash_out, ko_digest *digest, int n_threads);
 
 /* ---------------- "next" rows: minimizers + packed sequence store ---------------- */
 

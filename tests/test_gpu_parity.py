@@ -228,16 +228,142 @@ def test_single_sequence_sharded_with_halo(ctx, ko):
 
 
 # ------------------------------------------------------------------ pipelined host path
+def _host_case(ko, n, L, k, thresh=300):
+    bases = ko.generate_bases(42, 0, n * L, n_thresh20=thresh)
+    ref = ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, n_threads=8)
+    return bases, ref, (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+
+
+def _ref_any(ko, bases, k, n, L, validate):
+    """Oracle result with or without validation (Path-E bytes go through the restated Encoding::encode, single-threaded)."""
+    if validate:
+        return ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, n_threads=8)
+    r = ko.extract_canonical_wide(bases, k, enc=ko.NAIVE["ACGT"], validate=False, n_reads=n, fixed_len=L)
+    return dict(r, canon=r["canon"][:, 0].copy(), hash=r["hash"][:, 0].copy())
+
+
 def test_extract_canonical_host_pipelined(ctx, ko):
-    n, L, k = 150_000, 150, 31  # several 64 MiB chunks
-    bases = ko.generate_bases(42, 0, n * L, n_thresh20=300)
+    n, L, k = 150_000, 150, 31  # several chunks
+    bases, ref, rdig = _host_case(ko, n, L, k)
     canon = np.empty(n * (L - k + 1), dtype=np.uint64)
     hsh = np.empty_like(canon)
     dig = ctx.extract_canonical_host(bases, n, L, k, host_canon=canon, host_hash=hsh)
-    ref = ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, n_threads=8)
     assert np.array_equal(canon, ref["canon"]) and np.array_equal(hsh, ref["hash"])
-    assert dig == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+    assert dig == rdig
     assert ctx.extract_canonical_host(bases, n, L, k) == dig  # digest-only form
+    st = ctx.host_stats()
+    assert st["chunks"] >= 1 and st["raw_chunks"] == 0 and st["d2h_bytes"] == 0  # pageable input: every chunk is packed
+    assert st["h2d_bytes"] < 0.45 * n * L  # 3 bits per base (+ padding) crossed the link, not 8
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("chunk_mb", [1, 16])
+def test_host_pipeline_device_outputs_stay_resident(ctx, ko, monkeypatch, pinned, chunk_mb):
+    """Device-output mode: the kernels write the caller's full-batch device arrays in place (nothing is overwritten by a
+    later chunk), for pageable input (all chunks packed by the host workers) and pinned input (packed from the front,
+    raw ASCII from the back), with one and with many chunks."""
+    import torch
+    monkeypatch.setenv("KMB_PIPE_CHUNK_MB", str(chunk_mb))
+    n, L, k = 120_001, 150, 31
+    bases, ref, rdig = _host_case(ko, n, L, k)
+    src = bases
+    if pinned:
+        t = torch.empty(n * L, dtype=torch.uint8, pin_memory=True)
+        src = t.numpy()
+        src[:] = bases
+    W = L - k + 1
+    canon = torch.full((n * W,), -7, dtype=torch.int64, device="cuda")
+    hsh = torch.full((n * W,), -7, dtype=torch.int64, device="cuda")
+    dig = ctx.extract_canonical_host(src, n, L, k, out_canon=canon, out_hash=hsh)
+    assert dig == rdig
+    assert np.array_equal(canon.cpu().numpy().view(np.uint64), ref["canon"])
+    assert np.array_equal(hsh.cpu().numpy().view(np.uint64), ref["hash"])
+    st = ctx.host_stats()
+    assert st["chunks"] == -(-n // max(16, ((chunk_mb << 20) // L) // 16 * 16))
+    if not pinned:
+        assert st["raw_chunks"] == 0
+    # mixed: canonical words stay on the device, hashes come back to the host; and canonical words only
+    canon.fill_(-7)
+    h_host = np.empty(n * W, dtype=np.uint64)
+    assert ctx.extract_canonical_host(src, n, L, k, out_canon=canon, out_hash=h_host) == rdig
+    assert np.array_equal(canon.cpu().numpy().view(np.uint64), ref["canon"]) and np.array_equal(h_host, ref["hash"])
+    canon.fill_(-7)
+    assert ctx.extract_canonical_host(src, n, L, k, out_canon=canon) == rdig
+    assert np.array_equal(canon.cpu().numpy().view(np.uint64), ref["canon"])
+
+
+@pytest.mark.parametrize("mode", ["pack_only", "raw_only"])
+def test_host_pipeline_single_paths(ctx, ko, monkeypatch, mode):
+    """The two feeds on their own (the hybrid of the default run is any mixture of them): packed chunks only, raw ASCII only."""
+    import torch
+    monkeypatch.setenv("KMB_PIPE_CHUNK_MB", "1")
+    monkeypatch.setenv("KMB_PIPE_RAW" if mode == "pack_only" else "KMB_PIPE_PACK", "0")
+    n, L, k = 40_000, 150, 31
+    bases, ref, rdig = _host_case(ko, n, L, k, thresh=2000)
+    t = torch.empty(n * L, dtype=torch.uint8, pin_memory=True)
+    t.numpy()[:] = bases
+    canon = np.empty(n * (L - k + 1), dtype=np.uint64)
+    hsh = np.empty_like(canon)
+    assert ctx.extract_canonical_host(t.numpy(), n, L, k, out_canon=canon, out_hash=hsh) == rdig
+    assert np.array_equal(canon, ref["canon"]) and np.array_equal(hsh, ref["hash"])
+    st = ctx.host_stats()
+    assert st["raw_chunks"] == (0 if mode == "pack_only" else st["chunks"])
+    assert st["d2h_bytes"] == 2 * 8 * n * (L - k + 1)
+
+
+@pytest.mark.parametrize("L,k,n", [(150, 31, 1), (150, 31, 17), (31, 31, 1000), (37, 5, 3333), (1000, 32, 257), (10_000, 31, 50), (20, 31, 10)])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_pipeline_geometries(ctx, ko, monkeypatch, L, k, n, threads):
+    """Odd shapes through the packed staging format: chunks that end inside a 16-base word, reads shorter than k (no
+    windows at all), one read, long reads; soft-masked and IUPAC bytes; NO_VALIDATE (Path-E bytes through the host packer)."""
+    monkeypatch.setenv("KMB_PIPE_CHUNK_MB", "1")
+    ctx.set_host_threads(threads)
+    try:
+        rng = np.random.default_rng(L * 7 + k)
+        bases, _ = random_reads(rng, n, L, L, p_bad=0.01)
+        for validate in (True, False):
+            ref = _ref_any(ko, bases, k, n, L, validate)
+            W = max(0, L - k + 1)
+            canon = np.empty(n * W, dtype=np.uint64)
+            hsh = np.empty_like(canon)
+            dig = ctx.extract_canonical_host(bases, n, L, k, out_canon=canon, out_hash=hsh, validate=validate)
+            assert dig == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+            assert np.array_equal(canon, ref["canon"]) and np.array_equal(hsh, ref["hash"])
+    finally:
+        ctx.set_host_threads(0)
+
+
+def test_host_pipeline_prepacked_input(ctx, ko, monkeypatch):
+    """Reads the caller packed once with kmb_host_pack: bits + masks, and bits alone (SeqVector semantics: no invalid base)."""
+    import kmers_b200 as kb
+    monkeypatch.setenv("KMB_PIPE_CHUNK_MB", "1")
+    n, L, k = 20_000, 150, 31
+    bases, ref, rdig = _host_case(ko, n, L, k, thresh=1000)
+    bits, inv = kb.host_pack(bases)
+    canon = np.empty(n * (L - k + 1), dtype=np.uint64)
+    hsh = np.empty_like(canon)
+    assert ctx.extract_canonical_host_packed(bits, inv, n, L, k, out_canon=canon, out_hash=hsh) == rdig
+    assert np.array_equal(canon, ref["canon"]) and np.array_equal(hsh, ref["hash"])
+    st = ctx.host_stats()
+    assert st["h2d_bytes"] == 6 * ((n * L + 15) // 16) or st["h2d_bytes"] <= 6 * ((n * L + 15) // 16) + 6 * st["chunks"]
+    # without masks every window is emitted, bytes mapping by (c >> 1) & 3: the NO_VALIDATE result
+    ref_nv = _ref_any(ko, bases, k, n, L, False)
+    dig = ctx.extract_canonical_host_packed(bits, None, n, L, k, out_canon=canon, out_hash=hsh)
+    assert dig == (ref_nv["n_valid"], ref_nv["checksum_canon"], ref_nv["checksum_hash"])
+    assert np.array_equal(canon, ref_nv["canon"]) and np.array_equal(hsh, ref_nv["hash"])
+
+
+def test_host_pipeline_repeated_calls_and_errors(ctx, ko):
+    import kmers_b200 as kb
+    n, L, k = 20_000, 150, 31
+    bases, ref, rdig = _host_case(ko, n, L, k)
+    for _ in range(3):  # ring buffers, events and the pool are reused across calls
+        assert ctx.extract_canonical_host(bases, n, L, k) == rdig
+    with pytest.raises(kb.KmbPanic):
+        ctx.extract_canonical_host(bases, n, L, 33)
+    with pytest.raises(kb.KmbError):
+        ctx.extract_canonical_host(bases, n, 0, k)
+    assert ctx.extract_canonical_host(bases, n, L, k) == rdig  # still usable after an error
 
 
 # ------------------------------------------------------------------ wide extension (K <= 64)
