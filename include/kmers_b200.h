@@ -202,6 +202,9 @@ int32_t kmb_extract_canonical_host_packed(kmb_ctx *ctx, const uint32_t *host_bit
 int32_t kmb_host_pack(const uint8_t *bases, uint64_t n_bases, uint32_t *bits_out, uint16_t *inv_out);
 /* which implementation kmb_host_pack runs on this CPU: "avx512bw", "avx2" or "swar" */
 const char *kmb_host_pack_isa(void);
+/* diagnostic: time (seconds) n_threads host threads take to read n_bytes at buf once -- the floor of any path that has to
+ * stream the caller's reads out of host memory (bench.py reports the e2e number against it) */
+int32_t kmb_host_read_probe(const uint8_t *buf, uint64_t n_bytes, uint32_t n_threads, double *seconds_out);
 /* worker threads of the host pipeline (0 = default: the CPUs the process may run on, at most 32; one process per GPU on
  * a shared host should divide the cores between the ranks) */
 int32_t kmb_ctx_set_host_threads(kmb_ctx *ctx, uint32_t n_threads);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "kmb_extract_canonical_host_packed": (_i32, [_vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _pd]),
     "kmb_host_pack": (_i32, [_vp, _u64, _vp, _vp]),
     "kmb_host_pack_isa": (C.c_char_p, []),
+    "kmb_host_read_probe": (_i32, [_vp, _u64, _u32, C.POINTER(C.c_double)]),
     "kmb_ctx_set_host_threads": (_i32, [_vp, _u32]),
     "kmb_ctx_host_stats": (_i32, [_vp, _pu64]),
     "kmb_minimizers": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp]),

@@ -109,9 +109,10 @@ class Context:
     # Async contract: calls that write DEVICE outputs return once the work is enqueued on the context's stream.  The
     # tensors are allocated by torch on ITS current stream, so when the two streams differ (the default: a context owns a
     # private non-blocking stream) `_order_in` makes the context's stream wait for torch's pending work before the call and
-    # `_order_out` makes torch's current stream wait for the kernels after it (+ record_stream, so the caching allocator
-    # does not hand the memory out again while a kernel still writes it).  Any torch op on the results -- `.cpu()`,
-    # `CanonicalKmers.host()`, dropping the tensor -- is then ordered after the kernels.
+    # `_order_out` makes torch's current stream wait for the kernels after it.  Any torch op on the results -- `.cpu()`,
+    # `CanonicalKmers.host()`, or the caching allocator handing the memory of a dropped tensor to later work on that
+    # stream -- is then ordered after the kernels.  (No `record_stream`: the allocator would later record events on the
+    # context's stream, which may be gone by then -- contexts are closed while result tensors live on.)
     def _streams(self):
         t = _torch()
         if not t.cuda.is_available():
@@ -140,8 +141,6 @@ class Context:
         if st is not None:
             _, cur, ext = st
             cur.wait_stream(ext)
-            for x in ts:
-                x.record_stream(ext)
 
     @property
     def stream(self) -> int:
@@ -500,6 +499,13 @@ def host_pack(bases, bits: Optional[np.ndarray] = None, inv: Optional[np.ndarray
     assert bits.size >= nw and inv.size >= nw
     check(None, lib.kmb_host_pack(_ptr(b), b.size, _ptr(bits), _ptr(inv)))
     return bits, inv
+
+
+def host_read_probe(buf: np.ndarray, n_threads: int) -> float:
+    """Seconds n_threads host threads need to read `buf` once (kmb_host_read_probe): this host's memory-read floor."""
+    sec = C.c_double()
+    check(None, nv.lib().kmb_host_read_probe(_ptr(buf), buf.nbytes, n_threads, C.byref(sec)))
+    return float(sec.value)
 
 
 def host_pack_isa() -> str:

@@ -54,42 +54,74 @@ void pack_swar(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv
 // ---------------------------------------------------------------- AVX2 + BMI2: 32 bases per iteration
 // bit 1 / bit 2 of every byte through movemask (a 16-bit lane shift brings them to bit 7 of their own byte), the two
 // bit planes interleaved by pdep; validity = the byte, case-folded, equals the letter its low nibble claims (pshufb LUT).
+__attribute__((target("avx2,bmi2"), always_inline)) inline void pack32_avx2(const uint8_t* src, uint32_t* bits, uint16_t* inv, const __m256i table,
+                                                                           const __m256i m0f, const __m256i mdf) {
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src));
+    const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
+    const uint32_t m2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
+    const uint64_t w = _pdep_u64(m1 ^ m2, 0x5555555555555555ull) | _pdep_u64(m2, 0xAAAAAAAAAAAAAAAAull);
+    const __m256i expect = _mm256_shuffle_epi8(table, _mm256_and_si256(v, m0f));
+    const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, _mm256_and_si256(v, mdf)));
+    std::memcpy(bits, &w, 8);
+    std::memcpy(inv, &bad, 4);
+}
+
 __attribute__((target("avx2,bmi2"))) void pack_avx2(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
     const __m256i table = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,
                                            -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
     const __m256i m0f = _mm256_set1_epi8(0x0F), mdf = _mm256_set1_epi8((char)0xDF);
-    const size_t blocks = n_bases / 32;
-    for (size_t b = 0; b < blocks; ++b) {
-        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + 32 * b));
-        const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
-        const uint32_t m2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
-        const uint64_t w = _pdep_u64(m1 ^ m2, 0x5555555555555555ull) | _pdep_u64(m2, 0xAAAAAAAAAAAAAAAAull);
-        const __m256i expect = _mm256_shuffle_epi8(table, _mm256_and_si256(v, m0f));
-        const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, _mm256_and_si256(v, mdf)));
-        std::memcpy(bits + 2 * b, &w, 8);
-        std::memcpy(inv + 2 * b, &bad, 4);
+    constexpr size_t kStreams = 4;  // see pack_avx512
+    size_t done = 0;
+    if (n_bases >= 64 * 1024) {
+        const size_t per = n_bases / kStreams / 32;
+        for (size_t b = 0; b < per; ++b)
+            for (size_t s = 0; s < kStreams; ++s) {
+                const size_t blk = s * per + b;
+                pack32_avx2(src + 32 * blk, bits + 2 * blk, inv + 2 * blk, table, m0f, mdf);
+            }
+        done = kStreams * per;
     }
+    const size_t blocks = n_bases / 32;
+    for (size_t b = done; b < blocks; ++b) pack32_avx2(src + 32 * b, bits + 2 * b, inv + 2 * b, table, m0f, mdf);
     if (n_bases % 32) pack_swar(src + 32 * blocks, n_bases % 32, bits + 2 * blocks, inv + 2 * blocks);
 }
 
 // ---------------------------------------------------------------- AVX-512BW + BMI2: 64 bases per iteration
+__attribute__((target("avx512f,avx512bw,bmi2"), always_inline)) inline void pack64_avx512(const uint8_t* src, uint32_t* bits, uint16_t* inv,
+                                                                                         const __m512i table, const __m512i b1, const __m512i b2,
+                                                                                         const __m512i m0f, const __m512i mdf) {
+    const __m512i v = _mm512_loadu_si512(src);
+    const uint64_t m1 = _mm512_test_epi8_mask(v, b1), m2 = _mm512_test_epi8_mask(v, b2);
+    const uint64_t lo = m1 ^ m2;
+    const uint64_t w0 = _pdep_u64(lo, 0x5555555555555555ull) | _pdep_u64(m2, 0xAAAAAAAAAAAAAAAAull);
+    const uint64_t w1 = _pdep_u64(lo >> 32, 0x5555555555555555ull) | _pdep_u64(m2 >> 32, 0xAAAAAAAAAAAAAAAAull);
+    const __m512i expect = _mm512_shuffle_epi8(table, _mm512_and_si512(v, m0f));
+    const uint64_t bad = ~(uint64_t)_mm512_cmpeq_epi8_mask(expect, _mm512_and_si512(v, mdf));
+    std::memcpy(bits, &w0, 8);
+    std::memcpy(bits + 2, &w1, 8);
+    std::memcpy(inv, &bad, 8);
+}
+
+// A core streams memory faster from several places at once than from one (each stream gets its own hardware prefetcher
+// and the misses overlap; measured 8.7 -> 14.4 GB/s per core from one to four streams), and this loop is bound by exactly
+// that, so large inputs are walked as kStreams interleaved quarters.
 __attribute__((target("avx512f,avx512bw,bmi2"))) void pack_avx512(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
     const __m512i table = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
     const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04);
     const __m512i m0f = _mm512_set1_epi8(0x0F), mdf = _mm512_set1_epi8((char)0xDF);
-    const size_t blocks = n_bases / 64;
-    for (size_t b = 0; b < blocks; ++b) {
-        const __m512i v = _mm512_loadu_si512(src + 64 * b);
-        const uint64_t m1 = _mm512_test_epi8_mask(v, b1), m2 = _mm512_test_epi8_mask(v, b2);
-        const uint64_t lo = m1 ^ m2;
-        const uint64_t w0 = _pdep_u64(lo, 0x5555555555555555ull) | _pdep_u64(m2, 0xAAAAAAAAAAAAAAAAull);
-        const uint64_t w1 = _pdep_u64(lo >> 32, 0x5555555555555555ull) | _pdep_u64(m2 >> 32, 0xAAAAAAAAAAAAAAAAull);
-        const __m512i expect = _mm512_shuffle_epi8(table, _mm512_and_si512(v, m0f));
-        const uint64_t bad = ~(uint64_t)_mm512_cmpeq_epi8_mask(expect, _mm512_and_si512(v, mdf));
-        std::memcpy(bits + 4 * b, &w0, 8);
-        std::memcpy(bits + 4 * b + 2, &w1, 8);
-        std::memcpy(inv + 4 * b, &bad, 8);
+    constexpr size_t kStreams = 4;
+    size_t done = 0;
+    if (n_bases >= 64 * 1024) {
+        const size_t per = n_bases / kStreams / 64;  // 64-base blocks per stream
+        for (size_t b = 0; b < per; ++b)
+            for (size_t s = 0; s < kStreams; ++s) {
+                const size_t blk = s * per + b;
+                pack64_avx512(src + 64 * blk, bits + 4 * blk, inv + 4 * blk, table, b1, b2, m0f, mdf);
+            }
+        done = kStreams * per;
     }
+    const size_t blocks = n_bases / 64;
+    for (size_t b = done; b < blocks; ++b) pack64_avx512(src + 64 * b, bits + 4 * b, inv + 4 * b, table, b1, b2, m0f, mdf);
     if (n_bases % 64) pack_swar(src + 64 * blocks, n_bases % 64, bits + 4 * blocks, inv + 4 * blocks);
 }
 
@@ -127,6 +159,35 @@ void pack_ascii(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* in
 }
 const char* pack_isa() { return current().name; }
 void pack_force_isa(int which) { g_forced.store(which < 0 || which > 3 ? 0 : which, std::memory_order_relaxed); }
+
+namespace {
+__attribute__((target("avx2"))) uint64_t read_all_avx2(const uint8_t* p, size_t n) {
+    __m256i a0 = _mm256_setzero_si256(), a1 = a0, a2 = a0, a3 = a0;
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        a0 = _mm256_xor_si256(a0, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i)));
+        a1 = _mm256_xor_si256(a1, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i + 32)));
+        a2 = _mm256_xor_si256(a2, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i + 64)));
+        a3 = _mm256_xor_si256(a3, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i + 96)));
+    }
+    a0 = _mm256_xor_si256(_mm256_xor_si256(a0, a1), _mm256_xor_si256(a2, a3));
+    uint64_t w[4];
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(w), a0);
+    uint64_t r = w[0] ^ w[1] ^ w[2] ^ w[3];
+    for (; i < n; ++i) r ^= p[i];
+    return r;
+}
+}  // namespace
+
+uint64_t read_all(const uint8_t* p, size_t n) {
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx2")) return read_all_avx2(p, n);
+    uint64_t r = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t v; std::memcpy(&v, p + i, 8); r ^= v; }
+    for (; i < n; ++i) r ^= p[i];
+    return r;
+}
 
 unsigned usable_cpus() {
     cpu_set_t set;

@@ -40,4 +40,8 @@ private:
 // CPUs this process may run on (sched_getaffinity), at least 1
 unsigned usable_cpus();
 
+// XOR of every 8-byte word of [p, p + n): the cheapest possible consumer of a buffer, for measuring how fast this host can
+// stream its memory (the floor of any path that must read the caller's ASCII reads once)
+uint64_t read_all(const uint8_t* p, size_t n);
+
 }  // namespace kmbhost

@@ -366,10 +366,10 @@ int32_t host_common(kmb_ctx* ctx, const uint8_t* ascii, const uint32_t* pre_bits
         pl.out[0] = out_canon; pl.out[1] = out_hash;
         for (int a = 0; a < 2; ++a) pl.out_dev[a] = pl.out[a] && kmb_i_is_device_ptr(pl.out[a]);
         pl.want_digest = digest != nullptr;
-        // chunk: ~16 MiB of reads (3 bits/base of it cross the link when packed) and, when the results go back to the
+        // chunk: ~8 MiB of reads (3 bits/base of it cross the link when packed) and, when the results go back to the
         // host, no more output than the ring buffers should hold; a multiple of 16 reads keeps chunk starts on packed-word
         // boundaries and the output slots 32-byte aligned
-        uint64_t rpc = (env_mb("KMB_PIPE_CHUNK_MB", 16) << 20) / fixed_len;
+        uint64_t rpc = (env_mb("KMB_PIPE_CHUNK_MB", 8) << 20) / fixed_len;
         const bool host_out = (out_canon && !pl.out_dev[0]) || (out_hash && !pl.out_dev[1]);
         if (host_out) rpc = std::min<uint64_t>(rpc, (env_mb("KMB_PIPE_OUT_MB", 64) << 20) / (W * 8));
         rpc = std::max<uint64_t>(16, rpc / 16 * 16);
@@ -452,3 +452,29 @@ extern "C" int32_t kmb_host_pack(const uint8_t* bases, uint64_t n_bases, uint32_
 }
 
 extern "C" const char* kmb_host_pack_isa(void) { return kmbhost::pack_isa(); }
+
+extern "C" int32_t kmb_host_read_probe(const uint8_t* buf, uint64_t n_bytes, uint32_t n_threads, double* seconds_out) {
+    if (!buf || !seconds_out || n_threads < 1) return kmb_i_fail(nullptr, KMB_ERR_INVALID_ARG, "NULL pointer / no threads");
+    try {
+        kmbhost::Pool pool(n_threads);
+        std::mutex mu;
+        std::condition_variable cv;
+        const uint64_t job = (uint64_t)1 << 20;
+        const uint64_t n_jobs = (n_bytes + job - 1) / job;
+        std::atomic<uint64_t> left{n_jobs}, sink{0};
+        const auto t0 = std::chrono::steady_clock::now();
+        for (uint64_t j = 0; j < n_jobs; ++j)
+            pool.submit([&, j] {
+                sink.fetch_xor(kmbhost::read_all(buf + j * job, (size_t)std::min(job, n_bytes - j * job)), std::memory_order_relaxed);
+                if (left.fetch_sub(1, std::memory_order_acq_rel) == 1) { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
+            });
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return left.load(std::memory_order_acquire) == 0; });
+        }
+        *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } catch (...) {
+        return kmb_i_fail(nullptr, KMB_ERR_NOMEM, "could not run the read probe");
+    }
+    return KMB_OK;
+}
