@@ -149,11 +149,12 @@ int32_t kmb_extract_canonical(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t
  * every read, reads back to back in batch order:
  *   pos_out[i] = pos (i32, as the reference), canon_out[i], hash_out[i] as in kmb_extract_canonical,
  *   emit_offsets_out[r] = index of read r's first entry (n_reads + 1 entries; [n_reads] = total).
- * *n_emitted receives the number of emitted k-mers.  Call once with every output pointer NULL to
- * size the arrays, then with arrays of `capacity` >= *n_emitted entries (when the context owns the
- * batch -- upload / generate / ingest, not attach -- that second call reuses the first one's counts
- * instead of counting again).  Outputs may be host or device memory; any of them may be NULL.
- * Synchronous. */
+ * *n_emitted receives the number of emitted k-mers.  Size the arrays either by calling once with every output pointer
+ * NULL (a counting pass over the bases) or by giving them the worst case, one entry per slot (kmb_batch_num_slots): the
+ * emit call is ONE kernel launch that reads the bases once (it counts from its staged tiles and places every tile by a
+ * decoupled look-back over the earlier ones), so a caller with worst-case arrays never pays for the counting pass.
+ * Nothing is written at or beyond `capacity`; if *n_emitted > capacity the call fails with KMB_ERR_INVALID_ARG after
+ * reporting the needed size.  Outputs may be host or device memory; any of them may be NULL.  Synchronous. */
 int32_t kmb_extract_compact(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint64_t *canon_out, uint64_t *hash_out,
                             int32_t *pos_out, uint64_t *emit_offsets_out, uint64_t capacity, uint64_t *n_emitted);
 
@@ -200,7 +201,7 @@ int32_t kmb_extract_canonical_host_packed(kmb_ctx *ctx, const uint32_t *host_bit
  * bits_out / inv_out receive ceil(n_bases / 16) entries; bytes outside ACGTacgt encode by (c >> 1) & 3 like
  * Encoding::encode and set their invalid bit. */
 int32_t kmb_host_pack(const uint8_t *bases, uint64_t n_bases, uint32_t *bits_out, uint16_t *inv_out);
-/* which implementation kmb_host_pack runs on this CPU: "avx512bw", "avx2" or "swar" */
+/* which implementation kmb_host_pack runs on this CPU: "avx512gfni", "avx512bw", "avx2" or "swar" */
 const char *kmb_host_pack_isa(void);
 /* diagnostic: time (seconds) n_threads host threads take to read n_bytes at buf once -- the floor of any path that has to
  * stream the caller's reads out of host memory (bench.py reports the e2e number against it) */
@@ -300,6 +301,43 @@ int32_t kmb_lexhash_words(kmb_ctx *ctx, uint32_t k, const uint64_t *in, uint64_t
  * (canonical_kmer.rs:42-52, 152-161) -> KMB_*_MATCH as u8 */
 int32_t kmb_match_words(kmb_ctx *ctx, uint32_t k, const uint64_t *words, const uint64_t *others,
                         uint8_t *match_out, uint64_t n);
+
+
+/* ---- the small accessors of naive_impl::Kmer / CanonicalKmer and kmer::Kmer<P,K,B>, batched ------------------------- */
+/* Kmer::sub_kmer_word (naive_impl/kmer.rs:150-161): out[i] = (in[i] >> 2 pos) & MASK_TABLE[width]; pos < k and
+ * pos + width <= k or KMB_ERR_PANIC (the reference asserts).  width == 32 uses the intended all-ones mask. */
+int32_t kmb_sub_kmer_words(kmb_ctx *ctx, uint32_t k, uint32_t pos, uint32_t width, const uint64_t *in, uint64_t *out, uint64_t n);
+/* Kmer::append_base / append_base_u8 (naive_impl/kmer.rs:83-102; slide right along the read): out[i] = (in[i] >> 2) |
+ * (c << (2k - 2)), dropped_out[i] = the base shifted off (low two bits of in[i]).  bases[i] is a 2-bit code (Base), or a
+ * letter when bases_are_ascii != 0 -- encoded by encode_binary_u8 WITHOUT a guard, exactly like the reference: a byte
+ * outside ACGTacgt ORs u64::MAX << (2k - 2) into the word.  out / dropped_out may be NULL. */
+int32_t kmb_append_base_words(kmb_ctx *ctx, uint32_t k, const uint64_t *in, const uint8_t *bases, int32_t bases_are_ascii,
+                              uint64_t *out, uint8_t *dropped_out, uint64_t n);
+/* Kmer::prepend_base / prepend_base_u8 (naive_impl/kmer.rs:76-95): out[i] = MASK_TABLE[k] & ((in[i] << 2) | c),
+ * dropped_out[i] = the top base of in[i].  k == 32 uses the intended all-ones mask. */
+int32_t kmb_prepend_base_words(kmb_ctx *ctx, uint32_t k, const uint64_t *in, const uint8_t *bases, int32_t bases_are_ascii,
+                               uint64_t *out, uint8_t *dropped_out, uint64_t n);
+/* CanonicalKmer::append_base[_u8] / prepend_base[_u8] (naive_impl/canonical_kmer.rs:70-100) on (fw, rc) word pairs:
+ * append: fw.append_base(b), rc.prepend_base(complement_base(b)); prepend the other way round; dropped_out = what fw lost. */
+int32_t kmb_canonical_append_base_words(kmb_ctx *ctx, uint32_t k, const uint64_t *fw_in, const uint64_t *rc_in, const uint8_t *bases,
+                                        int32_t bases_are_ascii, uint64_t *fw_out, uint64_t *rc_out, uint8_t *dropped_out, uint64_t n);
+int32_t kmb_canonical_prepend_base_words(kmb_ctx *ctx, uint32_t k, const uint64_t *fw_in, const uint64_t *rc_in, const uint8_t *bases,
+                                         int32_t bases_are_ascii, uint64_t *fw_out, uint64_t *rc_out, uint8_t *dropped_out, uint64_t n);
+/* CanonicalKmer::is_fw_canonical (canonical_kmer.rs:67-69): out[i] = fw[i] < rc[i].  (CanonicalKmer::swap, :62-65, is the
+ * caller exchanging its two pointers; Kmer::orientation, naive_impl/kmer.rs:60-66, is kmb_canonical_words' is_canonical_out:
+ * 1 = IsCanonical, 0 = NotCanononical.) */
+int32_t kmb_is_fw_canonical_words(kmb_ctx *ctx, const uint64_t *fw, const uint64_t *rc, uint8_t *out, uint64_t n);
+/* kmer::Kmer<P,K,B>::get (kmer.rs:46-48): codes_out[i] = the 2-bit field `index` of array i (arrays = n_items byte images of
+ * words_per_item words of word_bits, as kmb_pack writes them).  An index beyond the array is KMB_ERR_PANIC (get_bits asserts). */
+int32_t kmb_kmer_get(kmb_ctx *ctx, uint32_t word_bits, uint32_t words_per_item, const void *arrays, uint64_t n_items, uint32_t index,
+                     uint8_t *codes_out);
+/* kmer::Kmer<P,K,B>::get_prefix (kmer.rs:50-52): words_out[i] (one word of word_bits) = bits 0 ..= 2 len of array i -- the
+ * reference's INCLUSIVE range, 2 len + 1 bits, matched as it is.  More bits than a P holds: KMB_ERR_PANIC. */
+int32_t kmb_kmer_get_prefix(kmb_ctx *ctx, uint32_t word_bits, uint32_t words_per_item, const void *arrays, uint64_t n_items, uint32_t len,
+                            void *words_out);
+/* bitmer_to_bytes (kmer.rs:71-91) on n u64 words: len upper-case letters each, base 0 first, A0 C1 G2 T3 whatever encoder
+ * produced the word (the reference hard-codes the table).  len <= 32. */
+int32_t kmb_bitmer_to_bytes(kmb_ctx *ctx, uint32_t len, const uint64_t *mers, uint64_t n, uint8_t *bases_out);
 
 #ifdef __cplusplus
 }

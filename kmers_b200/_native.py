@@ -92,6 +92,15 @@ SIGNATURES = {
     "kmb_canonical_words": (_i32, [_vp, _u32, _vp, _vp, _vp, _u64]),
     "kmb_lexhash_words": (_i32, [_vp, _u32, _vp, _vp, _u64]),
     "kmb_match_words": (_i32, [_vp, _u32, _vp, _vp, _vp, _u64]),
+    "kmb_sub_kmer_words": (_i32, [_vp, _u32, _u32, _u32, _vp, _vp, _u64]),
+    "kmb_append_base_words": (_i32, [_vp, _u32, _vp, _vp, _i32, _vp, _vp, _u64]),
+    "kmb_prepend_base_words": (_i32, [_vp, _u32, _vp, _vp, _i32, _vp, _vp, _u64]),
+    "kmb_canonical_append_base_words": (_i32, [_vp, _u32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _u64]),
+    "kmb_canonical_prepend_base_words": (_i32, [_vp, _u32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _u64]),
+    "kmb_is_fw_canonical_words": (_i32, [_vp, _vp, _vp, _vp, _u64]),
+    "kmb_kmer_get": (_i32, [_vp, _u32, _u32, _vp, _u64, _u32, _vp]),
+    "kmb_kmer_get_prefix": (_i32, [_vp, _u32, _u32, _vp, _u64, _u32, _vp]),
+    "kmb_bitmer_to_bytes": (_i32, [_vp, _u32, _vp, _u64, _vp]),
 }
 
 _lib = None

@@ -301,6 +301,74 @@ class Context:
         self.sync()
         return mm, off
 
+    # ---- the small Kmer / CanonicalKmer accessors, batched (host numpy in, host numpy out)
+    def sub_kmer_words(self, words, k: int, pos: int, width: int) -> np.ndarray:
+        """Kmer::sub_kmer_word (naive_impl/kmer.rs:150-161) on every word."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        out = np.empty_like(w)
+        self._ck(self._lib.kmb_sub_kmer_words(self._h, k, pos, width, _ptr(w), _ptr(out), w.size))
+        return out
+
+    def _shift(self, fn, words, bases, k, ascii_):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        b = np.ascontiguousarray(np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else bases, dtype=np.uint8)
+        assert b.size == w.size
+        out, dropped = np.empty_like(w), np.empty(w.size, dtype=np.uint8)
+        self._ck(fn(self._h, k, _ptr(w), _ptr(b), int(ascii_), _ptr(out), _ptr(dropped), w.size))
+        return out, dropped
+
+    def append_base_words(self, words, bases, k: int, ascii: bool = False):
+        """Kmer::append_base / append_base_u8 (naive_impl/kmer.rs:83-102) -> (shifted words, bases shifted off)."""
+        return self._shift(self._lib.kmb_append_base_words, words, bases, k, ascii)
+
+    def prepend_base_words(self, words, bases, k: int, ascii: bool = False):
+        """Kmer::prepend_base / prepend_base_u8 (naive_impl/kmer.rs:76-95) -> (shifted words, bases shifted off)."""
+        return self._shift(self._lib.kmb_prepend_base_words, words, bases, k, ascii)
+
+    def _cshift(self, fn, fw, rc, bases, k, ascii_):
+        f, r = np.ascontiguousarray(fw, dtype=np.uint64), np.ascontiguousarray(rc, dtype=np.uint64)
+        b = np.ascontiguousarray(np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else bases, dtype=np.uint8)
+        fo, ro, dropped = np.empty_like(f), np.empty_like(r), np.empty(f.size, dtype=np.uint8)
+        self._ck(fn(self._h, k, _ptr(f), _ptr(r), _ptr(b), int(ascii_), _ptr(fo), _ptr(ro), _ptr(dropped), f.size))
+        return fo, ro, dropped
+
+    def canonical_append_base_words(self, fw, rc, bases, k: int, ascii: bool = False):
+        """CanonicalKmer::append_base[_u8] (canonical_kmer.rs:70-92) on (fw, rc) pairs -> (fw, rc, dropped)."""
+        return self._cshift(self._lib.kmb_canonical_append_base_words, fw, rc, bases, k, ascii)
+
+    def canonical_prepend_base_words(self, fw, rc, bases, k: int, ascii: bool = False):
+        """CanonicalKmer::prepend_base[_u8] (canonical_kmer.rs:79-100) on (fw, rc) pairs -> (fw, rc, dropped)."""
+        return self._cshift(self._lib.kmb_canonical_prepend_base_words, fw, rc, bases, k, ascii)
+
+    def is_fw_canonical_words(self, fw, rc) -> np.ndarray:
+        """CanonicalKmer::is_fw_canonical (canonical_kmer.rs:67-69)."""
+        f, r = np.ascontiguousarray(fw, dtype=np.uint64), np.ascontiguousarray(rc, dtype=np.uint64)
+        out = np.empty(f.size, dtype=np.uint8)
+        self._ck(self._lib.kmb_is_fw_canonical_words(self._h, _ptr(f), _ptr(r), _ptr(out), f.size))
+        return out
+
+    def kmer_get(self, word_bits: int, words_per_item: int, arrays: np.ndarray, n_items: int, index: int) -> np.ndarray:
+        """kmer::Kmer<P,K,B>::get(index) (kmer.rs:46-48) on n_items arrays (byte image) -> 2-bit codes."""
+        img = np.ascontiguousarray(arrays).view(np.uint8).reshape(-1)
+        out = np.empty(n_items, dtype=np.uint8)
+        self._ck(self._lib.kmb_kmer_get(self._h, word_bits, words_per_item, _ptr(img), n_items, index, _ptr(out)))
+        return out
+
+    def kmer_get_prefix(self, word_bits: int, words_per_item: int, arrays: np.ndarray, n_items: int, length: int) -> np.ndarray:
+        """kmer::Kmer<P,K,B>::get_prefix(len) (kmer.rs:50-52; 2 len + 1 bits, as the reference) -> (n_items, word_bytes) byte image."""
+        img = np.ascontiguousarray(arrays).view(np.uint8).reshape(-1)
+        out = np.empty(n_items * word_bits // 8, dtype=np.uint8)
+        self._ck(self._lib.kmb_kmer_get_prefix(self._h, word_bits, words_per_item, _ptr(img), n_items, length, _ptr(out)))
+        return out.reshape(n_items, word_bits // 8)
+
+    def bitmer_to_bytes(self, mers, length: int) -> np.ndarray:
+        """bitmer_to_bytes (kmer.rs:71-91) on every u64 -> (n, length) upper-case ASCII."""
+        w = np.ascontiguousarray(mers, dtype=np.uint64)
+        out = np.empty((w.size, length), dtype=np.uint8)
+        self._ck(self._lib.kmb_bitmer_to_bytes(self._h, length, _ptr(w), w.size, _ptr(out)))
+        self.sync()
+        return out
+
     # ---- batched Encoding::decode / rev_comp on arrays [P; B]
     def words_to_strings(self, words, k: int) -> np.ndarray:
         """Batched `String::from(Kmer)` (naive_impl/kmer.rs:196-207): (n, k) lower-case ASCII (kmb_words_to_strings)."""

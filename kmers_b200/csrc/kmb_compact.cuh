@@ -5,9 +5,11 @@
 // exactly that sequence for every read of the batch, back to back in read order:
 //   pos_out[i]   = pos (i32, as the reference)         canon_out[i] = get_canonical_word()
 //   hash_out[i]  = hash_one(LexHasherState(k), canon)  emit_offsets[r] = index of read r's first entry
-// Two launches of the same geometry: COUNT_ONLY counts the valid windows of every CTA (reads the bases
-// only); after an exclusive scan of the CTA counts the emit launch re-derives the per-item offsets with a
-// CTA-wide scan and stores each valid window at its final index.
+// ONE launch, the bases are read once: a CTA stages its tile, counts the valid windows of its items from the staged
+// invalid masks, scans them CTA-wide, learns where its entries start in the output from a decoupled look-back over
+// the earlier tiles (single-pass chained scan: every tile publishes {aggregate | inclusive prefix} in one 64-bit
+// descriptor; tiles are handed out by an atomic ticket so a tile only ever waits for tiles that are already running),
+// and stores each valid window at its final index.  COUNT_ONLY (the sizing call) just adds up the CTA totals.
 #pragma once
 #include <cstddef>
 
@@ -20,23 +22,39 @@ struct CompactOut {
     uint64_t* hash;
     int32_t* pos;
     uint64_t* emit_offsets;              // n_reads + 1 (entry n_reads is written by the host)
-    unsigned long long* cta_counts;      // COUNT_ONLY: valid windows per CTA (out); emit: exclusive scan of them (in)
+    unsigned long long* desc;            // look-back descriptors, one per tile: status << 62 | value (zeroed before the launch)
+    unsigned long long* ticket;          // next tile to hand out (zeroed before the launch)
+    unsigned long long* total;           // COUNT_ONLY: += every CTA's count; emit: the last tile stores the grand total
+    uint64_t capacity;                   // entries the output arrays hold: nothing is written at or beyond it
 };
+
+constexpr unsigned long long kDescAggregate = 1ull << 62, kDescPrefix = 2ull << 62, kDescValue = (1ull << 62) - 1;
+__device__ __forceinline__ unsigned long long desc_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void desc_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 struct CompactParams {
     WinConst wc;
     CompactOut out;
 };
 
-constexpr int kCompactRound = kExtractThreads * kRun;  // entries one round of items can emit (2048)
+constexpr int kCompactRound = kExtractThreads * kRun;  // entries one round of items can emit (2048): 256 per warp
 
 // Shared memory of the compaction kernels beyond the tile: per-item counts, and the staging buffers through which
 // a round's entries reach global memory as coalesced stores (each thread's <= 8 entries land at arbitrary,
 // unaligned indices; storing them directly would touch every 32-byte sector 4-8 times).
 struct CompactShared {
     uint32_t cnt[kItemsPerCta + 1];
-    uint32_t round_off[kItemsPerCta / kExtractThreads + 2];  // exclusive offset of every round's first item, and the total
+    uint32_t wr_off[kItemsPerCta / 32 + 2];  // exclusive offset of the first item of every warp-round (32 items), and the total
     uint32_t warp_tot[kExtractThreads / 32];
+    uint32_t tile_id;                 // this CTA's ticket
+    uint32_t lb_has[kExtractThreads / 32];          // look-back: warp w's window holds a tile that knows its prefix
+    unsigned long long lb_sum[kExtractThreads / 32];  // ... and the values of its window up to that tile
     // staging buffers of the emit launch; the counting launch allocates the struct only up to here (kCompactCountBytes)
     // (no hash buffer: LexHash(canon) is one pair reversal, computed when the entry leaves -- cheaper than staging it)
     alignas(16) uint64_t canon[kCompactRound];
@@ -56,11 +74,70 @@ struct CompactEng {
     CompactShared& sh;
     uint64_t pass_base = 0;      // valid windows of this CTA's passes so far
     uint64_t cur_pass_base = 0;  // ... before the current pass
-    uint64_t cta_base = 0;       // valid windows of all earlier CTAs
+    uint64_t cta_base = 0;       // valid windows of all earlier tiles
+    uint32_t tile_id = 0;
+    bool placed = false;         // cta_base is known
 
-    __device__ CompactEng(const CompactParams& params, CompactShared& shared) : p(params), sh(shared) {
-        if (!COUNT_ONLY) cta_base = p.out.cta_counts[blockIdx.x];
+    __device__ CompactEng(const CompactParams& params, CompactShared& shared) : p(params), sh(shared) {}
+
+    // Take the next tile.  Called by all threads at the top of the kernel; the ticket order is the scheduling order, so
+    // every tile with a smaller id has started before this one and look-back cannot wait for a CTA that is not resident.
+    __device__ __forceinline__ uint32_t take_tile() {
+        if (COUNT_ONLY) { tile_id = blockIdx.x; return tile_id; }
+        if (threadIdx.x == 0) sh.tile_id = (uint32_t)atomicAdd(p.out.ticket, 1ull);
+        __syncthreads();
+        tile_id = sh.tile_id;
+        return tile_id;
     }
+
+    // After a pass's scan (pass_base = this CTA's count so far, incl. the pass).  Single-pass tiles -- all of them except
+    // CSR tiles whose reads are mostly shorter than k -- publish their aggregate, look back, publish their inclusive
+    // prefix.  A multi-pass tile looks back during its first pass without an aggregate to show (its successors wait) and
+    // publishes the inclusive prefix when its last pass has been counted.
+    __device__ __forceinline__ void place(bool last_pass) {
+        if (COUNT_ONLY) return;
+        if (!placed) {
+            if (last_pass && threadIdx.x == 0 && tile_id > 0) desc_store(p.out.desc + tile_id, kDescAggregate | pass_base);
+            // Look-back, the whole CTA at once: thread i reads the descriptor of tile (tile_id - 1 - i), so one round covers
+            // kExtractThreads predecessors with a single global-load latency (a warp-wide window needs a round per 32 tiles,
+            // and with ~600 tiles in flight the nearest tile that already knows its prefix is often 100+ tiles back).
+            const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+            unsigned long long excl = 0;
+            int64_t idx = (int64_t)tile_id - 1;
+            for (;;) {  // CTA-uniform
+                if (idx < 0) break;
+                const int64_t mine = idx - (int64_t)threadIdx.x;
+                unsigned long long d = kDescPrefix;  // before tile 0: "prefix 0"
+                if (mine >= 0) {
+                    do { d = desc_load(p.out.desc + mine); } while ((d >> 62) == 0ull);
+                }
+                const unsigned pf = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+                // value of this warp's window up to (and including) its nearest prefix holder
+                const unsigned upto = pf ? (unsigned)__ffs(pf) - 1u : 31u;
+                unsigned long long v = lane <= upto ? (d & kDescValue) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) { sh.lb_sum[warp] = v; sh.lb_has[warp] = pf != 0u; }
+                __syncthreads();
+                bool found = false;
+                for (int w = 0; w < kExtractThreads / 32 && !found; ++w) {  // nearest warps first; stop at the first prefix
+                    excl += sh.lb_sum[w];
+                    found = sh.lb_has[w] != 0u;
+                }
+                __syncthreads();
+                if (found) break;
+                idx -= kExtractThreads;
+            }
+            cta_base = excl;
+            placed = true;
+        }
+        if (last_pass && threadIdx.x == 0) {
+            const unsigned long long incl = cta_base + pass_base;
+            desc_store(p.out.desc + tile_id, kDescPrefix | incl);
+            if (tile_id + 1 == gridDim.x) *p.out.total = incl;
+        }
+    }
+
     __device__ __forceinline__ uint32_t K() const { return p.wc.K; }
     __device__ __forceinline__ Span load(const uint2* tile, uint32_t rel) const { return load_span<VALIDATE>(tile, rel, p.wc); }
     __device__ __forceinline__ bool dirty(const Span& s) const { return s.inv != 0ull; }
@@ -93,9 +170,10 @@ struct CompactEng {
         for (int i = 0; i < PER; ++i) { if (base + i < n_items) sh.cnt[base + i] = run; run += v[i]; }
         if (threadIdx.x == 0) sh.cnt[n_items] = total;
         __syncthreads();
-        // offsets at which the rounds of items start (the emit phase bumps cnt[] for single-window items)
-        const uint32_t rounds = (n_items + kExtractThreads - 1) / kExtractThreads;
-        if (threadIdx.x <= rounds) sh.round_off[threadIdx.x] = sh.cnt[min(threadIdx.x * kExtractThreads, n_items)];
+        // offsets at which the warp-rounds (32 consecutive items = one warp in one round) start; a copy, because the emit
+        // phase bumps cnt[] for single-window items
+        const uint32_t wrs = (n_items + 31) / 32;
+        if (threadIdx.x <= wrs) sh.wr_off[threadIdx.x] = sh.cnt[min(threadIdx.x * 32u, n_items)];
         cur_pass_base = pass_base;
         pass_base += total;
     }
@@ -106,9 +184,10 @@ struct CompactEng {
     // stride-8 write pattern and the linear read-out of round_end over all banks.
     __device__ static __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 4) & 15u); }
 
-    // stage one entry of the current round (local index = its offset inside the round)
+    // stage one entry of this warp's current round (local index = its offset inside the warp-round, < 256): every warp
+    // owns a 256-entry slice of the staging buffers, so a round needs no CTA-wide barrier
     __device__ __forceinline__ void put(uint32_t local, const Window& w, uint64_t pos) const {
-        const uint32_t i = swz(local);
+        const uint32_t i = (threadIdx.x >> 5) * (32 * kRun) + swz(local);
         sh.canon[i] = w.canon;
         sh.pos[i] = (int32_t)pos;
     }
@@ -116,7 +195,7 @@ struct CompactEng {
     template <bool TWO, bool CHECK>
     __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t, uint32_t nwin, const ItemCtx& ic) {
         const uint32_t off = sh.cnt[ic.li];
-        uint32_t local = off - sh.round_off[ic.li / kExtractThreads];
+        uint32_t local = off - sh.wr_off[ic.li >> 5];
         const uint64_t o0 = cta_base + cur_pass_base + off;  // global index of this item's first entry
         if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o0;  // this item opens read r_a
         uint32_t emitted = 0;
@@ -141,26 +220,40 @@ struct CompactEng {
         const Span s = load_span<VALIDATE>(tile, rel, p.wc);
         const bool ok = !VALIDATE || (((uint32_t)s.inv) & p.wc.kmask) == 0u;
         if (ok) {
-            put(off - sh.round_off[ic.li / kExtractThreads], make_window<KHI>(s, 0, p.wc), ic.pos_a);
+            put(off - sh.wr_off[ic.li >> 5], make_window<KHI>(s, 0, p.wc), ic.pos_a);
             sh.cnt[ic.li] = off + 1;
         }
     }
-    // all threads, once per round: the staged entries of the round leave as coalesced stores
-    __device__ __forceinline__ void round_end(uint32_t q_round, uint32_t) {
-        __syncthreads();
-        const uint32_t lo = sh.round_off[q_round], n = sh.round_off[q_round + 1] - lo;
-        const uint64_t g0 = cta_base + cur_pass_base + lo;
-        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-            const uint32_t i = swz(e);
-            const uint64_t c = sh.canon[i];
-            if (p.out.canon) p.out.canon[g0 + e] = c;
-            if (p.out.hash) p.out.hash[g0 + e] = pair_reverse64(c) >> (2 * (32 - p.wc.K));  // LexHasher::write_u64, hash.rs:60-71
-            if (p.out.pos) p.out.pos[g0 + e] = sh.pos[i];
+    // all threads, once per round: every warp writes the entries its 32 items staged -- one contiguous run of the output --
+    // as coalesced stores.  Warp-level synchronisation only.
+    __device__ __forceinline__ void round_end(uint32_t q_round, uint32_t n_items) {
+        __syncwarp();
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        const uint32_t wr = q_round * (kExtractThreads / 32) + warp;  // this warp-round's index among the pass's
+        if (wr * 32u < n_items) {
+            const uint32_t lo = sh.wr_off[wr], n = sh.wr_off[wr + 1] - lo;
+            const uint64_t g0 = cta_base + cur_pass_base + lo;
+            // the caller's arrays may be too small: the host reports it, nothing is overrun
+            const uint32_t n_ok = g0 >= p.out.capacity ? 0u : (uint32_t)min((uint64_t)n, p.out.capacity - g0);
+            const uint64_t* sc = sh.canon + warp * (32 * kRun);
+            const int32_t* sp = sh.pos + warp * (32 * kRun);
+            uint64_t* gc = p.out.canon ? p.out.canon + g0 : nullptr;
+            uint64_t* gh = p.out.hash ? p.out.hash + g0 : nullptr;
+            int32_t* gp = p.out.pos ? p.out.pos + g0 : nullptr;
+            const uint32_t hs = 2 * (32 - p.wc.K);
+#pragma unroll 2
+            for (uint32_t e = lane; e < n_ok; e += 32) {
+                const uint32_t i = swz(e);
+                const uint64_t c = sc[i];
+                if (gc) gc[e] = c;
+                if (gh) gh[e] = pair_reverse64(c) >> hs;  // LexHasher::write_u64, hash.rs:60-71
+                if (gp) gp[e] = sp[i];
+            }
         }
-        __syncthreads();  // the next round re-uses the staging buffers
+        __syncwarp();  // the next round re-uses this warp's slice
     }
     __device__ __forceinline__ void finish() {
-        if (COUNT_ONLY && threadIdx.x == 0) p.out.cta_counts[blockIdx.x] = pass_base;
+        if (COUNT_ONLY && threadIdx.x == 0 && pass_base) atomicAdd(p.out.total, (unsigned long long)pass_base);
     }
 };
 
@@ -171,7 +264,7 @@ __global__ void __launch_bounds__(kExtractThreads) compact_fixed_kernel(const Fi
     extern __shared__ uint2 tile[];
     CompactShared& sh = *reinterpret_cast<CompactShared*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);
     Eng eng(ep, sh);
-    fixed_body(g, enc, eng, tile, blockIdx.x);
+    fixed_body(g, enc, eng, tile, eng.take_tile());
     eng.finish();
 }
 
@@ -184,7 +277,7 @@ __global__ void __launch_bounds__(kExtractThreads) compact_csr_kernel(const CsrG
     uint64_t* c_win = c_off + (kCsrCache + 2);
     CompactShared& sh = *reinterpret_cast<CompactShared*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);
     Eng eng(ep, sh);
-    csr_body(g, enc, eng, tile, c_off, c_win, &pass, blockIdx.x);
+    csr_body(g, enc, eng, tile, c_off, c_win, &pass, eng.take_tile());
     eng.finish();
 }
 

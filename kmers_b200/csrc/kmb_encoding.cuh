@@ -250,6 +250,135 @@ __global__ void __launch_bounds__(256) unpack_tile_kernel(const uint8_t* in, uin
     for (uint32_t j = head + 16 * n_vec + threadIdx.x; j < n_bytes; j += blockDim.x) dst[j] = text[mis + j];
 }
 
+// ---------------------------------------------------------------- Encoding::decode, output-space form
+// One thread = one 16-byte aligned block of the OUTPUT text, so every store is a full 16-byte vector whatever the item
+// length is (31 letters for a 31-mer); the <= 16 letters of a block come from one or two items (more only for items
+// shorter than 16 letters), each fetched as a bit field of the packed input, and four letters at a time are decoded by
+// one PRMT: the 2-bit codes are spread to nibbles (three shift-or-mask steps per 8 codes) and select bytes of the
+// four-letter table `dec`.  ~3 instructions per letter instead of ~9 (the per-input-byte kernel above: 25 % of the copy peak).
+// All per-thread arithmetic is 32-bit and relative to the CTA's first item; SAFE = the CTA's whole input stretch (plus
+// the word a funnel shift may touch beyond it) lies inside the buffer, so loads need no bounds checks (all CTAs but the last).
+template <bool SAFE>
+__device__ __forceinline__ uint32_t fetch_bits32(const uint32_t* __restrict__ words, uint32_t bit, uint64_t words_left_bytes) {
+    const uint32_t widx = bit >> 5, sh = bit & 31u;
+    uint32_t lo, hi;
+    if (SAFE) {
+        lo = __ldg(words + widx);
+        hi = __ldg(words + widx + 1);
+    } else {  // byte-granular guards at the very end of the buffer
+        lo = hi = 0;
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(words);
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            if ((uint64_t)widx * 4 + i < words_left_bytes) lo |= (uint32_t)__ldg(b + (uint64_t)widx * 4 + i) << (8 * i);
+            if ((uint64_t)widx * 4 + 4 + i < words_left_bytes) hi |= (uint32_t)__ldg(b + (uint64_t)widx * 4 + 4 + i) << (8 * i);
+        }
+    }
+    return __funnelshift_r(lo, hi, sh);
+}
+// 8 two-bit codes (16 bits) -> 8 letters (two registers)
+__device__ __forceinline__ void decode8(uint32_t c16, uint32_t dec, uint32_t& out0, uint32_t& out1) {
+    uint32_t x = c16 & 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;  // code j in nibble j
+    out0 = __byte_perm(dec, 0u, x & 0xFFFFu);
+    out1 = __byte_perm(dec, 0u, x >> 16);
+}
+
+constexpr int kUnpackBlocksPerThread = 2;
+
+// the <= 16 codes of letters [rel, rel + n) of the CTA's item stream (rel counted from the first letter of the CTA's first item)
+template <bool SAFE>
+__device__ __forceinline__ uint32_t gather_codes(const uint32_t* __restrict__ cta_words, uint64_t cta_bytes_left, uint32_t bit_base,
+                                                 uint32_t rel, uint32_t n, uint32_t item_bits, uint32_t bases_per_item, uint32_t bpi_magic) {
+    uint32_t it = bases_per_item == 1 ? rel : __umulhi(rel, bpi_magic);  // exact: rel * bases_per_item < 2^32
+    const uint32_t o = rel - it * bases_per_item;
+    uint32_t take = min(n, bases_per_item - o);
+    uint32_t codes = fetch_bits32<SAFE>(cta_words, bit_base + it * item_bits + 2u * o, cta_bytes_left);
+    if (take < n) {  // the block runs into the next item(s)
+        codes &= (1u << (2 * take)) - 1u;
+        uint32_t done = take;
+        do {
+            ++it;
+            take = min(n - done, bases_per_item);
+            uint32_t bits = fetch_bits32<SAFE>(cta_words, bit_base + it * item_bits, cta_bytes_left);
+            if (take < 16u) bits &= (1u << (2 * take)) - 1u;
+            codes |= bits << (2 * done);
+            done += take;
+        } while (done < n);
+    }
+    return codes;
+}
+
+// INTERIOR: every block of the CTA is a full 16 letters inside the text (all CTAs but the first and the last): no per-block
+// bounds arithmetic, everything 32-bit and relative to the CTA.
+template <bool SAFE, bool INTERIOR>
+__device__ __forceinline__ void unpack_flat_body(const uint32_t* __restrict__ cta_words, uint64_t cta_bytes_left, uint32_t bit_base, uint32_t cta_off,
+                                                 int64_t cta_p0, uint32_t item_bits, uint32_t bases_per_item, uint32_t bpi_magic,
+                                                 uint32_t dec, uint8_t* __restrict__ out, uint64_t total_letters, uint32_t n_blocks_cta) {
+#pragma unroll
+    for (int u = 0; u < kUnpackBlocksPerThread; ++u) {
+        const uint32_t qrel = (uint32_t)u * 256u + threadIdx.x;
+        if (!INTERIOR && qrel >= n_blocks_cta) continue;
+        uint32_t j0 = 0, n = 16;
+        uint32_t rel = 16u * qrel + cta_off;  // INTERIOR: cta_off = offset of letter cta_p0 inside the CTA's first item
+        if (!INTERIOR) {
+            const int64_t p0 = cta_p0 + 16 * (int64_t)qrel;
+            const uint64_t lo = p0 < 0 ? 0ull : (uint64_t)p0;
+            const uint64_t hi = min((uint64_t)(p0 + 16), total_letters);
+            j0 = (uint32_t)((int64_t)lo - p0);  // non-zero only in the very first block of the text
+            n = (uint32_t)(hi - lo);
+            rel = (uint32_t)(lo - (uint64_t)(cta_p0 < 0 ? 0 : cta_p0)) + cta_off;
+        }
+        uint32_t codes = gather_codes<SAFE>(cta_words, cta_bytes_left, bit_base, rel, n, item_bits, bases_per_item, bpi_magic);
+        if (!INTERIOR) codes <<= 2 * j0;
+        uint32_t c0, c1, c2, c3;
+        decode8(codes, dec, c0, c1);
+        decode8(codes >> 16, dec, c2, c3);
+        uint8_t* dst = out + (cta_p0 + 16 * (int64_t)qrel);  // 16-byte aligned by construction
+        if (INTERIOR || n == 16u) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(c0, c1, c2, c3);
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) {
+                const uint32_t c = j < 4 ? c0 : (j < 8 ? c1 : (j < 12 ? c2 : c3));
+                if (j >= j0 && j < j0 + n) dst[j] = (uint8_t)(c >> (8 * (j & 3u)));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_flat_kernel(const uint8_t* __restrict__ in, uint64_t in_total_bytes, uint64_t n_items,
+                                                          uint32_t in_bytes_per_item, uint32_t bases_per_item, uint32_t bpi_magic,
+                                                          uint64_t bpi_magic64, uint32_t dec, uint8_t* __restrict__ out, uint64_t total_letters,
+                                                          uint64_t n_blocks) {
+    constexpr uint32_t kBlocksPerCta = 256 * kUnpackBlocksPerThread;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);  // block q covers letters [16 q - mis, 16 q - mis + 16)
+    const uint64_t q0 = (uint64_t)blockIdx.x * kBlocksPerCta;
+    const int64_t cta_p0 = (int64_t)(q0 * 16) - (int64_t)mis;  // first letter of the CTA's first block (negative only in CTA 0)
+    // first item of the CTA: one 64-bit division (by multiplication), everything after it in 32 bits relative to that item
+    const uint64_t cta_p = cta_p0 < 0 ? 0ull : (uint64_t)cta_p0;
+    const uint64_t cta_item = bases_per_item == 1 ? cta_p : __umul64hi(cta_p, bpi_magic64);
+    const uint32_t cta_off = (uint32_t)(cta_p - cta_item * bases_per_item);
+    const uint64_t cta_byte0 = cta_item * in_bytes_per_item;  // u8 / u16 word types: not always a multiple of 4 -> bit_base
+    const uint32_t* cta_words = reinterpret_cast<const uint32_t*>(in + (cta_byte0 & ~3ull));
+    const uint32_t bit_base = (uint32_t)(cta_byte0 & 3ull) * 8u;
+    const uint64_t left = in_total_bytes - (cta_byte0 & ~3ull);
+    // input the CTA can touch: its letters span at most (letters / bases_per_item + 2) items, plus the words a funnel shift may touch
+    const uint64_t span_items = (uint64_t)(kBlocksPerCta * 16 + cta_off) / bases_per_item + 2;
+    const bool safe = span_items * in_bytes_per_item + 12 <= left;
+    const bool interior = cta_p0 >= 0 && (uint64_t)cta_p0 + kBlocksPerCta * 16ull <= total_letters;
+    const uint32_t n_blocks_cta = (uint32_t)min((uint64_t)kBlocksPerCta, n_blocks - q0);
+    const uint32_t item_bits = in_bytes_per_item * 8u;
+    if (safe && interior)
+        unpack_flat_body<true, true>(cta_words, left, bit_base, cta_off, cta_p0, item_bits, bases_per_item, bpi_magic, dec, out, total_letters, n_blocks_cta);
+    else if (safe)
+        unpack_flat_body<true, false>(cta_words, left, bit_base, cta_off, cta_p0, item_bits, bases_per_item, bpi_magic, dec, out, total_letters, n_blocks_cta);
+    else
+        unpack_flat_body<false, false>(cta_words, left, bit_base, cta_off, cta_p0, item_bits, bases_per_item, bpi_magic, dec, out, total_letters, n_blocks_cta);
+}
+
 // ---------------------------------------------------------------- Encoding::rev_comp::<K>
 // encoding/naive.rs:138-154 / xor10.rs:86-103: fields 0..K-1 are reversed and
 // complemented, bits >= 2K untouched.  One thread = one item of NW32 32-bit
@@ -407,6 +536,84 @@ __global__ void __launch_bounds__(256) word_op_kernel(const uint64_t* in, const 
             }
         }
     }
+}
+
+// ---------------------------------------------------------------- the small Kmer / CanonicalKmer accessors, batched
+// naive_impl/mod.rs:40-50 on one byte: A/a 0, C/c 1, G/g 2, T/t 3, anything else u64::MAX (no guard in the *_u8 shifts)
+__device__ __forceinline__ uint64_t encode_binary_u8_dev(uint32_t c) {
+    const uint32_t u = c & 0xDFu;
+    return u == 'A' ? 0ull : (u == 'C' ? 1ull : (u == 'G' ? 2ull : (u == 'T' ? 3ull : ~0ull)));
+}
+// naive_impl/kmer.rs:76-102.  `mask` = intended MASK_TABLE[k] (all ones at k == 32).
+__device__ __forceinline__ uint64_t append_base_dev(uint64_t& data, uint64_t c, uint32_t k) {
+    const uint64_t r = data & 3ull;
+    data = (data >> 2) | (c << (2 * k - 2));
+    return r;
+}
+__device__ __forceinline__ uint64_t prepend_base_dev(uint64_t& data, uint64_t c, uint32_t k, uint64_t mask) {
+    const uint64_t r = (data >> (2 * k - 2)) & 3ull;
+    data = mask & ((data << 2) | c);
+    return r;
+}
+
+// OP 0: Kmer::sub_kmer_word (kmer.rs:150-161), a = pos, b_mask = MASK_TABLE[width]
+// OP 1: Kmer::append_base[_u8]   OP 2: Kmer::prepend_base[_u8]   (kmer.rs:76-102)  -> shifted word + the base shifted off
+// OP 3: CanonicalKmer::append_base[_u8]  OP 4: CanonicalKmer::prepend_base[_u8]  (canonical_kmer.rs:70-100): fw and rc words
+// OP 5: CanonicalKmer::is_fw_canonical (canonical_kmer.rs:67-69): fw < rc
+// bases: one per element -- 2-bit codes (Base) or, when ascii != 0, letters through encode_binary_u8
+template <int OP>
+__global__ void __launch_bounds__(256) kmer_shift_kernel(const uint64_t* __restrict__ fw_in, const uint64_t* __restrict__ rc_in,
+                                                         const uint8_t* __restrict__ bases, uint32_t ascii, uint64_t* __restrict__ fw_out,
+                                                         uint64_t* __restrict__ rc_out, uint8_t* __restrict__ out8, uint64_t n, uint32_t k,
+                                                         uint64_t mask, uint32_t a, uint64_t b_mask) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t fw = fw_in[i];
+    if (OP == 0) {
+        fw_out[i] = (fw >> (2 * a)) & b_mask;
+        return;
+    }
+    if (OP == 5) {
+        out8[i] = fw < rc_in[i] ? 1 : 0;
+        return;
+    }
+    const uint32_t raw = bases[i];
+    const uint64_t c = ascii ? encode_binary_u8_dev(raw) : (uint64_t)raw;
+    uint64_t r;
+    if (OP == 1) r = append_base_dev(fw, c, k);
+    if (OP == 2) r = prepend_base_dev(fw, c, k, mask);
+    if (OP == 3 || OP == 4) {
+        uint64_t rc = rc_in[i];
+        const uint64_t cb = 3ull - c;  // complement_base (naive_impl/mod.rs:81-84); wraps like a release build for an invalid byte
+        if (OP == 3) { r = append_base_dev(fw, c, k); prepend_base_dev(rc, cb, k, mask); }
+        else { r = prepend_base_dev(fw, c, k, mask); append_base_dev(rc, cb, k); }
+        if (rc_out) rc_out[i] = rc;
+    }
+    if (fw_out) fw_out[i] = fw;
+    if (out8) out8[i] = (uint8_t)r;
+}
+
+// kmer::Kmer<P,K,B>::get (kmer.rs:46-48): the 2-bit field `index` of every [P; B] array (byte image)
+__global__ void __launch_bounds__(256) kmer_get_kernel(const uint8_t* __restrict__ in, uint64_t n_items, uint32_t item_bytes, uint32_t index,
+                                                       uint8_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    out[i] = (in[i * item_bytes + (index >> 2)] >> (2 * (index & 3u))) & 3u;
+}
+// kmer::Kmer<P,K,B>::get_prefix (kmer.rs:50-52): bits 0 ..= 2 len of the array -- 2 len + 1 bits, the reference's inclusive
+// range -- as one word of P (word_bytes bytes, little endian); one thread per output byte
+__global__ void __launch_bounds__(256) kmer_get_prefix_kernel(const uint8_t* __restrict__ in, uint64_t n_items, uint32_t item_bytes,
+                                                              uint32_t word_bytes, uint32_t n_bits, uint8_t* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items * word_bytes) return;
+    const uint64_t i = t / word_bytes;
+    const uint32_t b = (uint32_t)(t - i * word_bytes);
+    uint32_t v = 0;
+    if (8 * b < n_bits) {
+        v = in[i * item_bytes + b];
+        if (n_bits - 8 * b < 8) v &= (1u << (n_bits - 8 * b)) - 1u;
+    }
+    out[t] = (uint8_t)v;
 }
 
 // per-read window / word counts for the CSR prefix sums

@@ -227,7 +227,7 @@ __device__ __forceinline__ void defer(uint32_t li) {
 // the three handlers (single: once per window).  Two-phase engines (compaction) first count the valid windows of
 // every item, scan the counts CTA-wide, then emit at the scanned offsets.
 template <class Eng, class Item>
-__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item) {
+__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item, bool last_pass = true) {
     constexpr uint32_t kAll = (uint32_t)Eng::Shape::kSpanSlots;
     // Two-phase engines cannot put their dirty items off to a second sweep (their output order is fixed by the scan), so
     // they run every item through the checking variant: a few instructions per window instead of both variants per warp.
@@ -263,6 +263,7 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
         eng.scan(n_items);
         __syncthreads();
         if (Eng::kCountOnly) return;
+        eng.place(last_pass);  // where this CTA's entries start in the output (decoupled look-back over the earlier tiles)
         for_each_item<true>(n_items, [&](uint32_t li) { item(li, emit_one, emit_two, emit_single); },
                             [&](uint32_t q_round) { eng.round_end(q_round, n_items); });
     } else {
@@ -471,7 +472,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
                 }
             }
         };
-        run_pass(eng, tile, K, n_items, item);
+        run_pass(eng, tile, K, n_items, item, ps.slot_hi == slot_end);
         __syncthreads();  // the next pass overwrites the tile
         cur = ps.slot_hi;
         r_cur = ps.r_hi;

@@ -125,6 +125,45 @@ __attribute__((target("avx512f,avx512bw,bmi2"))) void pack_avx512(const uint8_t*
     if (n_bases % 64) pack_swar(src + 64 * blocks, n_bases % 64, bits + 4 * blocks, inv + 4 * blocks);
 }
 
+// ---------------------------------------------------------------- AVX-512BW + GFNI: 64 bases per iteration, no mask round trip
+// The 2-bit code is a GF(2)-linear function of the byte (low = bit1 ^ bit2, high = bit2): one GF2P8AFFINEQB yields it in
+// every byte; two multiply-adds (x1,x4 then x1,x16) fold four codes into one byte, VPMOVDB compacts the 16 bytes.
+__attribute__((target("avx512f,avx512bw,gfni"), always_inline)) inline void pack64_gfni(const uint8_t* src, uint32_t* bits, uint16_t* inv,
+                                                                                      const __m512i table, const __m512i aff, const __m512i mul4,
+                                                                                      const __m512i mul16, const __m512i m0f, const __m512i mdf) {
+    const __m512i v = _mm512_loadu_si512(src);
+    const __m512i code = _mm512_gf2p8affine_epi64_epi8(v, aff, 0);
+    const __m512i nib = _mm512_maddubs_epi16(code, mul4);   // c0 + 4 c1 per 16-bit lane
+    const __m512i byt = _mm512_madd_epi16(nib, mul16);      // + 16 (c2 + 4 c3) per 32-bit lane
+    const __m128i packed = _mm512_cvtepi32_epi8(byt);
+    const __m512i expect = _mm512_shuffle_epi8(table, _mm512_and_si512(v, m0f));
+    const uint64_t bad = ~(uint64_t)_mm512_cmpeq_epi8_mask(expect, _mm512_and_si512(v, mdf));
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(bits), packed);
+    std::memcpy(inv, &bad, 8);
+}
+
+__attribute__((target("avx512f,avx512bw,gfni"))) void pack_gfni(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv) {
+    const __m512i table = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
+    // output bit i of every byte = parity(row[7 - i] & byte): bit 0 <- bits 1,2 (0x06); bit 1 <- bit 2 (0x04)
+    const __m512i aff = _mm512_set1_epi64((long long)((0x06ull << 56) | (0x04ull << 48)));
+    const __m512i mul4 = _mm512_set1_epi16(0x0401), mul16 = _mm512_set1_epi32(0x00100001);
+    const __m512i m0f = _mm512_set1_epi8(0x0F), mdf = _mm512_set1_epi8((char)0xDF);
+    constexpr size_t kStreams = 4;  // see pack_avx512
+    size_t done = 0;
+    if (n_bases >= 64 * 1024) {
+        const size_t per = n_bases / kStreams / 64;
+        for (size_t b = 0; b < per; ++b)
+            for (size_t s = 0; s < kStreams; ++s) {
+                const size_t blk = s * per + b;
+                pack64_gfni(src + 64 * blk, bits + 4 * blk, inv + 4 * blk, table, aff, mul4, mul16, m0f, mdf);
+            }
+        done = kStreams * per;
+    }
+    const size_t blocks = n_bases / 64;
+    for (size_t b = done; b < blocks; ++b) pack64_gfni(src + 64 * b, bits + 4 * b, inv + 4 * b, table, aff, mul4, mul16, m0f, mdf);
+    if (n_bases % 64) pack_swar(src + 64 * blocks, n_bases % 64, bits + 4 * blocks, inv + 4 * blocks);
+}
+
 using PackFn = void (*)(const uint8_t*, size_t, uint32_t*, uint16_t*);
 struct Choice {
     PackFn fn;
@@ -136,15 +175,17 @@ Choice choose(int which) {
     const bool bmi2 = __builtin_cpu_supports("bmi2");
     const bool avx2 = bmi2 && __builtin_cpu_supports("avx2");
     const bool avx512 = bmi2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
-    if ((which == 0 || which == 3) && avx512) return {pack_avx512, "avx512bw"};
-    if ((which == 0 || which == 2 || which == 3) && avx2) return {pack_avx2, "avx2"};
+    const bool gfni = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("gfni");
+    if ((which == 0 || which == 4) && gfni) return {pack_gfni, "avx512gfni"};
+    if ((which == 0 || which == 3 || which == 4) && avx512) return {pack_avx512, "avx512bw"};
+    if ((which == 0 || which == 2 || which == 3 || which == 4) && avx2) return {pack_avx2, "avx2"};
     return {pack_swar, "swar"};
 }
 std::atomic<int> g_forced{0};
 int env_isa() {  // KMB_HOST_PACK_ISA=swar|avx2|avx512bw caps the implementation (tests run every variant)
     const char* e = getenv("KMB_HOST_PACK_ISA");
     if (!e) return 0;
-    return !strcmp(e, "swar") ? 1 : (!strcmp(e, "avx2") ? 2 : (!strcmp(e, "avx512bw") ? 3 : 0));
+    return !strcmp(e, "swar") ? 1 : (!strcmp(e, "avx2") ? 2 : (!strcmp(e, "avx512bw") ? 3 : (!strcmp(e, "avx512gfni") ? 4 : 0)));
 }
 Choice current() {
     static const Choice best = choose(env_isa());
@@ -158,7 +199,7 @@ void pack_ascii(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* in
     if (n_bases) current().fn(src, n_bases, bits, inv);
 }
 const char* pack_isa() { return current().name; }
-void pack_force_isa(int which) { g_forced.store(which < 0 || which > 3 ? 0 : which, std::memory_order_relaxed); }
+void pack_force_isa(int which) { g_forced.store(which < 0 || which > 4 ? 0 : which, std::memory_order_relaxed); }
 
 namespace {
 __attribute__((target("avx2"))) uint64_t read_all_avx2(const uint8_t* p, size_t n) {

@@ -16,11 +16,11 @@
 namespace kmbhost {
 
 // Pack n_bases ASCII bytes.  bits / inv receive ceil(n_bases / 16) entries; in the last, partial entry the missing
-// bases read as code 0 / invalid.  Dispatches once to AVX-512BW+BMI2, AVX2+BMI2 or a portable SWAR loop.
+// bases read as code 0 / invalid.  Dispatches once to AVX-512BW+GFNI, AVX-512BW+BMI2, AVX2+BMI2 or a portable loop.
 void pack_ascii(const uint8_t* src, size_t n_bases, uint32_t* bits, uint16_t* inv);
-// which implementation pack_ascii resolved to: "avx512bw", "avx2" or "swar"
+// which implementation pack_ascii resolved to: "avx512gfni", "avx512bw", "avx2" or "swar"
 const char* pack_isa();
-// force an implementation (tests): 0 = best available, 1 = swar, 2 = avx2 (if supported), 3 = avx512 (if supported)
+// force an implementation (tests): 0 = best available, 1 = swar, 2 = avx2, 3 = avx512bw, 4 = avx512gfni (if supported)
 void pack_force_isa(int which);
 
 // Fixed-size pool of worker threads with a FIFO of jobs; the pipelined host path hands it pack / copy jobs.

@@ -45,14 +45,8 @@ struct kmb_ctx {
 
     uint64_t* d_first_read = nullptr;  // per-CTA first read of the CSR kernels
     size_t first_read_cap = 0;
-    unsigned long long* d_cta_counts = nullptr;  // compaction: valid windows per CTA / their scan
+    unsigned long long* d_cta_counts = nullptr;  // compaction: per-tile look-back descriptors, ticket, total
     size_t cta_counts_cap = 0;
-    // a counting call (all outputs NULL) leaves its scan for the emit call that follows it (same k / flags / representation,
-    // batch owned by the context so that nobody can have changed the bases in between); used once
-    bool compact_ready = false, compact_packed = false;
-    uint32_t compact_k = 0, compact_flags = 0;
-    unsigned compact_grid = 0;
-    uint64_t compact_total = 0;
 
     // scratch
     unsigned long long* d_digest = nullptr;  // 3 words (+1 spare)

@@ -1,4 +1,4 @@
-// kmb_tu_compact.cu -- instantiates the compaction engines (count pass, emit pass) on both geometries.
+// kmb_tu_compact.cu -- instantiates the compaction engines (sizing count; single-pass emit) on both geometries.
 #include "kmb_launch.h"
 
 namespace kmb {
@@ -37,10 +37,11 @@ cudaError_t launch_compact(bool count_only, bool validate, bool khi, const Fixed
 
 // Reads without a window (shorter than k) open no entry: their emit offset is that of the next read that has
 // windows (or the total).  win_offsets[r + 1] == win_offsets[r] identifies them.
-__global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_emitted,
-                                                               uint64_t* emit_offsets) {
+__global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* win_offsets, uint64_t n_reads,
+                                                               const unsigned long long* total_emitted_ptr, uint64_t* emit_offsets) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
+    const uint64_t total_emitted = *total_emitted_ptr;
     if (win_offsets[r + 1] != win_offsets[r]) return;
     // first read after r whose window offset exceeds win_offsets[r] - 1 ... i.e. first r' > r with windows
     uint64_t lo = r + 1, hi = n_reads;  // answer in [lo, hi]; n_reads = none
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* w
     emit_offsets[r] = lo < n_reads ? emit_offsets[lo] : total_emitted;
 }
 
-cudaError_t launch_compact_backfill(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_emitted, uint64_t* emit_offsets,
+cudaError_t launch_compact_backfill(const uint64_t* win_offsets, uint64_t n_reads, const unsigned long long* total_emitted, uint64_t* emit_offsets,
                                     cudaStream_t st) {
     compact_backfill_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(win_offsets, n_reads, total_emitted, emit_offsets);
     return cudaGetLastError();

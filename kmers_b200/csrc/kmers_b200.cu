@@ -209,7 +209,6 @@ static bool make_enc(int32_t enc, EncDesc* d, uint32_t* dec_letters) {
 
 // ======================================================================= batch
 static void drop_batch(kmb_ctx* ctx) {
-    ctx->compact_ready = false;
     ctx->have_batch = false;
     ctx->win_valid = false;
     ctx->d_bases = nullptr;
@@ -720,57 +719,51 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     }
     const FixedGeom* pf = csr ? nullptr : &fg;
     const CsrGeom* pc = csr ? &cg : nullptr;
-    if ((rc = grow(ctx, (void**)&ctx->d_cta_counts, &ctx->cta_counts_cap, ((size_t)l.grid + 1) * 8))) return rc;
+    // device words behind the launch: [grid look-back descriptors | ticket | total], zeroed before every launch
+    if ((rc = grow(ctx, (void**)&ctx->d_cta_counts, &ctx->cta_counts_cap, ((size_t)l.grid + 2) * 8))) return rc;
+    unsigned long long* d_ticket = ctx->d_cta_counts + l.grid;
+    unsigned long long* d_total = d_ticket + 1;
     CompactParams ep{};
     ep.wc = make_winconst(k, enc);
-    ep.out.cta_counts = ctx->d_cta_counts;
+    ep.out.desc = ctx->d_cta_counts; ep.out.ticket = d_ticket; ep.out.total = d_total;
     const bool counting_call = !canon_out && !hash_out && !pos_out && !emit_offsets_out;
-    const bool owned = ctx->d_bases == ctx->own_bases || ctx->d_bases == (const uint8_t*)ctx->own_packed;
-    uint64_t total;
-    if (!counting_call && ctx->compact_ready && ctx->compact_k == k && ctx->compact_flags == flags && ctx->compact_grid == l.grid &&
-        ctx->compact_packed == ctx->packed) {
-        total = ctx->compact_total;  // the counting call just before this one already left the scan in d_cta_counts
-    } else {
-        CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 1) * 8, ctx->stream));
-        // launch 1: valid windows per CTA, then their exclusive scan (entry [grid] becomes the total)
+    if (counting_call) {
+        // sizing: count only (reads the bases, writes nothing but the total)
+        CK(ctx, cudaMemsetAsync(d_total, 0, 8, ctx->stream));
         CK(ctx, launch_compact(true, validate, khi, pf, pc, l, ctx->stream, enc, ep));
         ctx->launches++;
-        size_t need = 0;
-        CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
-        if ((rc = grow(ctx, &ctx->d_cub, &ctx->cub_cap, need))) return rc;
-        CK(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub, need, ctx->d_cta_counts, ctx->d_cta_counts, (long long)l.grid + 1, ctx->stream));
-        ctx->launches++;
-        CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        total = ctx->h_digest[3];
-    }
-    ctx->compact_ready = false;
-    *n_emitted = total;
-    if (counting_call) {
-        if (owned) {
-            ctx->compact_ready = true; ctx->compact_k = k; ctx->compact_flags = flags; ctx->compact_grid = l.grid; ctx->compact_total = total;
-            ctx->compact_packed = ctx->packed;
-        }
+        *n_emitted = ctx->h_digest[3];
         return KMB_OK;
     }
-    if (total > capacity) return fail(ctx, KMB_ERR_INVALID_ARG, "capacity %llu < %llu emitted k-mers", (unsigned long long)capacity,
-                                      (unsigned long long)total);
+    // ONE launch: stage, count from the staged masks, look back over the earlier tiles, emit.  The arrays may be sized by a
+    // counting call or simply hold the worst case (one entry per slot); nothing is written at or beyond `capacity`.
+    const uint64_t cap = capacity < n_slots ? capacity : n_slots;
     OutBuf oc, oh, op;
-    if ((rc = out_prepare(ctx, 0, canon_out, total * 8, &oc))) return rc;
-    if ((rc = out_prepare(ctx, 1, hash_out, total * 8, &oh))) return rc;
-    if ((rc = out_prepare(ctx, 2, pos_out, total * 4, &op))) return rc;
+    if ((rc = out_prepare(ctx, 0, canon_out, cap * 8, &oc))) return rc;
+    if ((rc = out_prepare(ctx, 1, hash_out, cap * 8, &oh))) return rc;
+    if ((rc = out_prepare(ctx, 2, pos_out, cap * 4, &op))) return rc;
     ep.out.canon = (uint64_t*)oc.dev; ep.out.hash = (uint64_t*)oh.dev; ep.out.pos = (int32_t*)op.dev;
     ep.out.emit_offsets = (uint64_t*)oe.dev;
-    // launch 2: emit at the scanned offsets
+    ep.out.capacity = cap;
+    CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 2) * 8, ctx->stream));
     CK(ctx, launch_compact(false, validate, khi, pf, pc, l, ctx->stream, enc, ep));
     ctx->launches++;
     if (oe.dev) {
-        CK(ctx, cudaMemcpyAsync((uint64_t*)oe.dev + ctx->n_reads, ctx->d_cta_counts + l.grid, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync((uint64_t*)oe.dev + ctx->n_reads, d_total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (csr) {
-            CK(ctx, launch_compact_backfill(ctx->d_win_offsets, ctx->n_reads, total, (uint64_t*)oe.dev, ctx->stream));
+            CK(ctx, launch_compact_backfill(ctx->d_win_offsets, ctx->n_reads, d_total, (uint64_t*)oe.dev, ctx->stream));
             ctx->launches++;
         }
     }
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t total = ctx->h_digest[3];
+    *n_emitted = total;
+    if (total > capacity) return fail(ctx, KMB_ERR_INVALID_ARG, "capacity %llu < %llu emitted k-mers", (unsigned long long)capacity,
+                                      (unsigned long long)total);
+    oc.bytes = oc.host ? total * 8 : 0; oh.bytes = oh.host ? total * 8 : 0; op.bytes = op.host ? total * 4 : 0;  // only what was emitted goes back
     if ((rc = out_finish(ctx, oc)) || (rc = out_finish(ctx, oh)) || (rc = out_finish(ctx, op)) || (rc = out_finish(ctx, oe))) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return KMB_OK;
@@ -941,9 +934,6 @@ static int32_t set_packed(kmb_ctx* ctx, const uint64_t* d_words, uint64_t n_word
         ctx->launches++;
         ctx->d_base_starts = ctx->own_base_starts;
     }
-    // the batch changes representation: cached per-CTA compaction counts (taken with validation on the ASCII bytes) and the
-    // window-offset geometry they belong to no longer describe it
-    ctx->compact_ready = false;
     ctx->d_bases = (const uint8_t*)d_words;
     ctx->n_bytes = n_words * 8;
     ctx->n_bases_flat = n_words * 32;
@@ -1431,7 +1421,18 @@ static int32_t unpack_impl(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, con
     if (rc) return rc;
     OutBuf ob;
     if ((rc = out_prepare(ctx, 0, bases_out, n_items * bases_per_item, &ob))) return rc;
-    if (bases_per_item <= (uint32_t)kUnpackTile) {
+    if (bases_per_item <= (uint32_t)kUnpackTile && ((uintptr_t)d_in & 3u) == 0 && !getenv("KMB_UNPACK_TILE")) {
+        // output-space kernel: one aligned 16-byte block of text per thread step, four letters per PRMT
+        const uint64_t total = n_items * bases_per_item;
+        const uint64_t n_blocks = (((uintptr_t)ob.dev & 15u) + total + 15) / 16;
+        const uint64_t ctas = (n_blocks + 256 * kUnpackBlocksPerThread - 1) / (256 * kUnpackBlocksPerThread);
+        if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+        const uint32_t magic = bases_per_item > 1 ? (uint32_t)((1ull << 32) / bases_per_item + 1) : 0u;
+        const uint64_t magic64 = bases_per_item > 1 ? ~0ull / bases_per_item + 1 : 0ull;  // exact while letters * bases_per_item < 2^64
+        unpack_flat_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items * in_bytes_per_item, n_items,
+                                                                   (uint32_t)in_bytes_per_item, bases_per_item, magic, magic64, dec,
+                                                                   (uint8_t*)ob.dev, total, n_blocks);
+    } else if (bases_per_item <= (uint32_t)kUnpackTile) {
         // staged through shared memory: aligned 16-byte stores whatever the item length
         const uint32_t ipc = (uint32_t)kUnpackTile / bases_per_item;
         const uint64_t ctas = (n_items + ipc - 1) / ipc;
@@ -1534,4 +1535,140 @@ extern "C" int32_t kmb_match_words(kmb_ctx* ctx, uint32_t k, const uint64_t* wor
                                    uint8_t* match_out, uint64_t n) {
     if (ctx && n && (!others || !match_out)) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
     return word_op<3>(ctx, k, words, others, nullptr, match_out, n);
+}
+
+// ======================================================================= small Kmer / CanonicalKmer accessors, batched
+template <int OP>
+static int32_t shift_op(kmb_ctx* ctx, uint32_t k, const uint64_t* fw_in, const uint64_t* rc_in, const uint8_t* bases, int32_t ascii,
+                        uint64_t* fw_out, uint64_t* rc_out, uint8_t* out8, uint64_t n, uint32_t a, uint64_t b_mask) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (k < 1 || k > 32) return fail(ctx, KMB_ERR_PANIC, "k = %u: kmers longer than 32 bases not supported (and k >= 1)", k);
+    if (n == 0) return KMB_OK;
+    if (!fw_in) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL input");
+    const void *d_fw, *d_rc = nullptr, *d_bases = nullptr;
+    int32_t rc = in_prepare(ctx, 2, fw_in, n * 8, &d_fw);
+    if (rc) return rc;
+    if (rc_in && (rc = in_prepare(ctx, 3, rc_in, n * 8, &d_rc))) return rc;
+    OutBuf o_fw, o_rc, o8;
+    if ((rc = out_prepare(ctx, 0, fw_out, n * 8, &o_fw))) return rc;
+    if ((rc = out_prepare(ctx, 1, rc_out, n * 8, &o_rc))) return rc;
+    // bases (n bytes in) and the u8 output share one scratch block when both live on the host: [bases | out8]
+    uint8_t* d_o8 = out8;
+    const bool bases_host = bases && !is_device_ptr(bases), o8_host = out8 && !is_device_ptr(out8);
+    if (bases_host || o8_host) {
+        void* blk = nullptr;
+        CK(ctx, cudaMallocAsync(&blk, 2 * n + 16, ctx->stream));
+        if (bases_host) { rc = stage_h2d(ctx, blk, bases, n); d_bases = blk; }
+        if (o8_host) d_o8 = (uint8_t*)blk + n;
+        if (rc) { cudaFreeAsync(blk, ctx->stream); return rc; }
+        o8.user = blk;  // remembered for the release below
+    }
+    if (bases && !bases_host) d_bases = bases;
+    const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const uint64_t ctas = (n + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    kmer_shift_kernel<OP><<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint64_t*)d_fw, (const uint64_t*)d_rc, (const uint8_t*)d_bases,
+                                                                  (uint32_t)(ascii != 0), (uint64_t*)o_fw.dev, (uint64_t*)o_rc.dev, d_o8, n, k,
+                                                                  mask, a, b_mask);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, o_fw)) || (rc = out_finish(ctx, o_rc))) return rc;
+    if (o8_host) CK(ctx, cudaMemcpyAsync(out8, d_o8, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o8.user) CK(ctx, cudaFreeAsync(o8.user, ctx->stream));
+    if (o_fw.host || o_rc.host || o8_host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_sub_kmer_words(kmb_ctx* ctx, uint32_t k, uint32_t pos, uint32_t width, const uint64_t* in, uint64_t* out, uint64_t n) {
+    // assert!(pos < k); assert!(pos + width <= k);  (naive_impl/kmer.rs:155-157)
+    if (ctx && !(pos < k && pos + width <= k)) return fail(ctx, KMB_ERR_PANIC, "sub_kmer: need pos < k and pos + width <= k (k=%u pos=%u width=%u)", k, pos, width);
+    if (ctx && n && !out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL output");
+    const uint64_t wmask = width >= 32 ? ~0ull : ((1ull << (2 * width)) - 1ull);  // intended MASK_TABLE[width] (SURVEY Q1 at 32)
+    return shift_op<0>(ctx, k, in, nullptr, nullptr, 0, out, nullptr, nullptr, n, pos, wmask);
+}
+extern "C" int32_t kmb_append_base_words(kmb_ctx* ctx, uint32_t k, const uint64_t* in, const uint8_t* bases, int32_t bases_are_ascii,
+                                         uint64_t* out, uint8_t* dropped_out, uint64_t n) {
+    if (ctx && n && !bases) return fail(ctx, KMB_ERR_INVALID_ARG, "bases is NULL");
+    return shift_op<1>(ctx, k, in, nullptr, bases, bases_are_ascii, out, nullptr, dropped_out, n, 0, 0);
+}
+extern "C" int32_t kmb_prepend_base_words(kmb_ctx* ctx, uint32_t k, const uint64_t* in, const uint8_t* bases, int32_t bases_are_ascii,
+                                          uint64_t* out, uint8_t* dropped_out, uint64_t n) {
+    if (ctx && n && !bases) return fail(ctx, KMB_ERR_INVALID_ARG, "bases is NULL");
+    return shift_op<2>(ctx, k, in, nullptr, bases, bases_are_ascii, out, nullptr, dropped_out, n, 0, 0);
+}
+extern "C" int32_t kmb_canonical_append_base_words(kmb_ctx* ctx, uint32_t k, const uint64_t* fw_in, const uint64_t* rc_in, const uint8_t* bases,
+                                                   int32_t bases_are_ascii, uint64_t* fw_out, uint64_t* rc_out, uint8_t* dropped_out, uint64_t n) {
+    if (ctx && n && (!bases || !rc_in)) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    return shift_op<3>(ctx, k, fw_in, rc_in, bases, bases_are_ascii, fw_out, rc_out, dropped_out, n, 0, 0);
+}
+extern "C" int32_t kmb_canonical_prepend_base_words(kmb_ctx* ctx, uint32_t k, const uint64_t* fw_in, const uint64_t* rc_in, const uint8_t* bases,
+                                                    int32_t bases_are_ascii, uint64_t* fw_out, uint64_t* rc_out, uint8_t* dropped_out, uint64_t n) {
+    if (ctx && n && (!bases || !rc_in)) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    return shift_op<4>(ctx, k, fw_in, rc_in, bases, bases_are_ascii, fw_out, rc_out, dropped_out, n, 0, 0);
+}
+extern "C" int32_t kmb_is_fw_canonical_words(kmb_ctx* ctx, const uint64_t* fw, const uint64_t* rc, uint8_t* out, uint64_t n) {
+    if (ctx && n && (!rc || !out)) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    return shift_op<5>(ctx, 1, fw, rc, nullptr, 0, nullptr, nullptr, out, n, 0, 0);
+}
+
+extern "C" int32_t kmb_kmer_get(kmb_ctx* ctx, uint32_t word_bits, uint32_t words_per_item, const void* arrays, uint64_t n_items, uint32_t index,
+                                uint8_t* codes_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (!word_bits_ok(word_bits) || words_per_item < 1) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128 and words_per_item >= 1");
+    const uint64_t item_bytes = (uint64_t)words_per_item * (word_bits / 8);
+    // BitArray::get_bits asserts the range lies inside the array (bit_field 0.10)
+    if (2ull * index + 1 >= item_bytes * 8) return fail(ctx, KMB_ERR_PANIC, "get(%u): beyond the %llu bits of the array", index, (unsigned long long)(item_bytes * 8));
+    if (n_items == 0) return KMB_OK;
+    if (!arrays || !codes_out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    const void* d_in;
+    int32_t rc = in_prepare(ctx, 1, arrays, n_items * item_bytes, &d_in);
+    if (rc) return rc;
+    OutBuf ob;
+    if ((rc = out_prepare(ctx, 0, codes_out, n_items, &ob))) return rc;
+    const uint64_t ctas = (n_items + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    kmer_get_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items, (uint32_t)item_bytes, index, (uint8_t*)ob.dev);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_kmer_get_prefix(kmb_ctx* ctx, uint32_t word_bits, uint32_t words_per_item, const void* arrays, uint64_t n_items, uint32_t len,
+                                       void* words_out) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    if (!word_bits_ok(word_bits) || words_per_item < 1) return fail(ctx, KMB_ERR_INVALID_ARG, "word_bits must be 8/16/32/64/128 and words_per_item >= 1");
+    const uint64_t item_bytes = (uint64_t)words_per_item * (word_bits / 8);
+    const uint64_t n_bits = 2ull * len + 1;  // 0..=(len*2): the reference's inclusive range (kmer.rs:51)
+    // get_bits asserts the range fits one P and lies inside the array
+    if (n_bits > word_bits || n_bits > item_bytes * 8)
+        return fail(ctx, KMB_ERR_PANIC, "get_prefix(%u): %llu bits do not fit a u%u / the array", len, (unsigned long long)n_bits, word_bits);
+    if (n_items == 0) return KMB_OK;
+    if (!arrays || !words_out) return fail(ctx, KMB_ERR_INVALID_ARG, "NULL pointer");
+    const void* d_in;
+    int32_t rc = in_prepare(ctx, 1, arrays, n_items * item_bytes, &d_in);
+    if (rc) return rc;
+    const uint32_t word_bytes = word_bits / 8;
+    OutBuf ob;
+    if ((rc = out_prepare(ctx, 0, words_out, n_items * word_bytes, &ob))) return rc;
+    const uint64_t ctas = (n_items * word_bytes + 255) / 256;
+    if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
+    kmer_get_prefix_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>((const uint8_t*)d_in, n_items, (uint32_t)item_bytes, word_bytes, (uint32_t)n_bits,
+                                                                   (uint8_t*)ob.dev);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = out_finish(ctx, ob))) return rc;
+    if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// kmer.rs:71-91: always A0 C1 G2 T3, upper case, whatever encoder produced the word
+extern "C" int32_t kmb_bitmer_to_bytes(kmb_ctx* ctx, uint32_t len, const uint64_t* mers, uint64_t n, uint8_t* bases_out) {
+    NEED_CTX(ctx);
+    if (len > 32) return fail(ctx, KMB_ERR_INVALID_ARG, "len = %u: a u64 holds 32 bases", len);
+    return unpack_impl(ctx, KMB_ENC_ACGT, 64, mers, n, 1, len, bases_out, 0u);
 }

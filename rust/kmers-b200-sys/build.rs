@@ -1,11 +1,12 @@
 // UNVERIFIED SOURCE (no Rust toolchain in the build image).
-// Compiles the CUDA translation units (kmers_b200/csrc/*.cu) for sm_100a into one shared library and links it.
+// Compiles the translation units (kmers_b200/csrc/*.cu for sm_100a, *.cpp = the host packer, by nvcc's host compiler) into
+// one shared library and links it.
 use std::{env, path::PathBuf, process::Command};
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
     let mut srcs: Vec<PathBuf> = std::fs::read_dir(root.join("kmers_b200/csrc")).unwrap()
-        .map(|e| e.unwrap().path()).filter(|p| p.extension().map_or(false, |x| x == "cu")).collect();
+        .map(|e| e.unwrap().path()).filter(|p| p.extension().map_or(false, |x| x == "cu" || x == "cpp")).collect();
     srcs.sort();
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libkmers_b200.so");
@@ -14,6 +15,7 @@ fn main() {
         .args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
         .args(&srcs)
+        .args(["-ldl", "-lpthread"])
         .status()
         .expect("nvcc not runnable");
     assert!(status.success(), "nvcc failed");

@@ -19,7 +19,7 @@ torch.cuda.set_device(0)
 stream = torch.cuda.Stream()
 ctx = kb.Context(0, stream=stream.cuda_stream)
 i64 = lambda m: torch.empty(m, dtype=torch.int64, device="cuda")
-batch = ctx.generate(42, n, L, n_thresh20=1049 if what == "compact" else 0)
+batch = ctx.generate(42, n, L, n_thresh20=1049 if what.startswith("compact") else 0)
 W = L - K + 1
 n_slots = n * W
 if what == "csr_var":  # ragged reads of 100..150 bases cut from the same stream
@@ -62,6 +62,24 @@ elif what == "canon":
     alg = n * (L + W * 8)
     out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=None)
     step = lambda: batch.extract_canonical(K, out=out)
+elif what == "minword":
+    nk = 50_000_000
+    words = torch.randint(0, 2**62, (nk,), dtype=torch.int64, device="cuda")
+    mmw, mmo = torch.empty_like(words), torch.empty(nk, dtype=torch.int32, device="cuda")
+    alg = nk * 20
+    step = lambda: ctx._ck(ctx._lib.kmb_minimizer_words(ctx._h, 31, 15, 15, _ptr(words), nk, _ptr(mmw), _ptr(mmo)))
+elif what == "unpack":
+    ni = 25_000_000
+    words = torch.randint(0, 2**62, (ni,), dtype=torch.int64, device="cuda")
+    txt = torch.empty(ni * 31, dtype=torch.uint8, device="cuda")
+    alg = ni * (8 + 31)
+    step = lambda: ctx._ck(ctx._lib.kmb_unpack(ctx._h, kb.ENC_ACGT, 64, _ptr(words), ni, 1, 31, _ptr(txt)))
+elif what == "compact1":  # the single emit launch with worst-case arrays
+    import ctypes as C
+    alg = None
+    cc, ch, cp, ce = i64(n_slots), i64(n_slots), torch.empty(n_slots, dtype=torch.int32, device="cuda"), i64(n + 1)
+    cnt = C.c_uint64()
+    step = lambda: ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, K, 0, _ptr(cc), _ptr(ch), _ptr(cp), _ptr(ce), n_slots, C.byref(cnt)))
 elif what in ("pack8", "pack64"):
     alg = n * L + n * ((L + 31) // 32) * 8
     bits = int(what[4:])

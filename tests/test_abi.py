@@ -113,3 +113,27 @@ def test_static_shared_memory_leaves_room_for_the_tile():
             assert int(shared) <= 20 * 1024, (name, shared)   # + ~27 KiB of tile and offset tables
             checked += 1
     assert checked >= 40
+
+
+def test_rust_sys_matches_the_header():
+    """rust/kmers-b200-sys cannot be compiled here (no Rust toolchain), so its `extern "C"` block is GENERATED from the header
+    (scripts/gen_rust_sys.py) and this test fails when the committed file differs from a fresh generation: every entry
+    point of include/kmers_b200.h is declared, with the same arity and the pointer / integer types mapped one to one."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "scripts", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    hdr = open(os.path.join(ROOT, "include", "kmers_b200.h")).read()
+    cur = open(gen.LIB_RS).read()
+    assert gen.render(cur, gen.generate(hdr)) == cur, "run `python scripts/gen_rust_sys.py` after changing include/kmers_b200.h"
+    protos = gen.prototypes(hdr)
+    assert sorted(p[0] for p in protos) == _declared_symbols()
+    block = cur[cur.index(gen.BEGIN):cur.index(gen.END)]
+    for name, _, params in protos:
+        m = re.search(r"pub fn %s\((.*?)\)" % name, block)
+        assert m, name
+        assert (len(m.group(1).split(",")) if m.group(1).strip() else 0) == len(params), f"arity of {name}"
+    # the safe wrapper only calls functions the sys crate declares
+    wrapper = open(os.path.join(ROOT, "rust", "kmers-b200", "src", "lib.rs")).read()
+    for used in set(re.findall(r"sys::(kmb_[a-z0-9_]+)\(", wrapper)):
+        assert f"pub fn {used}(" in block, f"rust/kmers-b200 calls sys::{used}, which the header does not declare"

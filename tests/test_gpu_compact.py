@@ -128,8 +128,8 @@ def test_compact_capacity_and_empty(ctx):
 
 
 def test_counting_call_then_emit_reuses_counts(ctx):
-    """The sizing protocol (count with NULL outputs, then emit): the emit call may reuse the counting call's scan, but only
-    for the same k / flags and an unchanged, context-owned batch; anything in between must not leave stale counts."""
+    """The sizing protocol (count with NULL outputs, then emit) in every order: the emit call is self-contained (it counts
+    again from its staged tiles), so nothing a counting call left behind -- another k, another batch -- can leak into it."""
     import oracle as ko
     rng = np.random.default_rng(77)
     bases, _ = random_reads(rng, 3000, 150, 150, p_bad=0.01)
@@ -162,3 +162,60 @@ def test_counting_call_then_emit_reuses_counts(ctx):
     keep = r["canon"] != np.uint64(2**64 - 1)
     assert n2 == int(keep.sum()) and np.array_equal(c2, r["canon"][keep])
     assert n21 > n31
+
+
+def test_worst_case_capacity_needs_no_counting_call(ctx):
+    """Arrays that hold one entry per slot: a single emit call (one launch, decoupled look-back) returns the stream and its
+    length; thousands of tiles, so every look-back pattern (aggregate chains, prefixes, the 32-wide window) occurs."""
+    import torch
+    import oracle as ko
+    n, L, k = 400_000, 150, 31
+    W = L - k + 1
+    bases = ko.generate_bases(5, 0, n * L, n_thresh20=3000)
+    b = ctx.upload(bases, fixed_len=L)
+    cap = n * W
+    canon = torch.empty(cap, dtype=torch.int64, device="cuda")
+    hsh = torch.empty(cap, dtype=torch.int64, device="cuda")
+    pos = torch.empty(cap, dtype=torch.int32, device="cuda")
+    offs = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    m = C.c_uint64()
+    l0 = ctx.launch_count
+    ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, k, 0, canon.data_ptr(), hsh.data_ptr(), pos.data_ptr(), offs.data_ptr(), cap, C.byref(m)))
+    assert ctx.launch_count == l0 + 1  # ONE kernel: no counting launch, no scan launch
+    m = int(m.value)
+    ref = ko.extract_canonical(bases, k, n_reads=n, fixed_len=L, n_threads=8)
+    keep = ref["canon"] != np.uint64(2**64 - 1)
+    assert m == int(keep.sum()) == ref["n_valid"]
+    assert np.array_equal(canon[:m].cpu().numpy().view(np.uint64), ref["canon"][keep])
+    assert np.array_equal(hsh[:m].cpu().numpy().view(np.uint64), ref["hash"][keep])
+    assert np.array_equal(pos[:m].cpu().numpy(), np.tile(np.arange(W, dtype=np.int32), n)[keep])
+    per_read = keep.reshape(n, W).sum(axis=1)
+    want_offs = np.zeros(n + 1, dtype=np.uint64)
+    want_offs[1:] = np.cumsum(per_read)
+    assert np.array_equal(offs.cpu().numpy().view(np.uint64), want_offs)
+    # repeated launches reuse the descriptor array: it must be reset every time
+    for _ in range(3):
+        m2 = C.c_uint64()
+        ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, k, 0, canon.data_ptr(), None, None, None, cap, C.byref(m2)))
+        assert int(m2.value) == m
+    assert np.array_equal(canon[:m].cpu().numpy().view(np.uint64), ref["canon"][keep])
+
+
+def test_count_then_repack_then_emit(ctx):
+    """A counting call on the ASCII batch (validation on), then the batch is switched to the packed store without
+    validation (every window becomes valid), then the emit call: it must describe the batch as it is NOW."""
+    rng = np.random.default_rng(3)
+    n, L, k = 2000, 150, 31
+    bases, _ = random_reads(rng, n, L, L, p_bad=0.02)
+    b = ctx.upload(bases, fixed_len=L)
+    m = C.c_uint64()
+    ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, k, 0, None, None, None, None, 0, C.byref(m)))
+    n_ascii = int(m.value)
+    assert n_ascii < n * (L - k + 1)
+    b.to_packed(strict=False)
+    cap = n * (L - k + 1)
+    canon = np.zeros(cap, dtype=np.uint64)
+    ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, k, 0, canon.ctypes.data, None, None, None, cap, C.byref(m)))
+    assert int(m.value) == cap  # a packed store holds no invalid base: every window is emitted, and none beyond the arrays
+    dense = b.extract_canonical(k, to="host")
+    assert np.array_equal(canon, dense.canon)

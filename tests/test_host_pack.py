@@ -62,10 +62,10 @@ def test_matches_seqvector_words(kb):
 
 
 def test_isa_is_reported(kb):
-    assert kb.host_pack_isa() in ("avx512bw", "avx2", "swar")
+    assert kb.host_pack_isa() in ("avx512gfni", "avx512bw", "avx2", "swar")
 
 
-@pytest.mark.parametrize("isa", ["swar", "avx2", "avx512bw"])
+@pytest.mark.parametrize("isa", ["swar", "avx2", "avx512bw", "avx512gfni"])
 def test_every_simd_variant_agrees(kb, isa):
     """Each implementation (capped through KMB_HOST_PACK_ISA in a fresh process) gives the reference bytes."""
     import os
@@ -84,4 +84,5 @@ def test_every_simd_variant_agrees(kb, isa):
     rb, ri = _reference(b)
     assert (int(out[1]), int(out[2])) == (int(rb.astype(np.uint64).sum()), int(ri.astype(np.uint64).sum()))
     # the variant that ran is the requested one, or the best this CPU has below it
-    assert out[0] in {"swar": ("swar",), "avx2": ("avx2", "swar"), "avx512bw": ("avx512bw", "avx2", "swar")}[isa]
+    assert out[0] in {"swar": ("swar",), "avx2": ("avx2", "swar"), "avx512bw": ("avx512bw", "avx2", "swar"),
+                      "avx512gfni": ("avx512gfni", "avx512bw", "avx2", "swar")}[isa]
