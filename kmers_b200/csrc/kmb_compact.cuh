@@ -10,6 +10,7 @@
 // the earlier tiles (single-pass chained scan: every tile publishes {aggregate | inclusive prefix} in one 64-bit
 // descriptor; tiles are handed out by an atomic ticket so a tile only ever waits for tiles that are already running),
 // and stores each valid window at its final index.  COUNT_ONLY (the sizing call) just adds up the CTA totals.
+// emit_offsets are written tile-local by the kernel and shifted by the tiles' starts afterwards (compact_fixup_kernel).
 #pragma once
 #include <cstddef>
 
@@ -26,6 +27,7 @@ struct CompactOut {
     unsigned long long* ticket;          // next tile to hand out (zeroed before the launch)
     unsigned long long* total;           // COUNT_ONLY: += every CTA's count; emit: the last tile stores the grand total
     uint64_t capacity;                   // entries the output arrays hold: nothing is written at or beyond it
+    uint32_t vec16;                      // canon / hash are 16-byte aligned and pos 8-byte aligned: pairs leave as vectors
 };
 
 constexpr unsigned long long kDescAggregate = 1ull << 62, kDescPrefix = 2ull << 62, kDescValue = (1ull << 62) - 1;
@@ -44,6 +46,8 @@ struct CompactParams {
 };
 
 constexpr int kCompactRound = kExtractThreads * kRun;  // entries one round of items can emit (2048): 256 per warp
+constexpr int kCompactWarps = kExtractThreads / 32;
+constexpr int kWarpSlice = 32 * kRun;
 
 // Shared memory of the compaction kernels beyond the tile: per-item counts, and the staging buffers through which
 // a round's entries reach global memory as coalesced stores (each thread's <= 8 entries land at arbitrary,
@@ -55,10 +59,11 @@ struct CompactShared {
     uint32_t tile_id;                 // this CTA's ticket
     uint32_t lb_has[kExtractThreads / 32];          // look-back: warp w's window holds a tile that knows its prefix
     unsigned long long lb_sum[kExtractThreads / 32];  // ... and the values of its window up to that tile
-    // staging buffers of the emit launch; the counting launch allocates the struct only up to here (kCompactCountBytes)
-    // (no hash buffer: LexHash(canon) is one pair reversal, computed when the entry leaves -- cheaper than staging it)
-    alignas(16) uint64_t canon[kCompactRound];
-    int32_t pos[kCompactRound];
+    // staging buffers of the emit launch; the counting launch allocates the struct only up to here (kCompactCountBytes).
+    // One slice of kWarpSlice entries per warp: the 256 entries its 32 items can emit in a round.
+    alignas(16) uint64_t canon[kCompactWarps * kWarpSlice];
+    uint64_t hash[kCompactWarps * kWarpSlice];
+    int32_t pos[kCompactWarps * kWarpSlice];
 };
 constexpr size_t kCompactCountBytes = offsetof(CompactShared, canon);
 
@@ -77,6 +82,7 @@ struct CompactEng {
     uint64_t cta_base = 0;       // valid windows of all earlier tiles
     uint32_t tile_id = 0;
     bool placed = false;         // cta_base is known
+    bool final_pass = false;     // thread 0: the tile's last pass has been counted and published
 
     __device__ CompactEng(const CompactParams& params, CompactShared& shared) : p(params), sh(shared) {}
 
@@ -90,51 +96,60 @@ struct CompactEng {
         return tile_id;
     }
 
-    // After a pass's scan (pass_base = this CTA's count so far, incl. the pass).  Single-pass tiles -- all of them except
-    // CSR tiles whose reads are mostly shorter than k -- publish their aggregate, look back, publish their inclusive
-    // prefix.  A multi-pass tile looks back during its first pass without an aggregate to show (its successors wait) and
-    // publishes the inclusive prefix when its last pass has been counted.
-    __device__ __forceinline__ void place(bool last_pass) {
-        if (COUNT_ONLY) return;
+    // After a pass's scan (pass_base = this CTA's count so far, incl. the pass): tell the later tiles.  A tile whose start is
+    // not known yet publishes its aggregate (single-pass tiles: all of them except CSR tiles whose reads are mostly shorter
+    // than k; a multi-pass tile can only do so once its last pass is counted -- its successors wait); one that knows its
+    // start publishes the inclusive prefix.
+    __device__ __forceinline__ void publish(bool last_pass) {
+        if (COUNT_ONLY || !last_pass || threadIdx.x != 0) return;
         if (!placed) {
-            if (last_pass && threadIdx.x == 0 && tile_id > 0) desc_store(p.out.desc + tile_id, kDescAggregate | pass_base);
-            // Look-back, the whole CTA at once: thread i reads the descriptor of tile (tile_id - 1 - i), so one round covers
-            // kExtractThreads predecessors with a single global-load latency (a warp-wide window needs a round per 32 tiles,
-            // and with ~600 tiles in flight the nearest tile that already knows its prefix is often 100+ tiles back).
-            const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-            unsigned long long excl = 0;
-            int64_t idx = (int64_t)tile_id - 1;
-            for (;;) {  // CTA-uniform
-                if (idx < 0) break;
-                const int64_t mine = idx - (int64_t)threadIdx.x;
-                unsigned long long d = kDescPrefix;  // before tile 0: "prefix 0"
-                if (mine >= 0) {
-                    do { d = desc_load(p.out.desc + mine); } while ((d >> 62) == 0ull);
-                }
-                const unsigned pf = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-                // value of this warp's window up to (and including) its nearest prefix holder
-                const unsigned upto = pf ? (unsigned)__ffs(pf) - 1u : 31u;
-                unsigned long long v = lane <= upto ? (d & kDescValue) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) { sh.lb_sum[warp] = v; sh.lb_has[warp] = pf != 0u; }
-                __syncthreads();
-                bool found = false;
-                for (int w = 0; w < kExtractThreads / 32 && !found; ++w) {  // nearest warps first; stop at the first prefix
-                    excl += sh.lb_sum[w];
-                    found = sh.lb_has[w] != 0u;
-                }
-                __syncthreads();
-                if (found) break;
-                idx -= kExtractThreads;
-            }
-            cta_base = excl;
-            placed = true;
+            if (tile_id > 0) desc_store(p.out.desc + tile_id, kDescAggregate | pass_base);
+        } else {
+            desc_store(p.out.desc + tile_id, kDescPrefix | (cta_base + pass_base));
+            if (tile_id + 1 == gridDim.x) *p.out.total = cta_base + pass_base;
         }
-        if (last_pass && threadIdx.x == 0) {
-            const unsigned long long incl = cta_base + pass_base;
-            desc_store(p.out.desc + tile_id, kDescPrefix | incl);
-            if (tile_id + 1 == gridDim.x) *p.out.total = incl;
+        final_pass = true;  // (thread 0 only: it is the one that publishes again in place())
+    }
+
+    // Where this tile's entries start in the output: decoupled look-back over the earlier tiles, by the whole CTA at once --
+    // thread i reads the descriptor of tile (tile_id - 1 - i), so one round covers kExtractThreads predecessors with a
+    // single global-load latency.  Called from the first round_end of the tile, i.e. AFTER the first round of windows has
+    // been computed and staged: the tiles just ahead of this one, which started moments earlier, have had that long to
+    // count and publish, so the CTA rarely has to wait here (looking back right after the scan cost 22 % of the kernel in
+    // spinning: ncu kernels_r02f).  Nothing before the write-out needs the result.
+    __device__ __forceinline__ void place() {
+        const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        unsigned long long excl = 0;
+        int64_t idx = (int64_t)tile_id - 1;
+        for (;;) {  // CTA-uniform
+            if (idx < 0) break;
+            const int64_t mine = idx - (int64_t)threadIdx.x;
+            unsigned long long d = kDescPrefix;  // before tile 0: "prefix 0"
+            if (mine >= 0) {
+                do { d = desc_load(p.out.desc + mine); } while ((d >> 62) == 0ull);
+            }
+            const unsigned pf = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+            // value of this warp's window up to (and including) its nearest prefix holder
+            const unsigned upto = pf ? (unsigned)__ffs(pf) - 1u : 31u;
+            unsigned long long v = lane <= upto ? (d & kDescValue) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) { sh.lb_sum[warp] = v; sh.lb_has[warp] = pf != 0u; }
+            __syncthreads();
+            bool found = false;
+            for (int w = 0; w < kExtractThreads / 32 && !found; ++w) {  // nearest warps first; stop at the first prefix
+                excl += sh.lb_sum[w];
+                found = sh.lb_has[w] != 0u;
+            }
+            __syncthreads();
+            if (found) break;
+            idx -= kExtractThreads;
+        }
+        cta_base = excl;
+        placed = true;
+        if (final_pass) {  // thread 0 of a tile whose last pass is the current one: the count it published was complete
+            desc_store(p.out.desc + tile_id, kDescPrefix | (cta_base + pass_base));
+            if (tile_id + 1 == gridDim.x) *p.out.total = cta_base + pass_base;
         }
     }
 
@@ -187,16 +202,20 @@ struct CompactEng {
     // stage one entry of this warp's current round (local index = its offset inside the warp-round, < 256): every warp
     // owns a 256-entry slice of the staging buffers, so a round needs no CTA-wide barrier
     __device__ __forceinline__ void put(uint32_t local, const Window& w, uint64_t pos) const {
-        const uint32_t i = (threadIdx.x >> 5) * (32 * kRun) + swz(local);
+        const uint32_t i = (threadIdx.x >> 5) * kWarpSlice + swz(local);
         sh.canon[i] = w.canon;
+        sh.hash[i] = w.hash;  // the XOR fold of make_window: two LOP3, against ten for a pair reversal when the entry leaves
         sh.pos[i] = (int32_t)pos;
     }
 
     template <bool TWO, bool CHECK>
     __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t, uint32_t nwin, const ItemCtx& ic) {
         const uint32_t off = sh.cnt[ic.li];
-        uint32_t local = off - sh.wr_off[ic.li >> 5];
-        const uint64_t o0 = cta_base + cur_pass_base + off;  // global index of this item's first entry
+        const uint32_t wlo = sh.wr_off[ic.li >> 5];
+        // index of this item's first entry, counted from the tile's first: the tile's own start is not known yet (place()) and
+        // is added to emit_offsets afterwards (compact_fixup_kernel)
+        const uint64_t o0 = cur_pass_base + off;
+        uint32_t local = off - wlo;  // position inside the warp's staging slice
         if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = o0;  // this item opens read r_a
         uint32_t emitted = 0;
 #pragma unroll
@@ -216,7 +235,7 @@ struct CompactEng {
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t, const ItemCtx& ic) {
         // windows of one item arrive in order; the running index lives in cnt[li] (owned by this thread)
         const uint32_t off = sh.cnt[ic.li];
-        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = cta_base + cur_pass_base + off;
+        if (ic.pos_a == 0 && p.out.emit_offsets) p.out.emit_offsets[ic.r_a] = cur_pass_base + off;  // tile-local, see run()
         const Span s = load_span<VALIDATE>(tile, rel, p.wc);
         const bool ok = !VALIDATE || (((uint32_t)s.inv) & p.wc.kmask) == 0u;
         if (ok) {
@@ -225,29 +244,55 @@ struct CompactEng {
         }
     }
     // all threads, once per round: every warp writes the entries its 32 items staged -- one contiguous run of the output --
-    // as coalesced stores.  Warp-level synchronisation only.
+    // two entries per lane and step: an aligned pair of the output arrays leaves as one 16-byte store per 8-byte array and
+    // one 8-byte store for the positions (the pair's two entries are wherever the parity of the run's first index puts them
+    // in the slice).  The tile's start is looked up on the way into the first round's write-out.
     __device__ __forceinline__ void round_end(uint32_t q_round, uint32_t n_items) {
+        if (!placed) place();  // CTA-uniform: contains barriers
         __syncwarp();
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-        const uint32_t wr = q_round * (kExtractThreads / 32) + warp;  // this warp-round's index among the pass's
+        const uint32_t wr = q_round * kCompactWarps + warp;  // this warp-round's index among the pass's
         if (wr * 32u < n_items) {
             const uint32_t lo = sh.wr_off[wr], n = sh.wr_off[wr + 1] - lo;
             const uint64_t g0 = cta_base + cur_pass_base + lo;
             // the caller's arrays may be too small: the host reports it, nothing is overrun
             const uint32_t n_ok = g0 >= p.out.capacity ? 0u : (uint32_t)min((uint64_t)n, p.out.capacity - g0);
-            const uint64_t* sc = sh.canon + warp * (32 * kRun);
-            const int32_t* sp = sh.pos + warp * (32 * kRun);
-            uint64_t* gc = p.out.canon ? p.out.canon + g0 : nullptr;
-            uint64_t* gh = p.out.hash ? p.out.hash + g0 : nullptr;
-            int32_t* gp = p.out.pos ? p.out.pos + g0 : nullptr;
-            const uint32_t hs = 2 * (32 - p.wc.K);
-#pragma unroll 2
-            for (uint32_t e = lane; e < n_ok; e += 32) {
-                const uint32_t i = swz(e);
-                const uint64_t c = sc[i];
-                if (gc) gc[e] = c;
-                if (gh) gh[e] = pair_reverse64(c) >> hs;  // LexHasher::write_u64, hash.rs:60-71
-                if (gp) gp[e] = sp[i];
+            const uint32_t par = (uint32_t)(g0 & 1ull);
+            const uint64_t* sc = sh.canon + warp * kWarpSlice;
+            const uint64_t* shh = sh.hash + warp * kWarpSlice;
+            const int32_t* sp = sh.pos + warp * kWarpSlice;
+            // aligned position i <-> global index gb + i <-> staged entry i - par; entries [0, n_ok) exist
+            const uint64_t gb = g0 - par;
+            uint64_t* gc = p.out.canon ? p.out.canon + gb : nullptr;
+            uint64_t* gh = p.out.hash ? p.out.hash + gb : nullptr;
+            int32_t* gp = p.out.pos ? p.out.pos + gb : nullptr;
+            const uint32_t end = par + n_ok;
+            // full aligned pairs: positions [i_lo, i_hi); at most one lone entry on either side of them
+            const uint32_t i_lo = 2 * par, i_hi = end & ~1u;
+            if (p.out.vec16) {  // the output arrays are 16-byte (positions: 8-byte) aligned
+                for (uint32_t i = i_lo + 2 * lane; i < i_hi; i += 64) {
+                    const uint32_t i0 = swz(i - par), i1 = swz(i + 1 - par);
+                    if (gc) *reinterpret_cast<ulonglong2*>(gc + i) = make_ulonglong2(sc[i0], sc[i1]);
+                    if (gh) *reinterpret_cast<ulonglong2*>(gh + i) = make_ulonglong2(shh[i0], shh[i1]);
+                    if (gp) *reinterpret_cast<int2*>(gp + i) = make_int2(sp[i0], sp[i1]);
+                }
+            } else {
+                for (uint32_t i = i_lo + lane; i < i_hi; i += 32) {
+                    const uint32_t i0 = swz(i - par);
+                    if (gc) gc[i] = sc[i0];
+                    if (gh) gh[i] = shh[i0];
+                    if (gp) gp[i] = sp[i0];
+                }
+            }
+            // the lone entries: position 1 when the run starts on an odd index, position end - 1 when it ends on an even one
+            uint32_t lone = 0xFFFFFFFFu;
+            if (lane == 0 && par && end > 1u) lone = 1u;
+            if (lane == 1 && (end & 1u) && end - 1u >= i_lo && end - 1u >= par) lone = end - 1u;
+            if (lone != 0xFFFFFFFFu) {
+                const uint32_t i0 = swz(lone - par);
+                if (gc) gc[lone] = sc[i0];
+                if (gh) gh[lone] = shh[i0];
+                if (gp) gp[lone] = sp[i0];
             }
         }
         __syncwarp();  // the next round re-uses this warp's slice

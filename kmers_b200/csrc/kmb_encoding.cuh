@@ -286,7 +286,7 @@ __device__ __forceinline__ void decode8(uint32_t c16, uint32_t dec, uint32_t& ou
     out1 = __byte_perm(dec, 0u, x >> 16);
 }
 
-constexpr int kUnpackBlocksPerThread = 2;
+constexpr int kUnpackBlocksPerThread = 4;
 
 // the <= 16 codes of letters [rel, rel + n) of the CTA's item stream (rel counted from the first letter of the CTA's first item)
 template <bool SAFE>

@@ -43,6 +43,10 @@ struct OutPtrs {
     unsigned int* s_hist;        // MODE 2: this CTA's bins in shared memory, two 16-bit counters per word (smem_hist_add)
     uint32_t hist_shift;         // 2K - hist_bits
     uint32_t vec_ok;             // output pointers are 32-byte aligned
+    uint32_t one;                // the constant 1, from the parameter bank: a multiplier ptxas cannot fold, so that
+                                 // 64-bit accumulation is issued as IMAD.WIDE on the FMA pipe (see HistAcc)
+    uint32_t hist_hi_shift;      // MODE 2 fast path: bin = (~max_hi & mask_hi) >> hist_hi_shift (hist_shift >= 32), else 0xFFFFFFFF
+    uint32_t bin_mask;           // (1 << hist_bits) - 1
 };
 
 struct NarrowParams {
@@ -117,16 +121,96 @@ struct Acc {
 };
 
 // MODE 2: one count into this CTA's shared-memory histogram.  Two 16-bit counters share a 32-bit word.  The
-// increment that takes a counter to 2^15 (its atomicAdd returned 0x7FFF: exactly one thread per lap sees that) moves
-// those 2^15 to the global bin at once.  A counter therefore stays far below 2^16 -- it would take another 32768
-// increments of the same bin between that thread's two consecutive atomics to overflow it -- so no carry ever
+// increment that takes a counter to 2^15 (its atomicAdd returned 0x7FFF in that half: exactly one thread per lap sees
+// that) moves those 2^15 to the global bin at once.  A counter therefore stays far below 2^16 -- it would take another
+// 32768 increments of the same bin between that thread's two consecutive atomics to overflow it -- so no carry ever
 // crosses into the neighbouring counter and the shared counts stay exact.
+// The fused-histogram kernels are bound by the integer ALU pipe, so the bookkeeping around the atomic is written to go
+// through the FMA pipe where it can (IMAD with multipliers from the parameter bank): one LOP3 for the half, one for the
+// word address, one for the overflow test.
 __device__ __forceinline__ void smem_hist_add(const OutPtrs& o, uint32_t bin) {
-    const uint32_t sh = (bin & 1u) * 16;
-    const uint32_t old = atomicAdd(o.s_hist + (bin >> 1), 1u << sh);
-    if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {
-        atomicSub(o.s_hist + (bin >> 1), 0x8000u << sh);
-        atomicAdd(o.hist + bin, 32768ull);
+    const uint32_t inc = 1u << ((bin * (16u * o.one)) & 16u);  // 1 or 0x10000: the counter's half     (IMAD, LOP3, SHF)
+    const uint32_t m = inc * 0x7FFFu;                          // the counter's low 15 bits            (IMAD)
+    const uint32_t off = (bin * (2u * o.one)) & ~3u;           // byte offset of the word              (IMAD, LOP3)
+    unsigned int* w = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(o.s_hist) + off);
+    const uint32_t old = atomicAdd(w, inc);
+    if ((~old & m) == 0u) {                                     // the half held 0x7FFF before this increment
+        atomicSub(w, m + inc);                                  // take 2^15 out of it ...
+        atomicAdd(o.hist + bin, 32768ull);                      // ... and give them to the global bin
+    }
+}
+
+// Digest of the fused-histogram kernels, kept off the ALU pipe.  With mx = max(fw, rc):
+//   canonical = fw + rc - mx,   LexHash(canonical) = ~mx & mask = mask - mx      (kmb_extract.cuh header)
+// so three running sums -- of fw + rc, of mx, and the window count -- give both checksums, and each 32-bit half is added
+// into a 64-bit accumulator by one IMAD.WIDE (x * counted + acc: the multiplier doubles as the predicate).
+struct HistAcc {
+    uint64_t s_lo = 0, m_lo = 0;  // sums of the low words of fw and rc / of max(fw, rc): the carries out of bit 31 matter
+    uint32_t s_hi = 0, m_hi = 0;  // sums of the high words: only their low 32 bits reach a checksum mod 2^64
+    uint32_t valid = 0;
+    __device__ __forceinline__ void add(uint32_t flo, uint32_t fhi, uint32_t rlo, uint32_t rhi, uint32_t mlo, uint32_t mhi, uint32_t counted) {
+        s_lo += (uint64_t)flo * counted; s_lo += (uint64_t)rlo * counted;  // IMAD.WIDE
+        s_hi += fhi * counted; s_hi += rhi * counted;                      // IMAD
+        m_lo += (uint64_t)mlo * counted; m_hi += mhi * counted;
+        valid += counted;
+    }
+    __device__ __forceinline__ void to(Acc& a, uint64_t mask) const {
+        const uint64_t mx = m_lo + ((uint64_t)m_hi << 32);
+        a.valid = valid;
+        a.canon = s_lo + ((uint64_t)s_hi << 32) - mx;
+        a.hash = (uint64_t)valid * mask - mx;
+    }
+};
+
+// One window of the fused histogram (MODE 2): only what the bin and the digest need.  The bin is the top hist_bits of
+// LexHash(canonical) = ~max(fw, rc) & mask, i.e. (for 2K - hist_bits >= 32) a field of the HIGH word of the larger strand:
+// no canonical word, no hash word, no 64-bit shift.
+// HIBIN: 2K - hist_bits >= 32, the bin is a field of the high word (a template parameter: as a run-time test both variants
+// would be issued, predicated).  GUARD: the window may be missing or invalid (`counted`); without it every window counts.
+template <bool KHI, bool DIGEST, bool HIBIN, bool GUARD>
+__device__ __forceinline__ void hist_window(const Span& s, int j, const WinConst& wc, const OutPtrs& o, bool counted, HistAcc& hacc) {
+    uint32_t flo = __funnelshift_r(s.a0, s.a1, 2 * j), rlo = __funnelshift_r(s.d0, s.d1, 2 * (kRun - 1 - j));
+    uint32_t fhi = 0, rhi = 0;
+    bool fw_less;
+    if (KHI) {
+        fhi = __funnelshift_r(s.a1, s.a2, 2 * j) & wc.mask_hi;
+        rhi = __funnelshift_r(s.d1, s.d2, 2 * (kRun - 1 - j)) & wc.mask_hi;
+        fw_less = mk64(flo, fhi) < mk64(rlo, rhi);
+    } else {
+        flo &= wc.mask_lo;
+        rlo &= wc.mask_lo;
+        fw_less = flo < rlo;
+    }
+    const uint32_t mx_hi = fw_less ? rhi : fhi;
+    uint32_t bin;
+    const uint32_t mult = GUARD ? (counted ? o.one : 0u) : o.one;
+    if (KHI && HIBIN) {
+        bin = (~mx_hi & wc.mask_hi) >> o.hist_hi_shift;
+        if (DIGEST) hacc.add(flo, fhi, rlo, rhi, fw_less ? rlo : flo, mx_hi, mult);
+    } else {
+        const uint32_t mx_lo = fw_less ? rlo : flo;
+        const uint64_t hash = ~mk64(mx_lo, mx_hi) & mk64(wc.mask_lo, wc.mask_hi);
+        bin = (uint32_t)(hash >> o.hist_shift);
+        if (DIGEST) hacc.add(flo, fhi, rlo, rhi, mx_lo, mx_hi, mult);
+    }
+    if (!GUARD || counted) smem_hist_add(o, bin);
+}
+
+// the kRun windows of one work item into the shared-memory histogram (MODE 2)
+template <bool TWO, bool CHECK, bool DIGEST, bool KHI, bool HIBIN>
+__device__ __forceinline__ void emit_run_hist(const Span& A, const Span& B, uint32_t n_first, const WinConst& wc, const OutPtrs& o,
+                                              uint32_t nwin, HistAcc& hacc) {
+    if (!CHECK && nwin == kRun) {  // the common case: a full item without an invalid base -- no per-window guards at all
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) hist_window<KHI, DIGEST, HIBIN, false>((TWO && (uint32_t)j >= n_first) ? B : A, j, wc, o, true, hacc);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) {
+        const Span& s = (TWO && (uint32_t)j >= n_first) ? B : A;
+        bool ok = true;
+        if (CHECK) ok = (((uint32_t)(s.inv >> j)) & wc.kmask) == 0u;
+        hist_window<KHI, DIGEST, HIBIN, true>(s, j, wc, o, ok && (uint32_t)j < nwin, hacc);
     }
 }
 
@@ -206,10 +290,6 @@ __device__ __forceinline__ void emit_single(const uint2* tile, uint32_t rel, con
         if (ok) atomicAdd(o.hist + (w.hash >> o.hist_shift), 1ull);
         return;
     }
-    if (MODE == 2) {
-        if (ok) smem_hist_add(o, (uint32_t)(w.hash >> o.hist_shift));
-        return;
-    }
     if (o.canon) st_stream_u64(o.canon + slot, ok ? w.canon : ~0ull);
     if (o.hash) st_stream_u64(o.hash + slot, ok ? w.hash : ~0ull);
     if (FWRC) {
@@ -242,6 +322,9 @@ struct NarrowEng {
     using Params = NarrowParams;
     using Span = kmb::Span;
     static constexpr bool kValidate = VALIDATE;
+    // MODE 2 re-uses the HASH parameter (it materialises nothing): HASH == false selects the variant whose bin is a field of
+    // the high word of the larger strand (2K - hist_bits >= 32)
+    static constexpr bool kHiBin = MODE == 2 && KHI && !HASH;
     using Shape = ShapeRun;
     static constexpr bool kTwoPhase = false, kCountOnly = false;
     static constexpr int kSpanEntries = 4;  // tile entries one span reads
@@ -251,18 +334,26 @@ struct NarrowEng {
     static constexpr int kMinCtas = 0, kMinCtasCsr = FWRC ? 2 : 4;
     const NarrowParams& p;
     Acc acc;
+    HistAcc hacc;  // MODE 2 only
     __device__ explicit NarrowEng(const NarrowParams& params) : p(params) {}
     __device__ __forceinline__ uint32_t K() const { return p.wc.K; }
     __device__ __forceinline__ Span load(const uint2* tile, uint32_t rel) const { return load_span<VALIDATE>(tile, rel, p.wc); }
     __device__ __forceinline__ bool dirty(const Span& s) const { return s.inv != 0ull; }
     template <bool TWO, bool CHECK>
     __device__ __forceinline__ void run(const Span& a, const Span& b, uint32_t n_first, uint64_t slot0, uint32_t nwin, const ItemCtx&) {
-        emit_run<TWO, CHECK, DIGEST, FWRC, MODE, KHI, HASH>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
+        if constexpr (MODE == 2) emit_run_hist<TWO, CHECK, DIGEST, KHI, kHiBin>(a, b, n_first, p.wc, p.out, nwin, hacc);
+        else emit_run<TWO, CHECK, DIGEST, FWRC, MODE, KHI, HASH>(a, b, n_first, p.wc, p.out, slot0, nwin, acc);
     }
     __device__ __forceinline__ void single(const uint2* tile, uint32_t rel, uint64_t slot, const ItemCtx&) {
-        emit_single<VALIDATE, DIGEST, FWRC, MODE, KHI>(tile, rel, p.wc, p.out, slot, acc);
+        if constexpr (MODE == 2) {
+            const Span s = load_span<VALIDATE>(tile, rel, p.wc);
+            hist_window<KHI, DIGEST, kHiBin, true>(s, 0, p.wc, p.out, !VALIDATE || (((uint32_t)s.inv) & p.wc.kmask) == 0u, hacc);
+        } else {
+            emit_single<VALIDATE, DIGEST, FWRC, MODE, KHI>(tile, rel, p.wc, p.out, slot, acc);
+        }
     }
     __device__ __forceinline__ void finish(unsigned long long (&red)[3][32]) {
+        if (MODE == 2 && DIGEST) hacc.to(acc, mk64(p.wc.mask_lo, p.wc.mask_hi));
         reduce_digest<DIGEST>(red, p.out.digest, acc);
     }
 };

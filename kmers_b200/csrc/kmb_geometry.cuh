@@ -263,7 +263,7 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
         eng.scan(n_items);
         __syncthreads();
         if (Eng::kCountOnly) return;
-        eng.place(last_pass);  // where this CTA's entries start in the output (decoupled look-back over the earlier tiles)
+        eng.publish(last_pass);  // the tile's count goes out at once; where its entries start is looked up as late as possible (round_end)
         for_each_item<true>(n_items, [&](uint32_t li) { item(li, emit_one, emit_two, emit_single); },
                             [&](uint32_t q_round) { eng.round_end(q_round, n_items); });
     } else {

@@ -36,6 +36,8 @@ cudaError_t launch_hist_smem(bool validate, bool digest, bool khi, const FixedGe
 // kmb_tu_compact.cu: iterator-identical compacted stream
 cudaError_t launch_compact(bool count_only, bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
                            cudaStream_t st, const EncDesc& enc, const CompactParams& ep);
+cudaError_t launch_compact_fixup(const uint64_t* win_offsets, uint64_t W, uint64_t n_reads, uint64_t slots_per_cta, const unsigned long long* desc,
+                                 uint64_t* emit_offsets, cudaStream_t st);
 cudaError_t launch_compact_backfill(const uint64_t* win_offsets, uint64_t n_reads, const unsigned long long* total_emitted,
                                     uint64_t* emit_offsets, cudaStream_t st);
 // kmb_tu_minimizer.cu

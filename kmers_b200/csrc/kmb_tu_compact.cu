@@ -35,6 +35,30 @@ cudaError_t launch_compact(bool count_only, bool validate, bool khi, const Fixed
                       : launch_compact<false>(validate, khi, fg, cg, l, st, enc, ep);
 }
 
+// The emit kernel wrote every read's first-entry index counted from its TILE's first entry (the tile's start is the last thing
+// a CTA learns); after the launch every descriptor holds the tile's inclusive prefix, so the start of tile t is desc[t - 1].
+// win_offsets == NULL: fixed-length reads, read r's first slot is r * W.
+__global__ void __launch_bounds__(256) compact_fixup_kernel(const uint64_t* win_offsets, uint64_t W, uint64_t n_reads, uint64_t slots_per_cta,
+                                                            const unsigned long long* desc, uint64_t* emit_offsets) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint64_t slot;
+    if (win_offsets) {
+        slot = win_offsets[r];
+        if (win_offsets[r + 1] == slot) return;  // no window, no entry: compact_backfill_kernel fills these in
+    } else {
+        slot = r * W;
+    }
+    const uint64_t tile = slot / slots_per_cta;
+    if (tile) emit_offsets[r] += desc[tile - 1] & kDescValue;
+}
+
+cudaError_t launch_compact_fixup(const uint64_t* win_offsets, uint64_t W, uint64_t n_reads, uint64_t slots_per_cta, const unsigned long long* desc,
+                                 uint64_t* emit_offsets, cudaStream_t st) {
+    compact_fixup_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(win_offsets, W, n_reads, slots_per_cta, desc, emit_offsets);
+    return cudaGetLastError();
+}
+
 // Reads without a window (shorter than k) open no entry: their emit offset is that of the next read that has
 // windows (or the total).  win_offsets[r + 1] == win_offsets[r] identifies them.
 __global__ void __launch_bounds__(256) compact_backfill_kernel(const uint64_t* win_offsets, uint64_t n_reads,

@@ -56,10 +56,15 @@ cudaError_t launch_narrow_hist_global(bool validate, bool digest, bool khi, cons
 cudaError_t launch_hist_smem(bool validate, bool digest, bool khi, const FixedGeom* fg, const CsrGeom* cg, unsigned grid,
                                     size_t smem, uint32_t n_tiles, uint32_t tile_words, uint32_t n_bins, cudaStream_t st,
                                     const EncDesc& enc, const NarrowParams& ep) {
+    const bool hibin = khi && ep.out.hist_hi_shift != 0xFFFFFFFFu;  // the bin is a field of the high word (NarrowEng::kHiBin)
 #define KMB_CASE(V, D, H) \
-    if (validate == V && digest == D && khi == H) return launch_hist_eng<NarrowEng<V, D, false, 2, H>>(fg, cg, grid, smem, n_tiles, tile_words, n_bins, st, enc, ep);
+    if (validate == V && digest == D && khi == H && !hibin) return launch_hist_eng<NarrowEng<V, D, false, 2, H, true>>(fg, cg, grid, smem, n_tiles, tile_words, n_bins, st, enc, ep);
     KMB_CASE(true, false, true) KMB_CASE(true, false, false) KMB_CASE(true, true, true) KMB_CASE(true, true, false)
     KMB_CASE(false, false, true) KMB_CASE(false, false, false) KMB_CASE(false, true, true) KMB_CASE(false, true, false)
+#undef KMB_CASE
+#define KMB_CASE(V, D) \
+    if (validate == V && digest == D && hibin) return launch_hist_eng<NarrowEng<V, D, false, 2, true, false>>(fg, cg, grid, smem, n_tiles, tile_words, n_bins, st, enc, ep);
+    KMB_CASE(true, false) KMB_CASE(true, true) KMB_CASE(false, false) KMB_CASE(false, true)
 #undef KMB_CASE
     return cudaErrorInvalidValue;
 }

@@ -28,7 +28,7 @@ cudaError_t launch_minimizers(bool validate, const FixedGeom* fg, const CsrGeom*
 //   CLS 1  width <= 16: 32-bit rank, candidates walked right to left so that '<=' keeps the leftmost minimum
 //   CLS 2  wider      : 64-bit ranks (at most 16 candidates)
 // and every thread works on kMinWordsPerThread words at once.
-constexpr int kMinWordsPerThread = 2;
+constexpr int kMinWordsPerThread = 4;
 
 // 2^i as a constant-bank operand.  Integer shifts run on the ALU pipe, which this kernel saturates; IMAD runs on the FMA
 // pipe, which it leaves idle (both issue one warp instruction per 2 cycles per SM sub-partition).  A shift written as a

@@ -581,6 +581,9 @@ int32_t kmb_i_run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint64
     ep.out.canon = canon; ep.out.hash = hash; ep.out.fw = fw; ep.out.rc = rc;
     ep.out.digest = d_digest ? d_digest : ctx->d_digest; ep.out.hist = hist; ep.out.hist_shift = 2 * k - hist_bits;
     ep.out.vec_ok = ((((uintptr_t)canon | (uintptr_t)hash | (uintptr_t)fw | (uintptr_t)rc) & 31u) == 0) ? 1u : 0u;
+    ep.out.one = 1u;
+    ep.out.bin_mask = hist ? (uint32_t)((1ull << hist_bits) - 1ull) : 0u;
+    ep.out.hist_hi_shift = (hist && ep.out.hist_shift >= 32u) ? ep.out.hist_shift - 32u : 0xFFFFFFFFu;
     FixedGeom fg{};
     CsrGeom cg{};
     Launch l;
@@ -747,10 +750,16 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     ep.out.canon = (uint64_t*)oc.dev; ep.out.hash = (uint64_t*)oh.dev; ep.out.pos = (int32_t*)op.dev;
     ep.out.emit_offsets = (uint64_t*)oe.dev;
     ep.out.capacity = cap;
+    ep.out.vec16 = ((((uintptr_t)oc.dev | (uintptr_t)oh.dev) & 15u) == 0 && ((uintptr_t)op.dev & 7u) == 0) ? 1u : 0u;
     CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 2) * 8, ctx->stream));
     CK(ctx, launch_compact(false, validate, khi, pf, pc, l, ctx->stream, enc, ep));
     ctx->launches++;
     if (oe.dev) {
+        // the kernel wrote tile-local first-entry indices: add the tiles' starts (their inclusive prefixes are in the descriptors now)
+        const uint64_t slots_per_cta = (uint64_t)(csr ? cg.items_per_cta : fg.items_per_cta) * kRun;
+        CK(ctx, launch_compact_fixup(csr ? ctx->d_win_offsets : nullptr, csr ? 0 : fg.W, ctx->n_reads, slots_per_cta, ctx->d_cta_counts,
+                                     (uint64_t*)oe.dev, ctx->stream));
+        ctx->launches++;
         CK(ctx, cudaMemcpyAsync((uint64_t*)oe.dev + ctx->n_reads, d_total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (csr) {
             CK(ctx, launch_compact_backfill(ctx->d_win_offsets, ctx->n_reads, d_total, (uint64_t*)oe.dev, ctx->stream));

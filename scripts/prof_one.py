@@ -39,7 +39,12 @@ if what in ("wide", "csr_wide"):
     step = lambda: ctx._ck(ctx._lib.kmb_extract_canonical_wide(ctx._h, 63, kb.ENC_ACGT, 0, _ptr(c), None, None))
 elif what == "hist":
     alg = n * L
-    step = lambda: batch.histogram(K, 16, digest=False)
+    hb = i64(65536 + 3)
+    step = lambda: batch.histogram(K, 16, hist=hb, digest=False)
+elif what == "histd":  # with the digest accumulated behind the bins (config 5's step)
+    alg = n * L
+    hb = i64(65536 + 3)
+    step = lambda: batch.histogram(K, 16, hist=hb, digest_in_hist=True)
 elif what == "compact":
     alg = None
     step = lambda: batch.extract_compact(K, to="device")
