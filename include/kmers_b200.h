@@ -218,7 +218,10 @@ int32_t kmb_ctx_host_stats(const kmb_ctx *ctx, uint64_t *stats4);
  * (naive_impl/seq_vector/minimizers.rs:38-142; ties keep the older entry, :72-78).  mmer_out[slot] = the lmer word
  * (forward strand, SeqVector::get_kmer_u64, seq_vector.rs:96-99), pos_out[slot] = its position inside the read.
  * EXTENSION: a SeqVector cannot hold non-ACGT bases; windows holding one get KMB_SENTINEL / UINT32_MAX.
- * 1 <= w <= k <= 32, 1 <= hash_k <= 32. */
+ * 1 <= w <= k <= 32, 1 <= hash_k <= 32.
+ * The reference's iterator is generic over the hasher (SeqVecMinimizerIter<T: BuildHasher>, minimizers.rs:38-60); the
+ * hasher here is always LexHasherState(hash_k), the only one whose arithmetic is in the reference tree (std's SipHash
+ * DefaultHasher is randomly keyed and cannot be pinned). */
 int32_t kmb_minimizers(kmb_ctx *ctx, uint32_t k, uint32_t w, uint32_t hash_k, uint32_t flags, uint64_t *mmer_out,
                        uint32_t *pos_out);
 /* Kmer::minimizer_word (naive_impl/kmer.rs:170-191) with LexHasherState(hash_k) on n k-mer words:
@@ -244,6 +247,21 @@ int32_t kmb_batch_attach_packed(kmb_ctx *ctx, const uint64_t *dev_words, uint64_
 /* SeqVector::get_kmer_u64 (seq_vector.rs:96-99) for n (read, pos) pairs (reads == NULL: read 0): out[i] = the k bases
  * at pos[i] of read reads[i], or KMB_SENTINEL where the reference's assert!(pos < len) / the read's end is violated. */
 int32_t kmb_packed_get_kmers(kmb_ctx *ctx, uint32_t k, const uint64_t *reads, const uint64_t *pos, uint64_t n, uint64_t *out);
+
+/* SeqVector::with_capacity + push_chars (seq_vector.rs:135-161): an empty packed sequence owned by the context, grown by
+ * appending ASCII bases (host or device memory).  A byte outside ACGTacgt is KMB_ERR_PANIC and nothing is appended (push_chars
+ * goes through Kmer::from, which panics).  push_chars needs a context-owned packed batch of ONE sequence: kmb_batch_new_packed,
+ * or kmb_batch_repack of a one-read batch.  Every extraction op then sees the grown sequence. */
+int32_t kmb_batch_new_packed(kmb_ctx *ctx, uint64_t capacity_bases);
+int32_t kmb_packed_push_chars(kmb_ctx *ctx, const uint8_t *bases, uint64_t n);
+/* SeqVector::slice / SeqVectorSlice (seq_vector.rs:24-90): turn the resident packed batch into a one-read VIEW of bases
+ * [start, start + len) of `read` -- no copy; kmb_extract_canonical (fw_out = SeqVectorSlice::iter_kmers), kmb_minimizers
+ * (= iter_minimizers), kmb_extract_compact, kmb_histogram and kmb_packed_get_kmers (= SeqVectorSlice::get_kmer_u64) then
+ * work on the view.  start / len are always counted in the parent read, also when a view is already in place (which is what
+ * the reference's nested slice() does: it stores `start` as the new start_pos, seq_vector.rs:57-64).  A range beyond the read
+ * is KMB_ERR_PANIC (assert!(end <= self.len())).  kmb_batch_unslice restores the whole batch. */
+int32_t kmb_batch_slice(kmb_ctx *ctx, uint64_t read, uint64_t start, uint64_t len);
+int32_t kmb_batch_unslice(kmb_ctx *ctx);
 
 /* ---- final reduction across GPUs ------------------------------- */
 /* One process driving several GPUs: in-place element-wise wrapping-u64 sum of dev_bufs[i] (count words in the memory of

@@ -80,6 +80,10 @@ SIGNATURES = {
     "kmb_batch_repack": (_i32, [_vp, _i32]),
     "kmb_batch_attach_packed": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, _u64]),
     "kmb_packed_get_kmers": (_i32, [_vp, _u32, _vp, _vp, _u64, _vp]),
+    "kmb_batch_new_packed": (_i32, [_vp, _u64]),
+    "kmb_packed_push_chars": (_i32, [_vp, _vp, _u64]),
+    "kmb_batch_slice": (_i32, [_vp, _u64, _u64, _u64]),
+    "kmb_batch_unslice": (_i32, [_vp]),
     "kmb_allreduce_u64": (_i32, [_vp, _i32, _vp, _u64]),
     "kmb_parse_fastx": (_i32, [C.c_char_p, _u64, _vp, _u64, _vp, _u64, _pu64, _pu64]),
     "kmb_batch_ingest_fastx": (_i32, [_vp, C.c_char_p, _u64, _pu64, _pu64]),

@@ -183,6 +183,14 @@ class Context:
         self._keep = []
         return ReadBatch(self, n_reads * fixed_len, n_reads, fixed_len, False)
 
+    def new_packed(self, capacity_bases: int = 0) -> "ReadBatch":
+        """SeqVector::with_capacity (seq_vector.rs:135-139): an empty packed sequence, grown with ReadBatch.push_chars."""
+        self._ck(self._lib.kmb_batch_new_packed(self._h, capacity_bases))
+        self._keep = []
+        b = ReadBatch(self, 0, 1, 0, False)
+        b.packed = True
+        return b
+
     def ingest_fastx(self, text: bytes) -> "ReadBatch":
         """FASTA / FASTQ text -> pinned host batch -> device (kmb_batch_ingest_fastx); returns the ragged ReadBatch."""
         nr, nb = C.c_uint64(), C.c_uint64()
@@ -457,6 +465,30 @@ class ReadBatch:
         KmbPanic on a byte outside ACGTacgt, as SeqVector::from would panic."""
         self.ctx._ck(self.ctx._lib.kmb_batch_repack(self.ctx._h, int(strict)))
         self.packed = True
+        return self
+
+    def push_chars(self, bases) -> "ReadBatch":
+        """SeqVector::push_chars (seq_vector.rs:141-161): append ASCII bases to a one-sequence packed batch."""
+        b = np.ascontiguousarray(np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else bases, dtype=np.uint8)
+        self.ctx._ck(self.ctx._lib.kmb_packed_push_chars(self.ctx._h, _ptr(b), b.size))
+        self.fixed_len += b.size
+        self.n_bytes = (self.fixed_len + 31) // 32 * 8
+        return self
+
+    def slice(self, read: int, start: int, length: int) -> "ReadBatch":
+        """SeqVector::slice / SeqVectorSlice (seq_vector.rs:24-90): the batch becomes a view of bases [start, start + length)
+        of `read` (no copy) until `unslice()`; extraction, minimizers, get_kmers then work on the view."""
+        self.ctx._ck(self.ctx._lib.kmb_batch_slice(self.ctx._h, read, start, length))
+        if not hasattr(self, "_parent"):
+            self._parent = (self.n_reads, self.fixed_len, self.ragged)
+        self.n_reads, self.fixed_len, self.ragged = 1, 0, True
+        return self
+
+    def unslice(self) -> "ReadBatch":
+        self.ctx._ck(self.ctx._lib.kmb_batch_unslice(self.ctx._h))
+        if hasattr(self, "_parent"):
+            self.n_reads, self.fixed_len, self.ragged = self._parent
+            del self._parent
         return self
 
     def get_kmers(self, k: int, pos, reads=None) -> np.ndarray:

@@ -629,13 +629,26 @@ __global__ void __launch_bounds__(256) read_counts_kernel(const uint64_t* offset
 
 // first_read[b] = read owning slot b * slots_per_cta (b < grid); first_read[grid] = read owning the last slot.
 // One thread per CTA of the extraction grid: the log2(n_reads)-deep searches all run concurrently here
-// instead of serially at the head of every extraction CTA.
-__global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_slots,
-                                                        uint64_t slots_per_cta, uint64_t grid, uint64_t* first_read) {
+// instead of serially at the head of every extraction CTA.  The same thread works out the tile's staged stretch
+// (CsrTileDesc) when the whole tile fits one pass of tile_bases bases.
+__global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* offsets, const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_slots,
+                                                        uint64_t slots_per_cta, uint64_t grid, uint32_t k, uint32_t tile_bases,
+                                                        uint64_t* first_read, CsrTileDesc* tile_desc) {
     const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b > grid) return;
     const uint64_t slot = b < grid ? b * slots_per_cta : total_slots - 1;
-    first_read[b] = last_le(win_offsets, 0, n_reads - 1, slot);  // skips window-less reads: takes the last equal entry
+    const uint64_t r_lo = last_le(win_offsets, 0, n_reads - 1, slot);  // skips window-less reads: takes the last equal entry
+    first_read[b] = r_lo;
+    if (b == grid) return;
+    const uint64_t slot_end = min(total_slots, slot + slots_per_cta);
+    const uint64_t r_last = last_le(win_offsets, r_lo, n_reads - 1, slot_end - 1);
+    CsrTileDesc td;
+    td.g0 = offsets[r_lo] + (slot - win_offsets[r_lo]);
+    td.r_last = r_last;
+    const uint64_t g_end = offsets[r_last] + (slot_end - 1 - win_offsets[r_last]) + k;
+    td.span = g_end - td.g0 <= (uint64_t)tile_bases ? (uint32_t)(g_end - td.g0) : 0xFFFFFFFFu;
+    td.pad = 0;
+    tile_desc[b] = td;
 }
 
 }  // namespace kmb

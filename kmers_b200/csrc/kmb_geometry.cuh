@@ -344,6 +344,16 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
 constexpr int kCsrCache = 512;   // reads whose offsets a CTA keeps in shared memory (more: read from global)
 constexpr int kCsrGroup = 8;     // items per entry of the per-pass owner table
 
+// What a CTA of the ragged kernels needs to know before it can fetch anything, precomputed per tile by csr_index_kernel
+// for the common case that the tile's whole stretch fits one staged pass: the CTA then starts staging at once, with no
+// serial set-up by thread 0 and one barrier less.
+struct CsrTileDesc {
+    uint64_t g0;      // flat base index of the first base the tile needs
+    uint64_t r_last;  // read owning the tile's last slot
+    uint32_t span;    // bases from g0 to the last window's last base; 0xFFFFFFFF: more than one pass (set up in the kernel)
+    uint32_t pad;
+};
+
 struct CsrGeom {
     const uint8_t* bases;
     uint64_t n_bytes;             // bytes of the buffer behind `bases`
@@ -351,6 +361,7 @@ struct CsrGeom {
     const uint64_t* offsets;      // n_reads + 1: flat base index of every read's first base
     const uint64_t* win_offsets;  // n_reads + 1, exclusive prefix of per-read window counts
     const uint64_t* first_read;   // grid + 1: read owning each CTA's first slot (csr_index_kernel)
+    const CsrTileDesc* tile_desc; // grid entries (csr_index_kernel)
     uint64_t n_reads;
     uint64_t total_slots;
     uint32_t items_per_cta;
@@ -371,6 +382,37 @@ struct CsrPass {  // one staged stretch: slots [slot_lo, slot_hi) of reads [r_lo
     uint64_t slot_lo, slot_hi, r_lo, r_hi, g0;
     uint32_t span;
 };
+
+// One work item of a ragged pass: which read(s) its slots belong to, then one span / two spans / window by window.
+template <class Shape, class One, class Two, class Single>
+__device__ __forceinline__ void csr_item(uint32_t li, uint32_t n_slots, const CsrPass& ps, const uint64_t* off, const uint64_t* win,
+                                         const uint64_t* grp, uint32_t mis, One&& one, Two&& two, Single&& single) {
+    const uint32_t fs = Shape::first(li);
+    if (fs >= n_slots) return;
+    const uint64_t slot0 = ps.slot_lo + fs;
+    const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, n_slots - fs);
+    uint64_t r = last_le(win, grp[li / kCsrGroup], grp[li / kCsrGroup + 1], slot0);
+    const uint64_t pos = slot0 - win[r];
+    const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
+    const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
+    if (left >= nwin) {
+        one(rel, slot0, nwin, ItemCtx{li, r, pos, 0});
+        return;
+    }
+    uint64_t r2 = r + 1;
+    while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+    if (left + (win[r2 + 1] - win[r2]) >= nwin) {
+        two(rel, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left, (uint32_t)left, slot0, nwin, ItemCtx{li, r, pos, r2});
+        return;
+    }
+    // several short reads inside one item: window by window
+    uint64_t p = pos, w_r = win[r + 1] - win[r];
+    for (uint32_t s = 0; s < nwin; ++s) {
+        while (p >= w_r) { ++r; p = 0; w_r = win[r + 1] - win[r]; }
+        if (Shape::owns(s)) single((uint32_t)(off[r] + p - ps.g0) + mis, slot0 + s, ItemCtx{li, r, p, 0});
+        ++p;
+    }
+}
 
 template <class Eng>
 __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint64_t* c_off,
@@ -396,9 +438,39 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         off = c_off - R_lo;
         win = c_win - R_lo;
     }
-    __syncthreads();
 
     uint64_t cur = slot_begin, r_cur = R_lo;
+    // The common case: the offsets of the tile's reads are in shared memory and the whole tile is one pass whose stretch
+    // csr_index_kernel already worked out.  Staging starts at once, next to the loads of the offsets (one barrier for
+    // both), and the per-group owner table is filled by the reads themselves -- every read marks the groups whose first
+    // slot it owns -- instead of one binary search per group.
+    const CsrTileDesc td = g.tile_desc[tile_idx];
+    if (off != g.offsets && td.span != 0xFFFFFFFFu) {
+        CsrPass ps;
+        ps.slot_lo = slot_begin; ps.slot_hi = slot_end; ps.r_lo = R_lo; ps.r_hi = td.r_last; ps.g0 = td.g0; ps.span = td.span;
+        const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
+        const uint32_t n_items = Shape::n_items(n_slots);
+        const uint32_t n_groups = (n_items + kCsrGroup - 1) / kCsrGroup;
+        const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, ps.g0, ps.span, Eng::kSpanEntries, enc, tile);
+        if constexpr (!Eng::kTwoPhase) deferred_reset();
+        __syncthreads();  // the offsets (loaded above) and the tile
+        constexpr uint32_t kGroupSlots = kCsrGroup * kRun;
+        for (uint64_t r = R_lo + threadIdx.x; r <= ps.r_hi; r += blockDim.x) {
+            const uint64_t a = max(win[r], ps.slot_lo), b = min(win[r + 1], ps.slot_hi);
+            if (b > a) {
+                const uint32_t t1 = (uint32_t)((b - 1 - ps.slot_lo) / kGroupSlots);
+                for (uint32_t t = (uint32_t)((a - ps.slot_lo + kGroupSlots - 1) / kGroupSlots); t <= t1; ++t) grp[t] = r;
+            }
+        }
+        if (threadIdx.x == 0) grp[n_groups] = ps.r_hi;
+        __syncthreads();
+        auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
+            csr_item<Shape>(li, n_slots, ps, off, win, grp, mis, one, two, single);
+        };
+        run_pass(eng, tile, K, n_items, item, true);
+        return;
+    }
+    __syncthreads();  // the cached offsets
     while (cur < slot_end) {  // CTA-uniform; one pass unless a stretch of very short reads overflows the tile
         if (threadIdx.x == 0) {
             CsrPass ps;
@@ -444,33 +516,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         __syncthreads();
 
         auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
-            {
-                const uint32_t fs = Shape::first(li);
-                if (fs >= n_slots) return;
-                const uint64_t slot0 = ps.slot_lo + fs;
-                const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, n_slots - fs);
-                uint64_t r = last_le(win, grp[li / kCsrGroup], grp[li / kCsrGroup + 1], slot0);
-                const uint64_t pos = slot0 - win[r];
-                const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
-                const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
-                if (left >= nwin) {
-                    one(rel, slot0, nwin, ItemCtx{li, r, pos, 0});
-                    return;
-                }
-                uint64_t r2 = r + 1;
-                while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
-                if (left + (win[r2 + 1] - win[r2]) >= nwin) {
-                    two(rel, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left, (uint32_t)left, slot0, nwin, ItemCtx{li, r, pos, r2});
-                    return;
-                }
-                // several short reads inside one item: window by window
-                uint64_t p = pos, w_r = win[r + 1] - win[r];
-                for (uint32_t s = 0; s < nwin; ++s) {
-                    while (p >= w_r) { ++r; p = 0; w_r = win[r + 1] - win[r]; }
-                    if (Shape::owns(s)) single((uint32_t)(off[r] + p - ps.g0) + mis, slot0 + s, ItemCtx{li, r, p, 0});
-                    ++p;
-                }
-            }
+            csr_item<Shape>(li, n_slots, ps, off, win, grp, mis, one, two, single);
         };
         run_pass(eng, tile, K, n_items, item, ps.slot_hi == slot_end);
         __syncthreads();  // the next pass overwrites the tile

@@ -35,6 +35,12 @@ struct kmb_ctx {
     size_t own_packed_cap = 0;
     uint64_t* own_base_starts = nullptr;
     size_t own_base_starts_cap = 0;
+    // a view of one read of the packed store (SeqVectorSlice): the parent's description while the view is in place
+    bool sliced = false;
+    uint64_t* own_slice = nullptr;  // 4 words: offsets [0, len], base starts [flat start, flat end]
+    const uint64_t* parent_offsets = nullptr;
+    const uint64_t* parent_base_starts = nullptr;
+    uint64_t parent_n_reads = 0, parent_fixed_len = 0;
 
     // CSR window-offset cache (per k)
     uint64_t* d_win_offsets = nullptr;

@@ -115,6 +115,7 @@ extern "C" int32_t kmb_ctx_destroy(kmb_ctx* ctx) {
     cudaFree(ctx->own_offsets);
     cudaFree(ctx->own_packed);
     cudaFree(ctx->own_base_starts);
+    cudaFree(ctx->own_slice);
     cudaFree(ctx->d_win_offsets);
     cudaFree(ctx->d_first_read);
     cudaFree(ctx->d_cta_counts);
@@ -210,6 +211,7 @@ static bool make_enc(int32_t enc, EncDesc* d, uint32_t* dec_letters) {
 // ======================================================================= batch
 static void drop_batch(kmb_ctx* ctx) {
     ctx->have_batch = false;
+    ctx->sliced = false;
     ctx->win_valid = false;
     ctx->d_bases = nullptr;
     ctx->d_offsets = nullptr;
@@ -540,11 +542,15 @@ static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, Cs
     if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
     l->grid = (unsigned)ctas;
     l->smem = (size_t)g->tile_entries * sizeof(uint2) + 2 * (size_t)(kCsrCache + 2) * sizeof(uint64_t);
-    if ((rc = grow(ctx, (void**)&ctx->d_first_read, &ctx->first_read_cap, (ctas + 1) * 8))) return rc;
+    // [ctas + 1 first reads | ctas tile descriptors]
+    if ((rc = grow(ctx, (void**)&ctx->d_first_read, &ctx->first_read_cap, (ctas + 1) * 8 + ctas * sizeof(CsrTileDesc)))) return rc;
     g->first_read = ctx->d_first_read;
+    CsrTileDesc* d_desc = reinterpret_cast<CsrTileDesc*>(ctx->d_first_read + ctas + 1);
+    g->tile_desc = d_desc;
     if (ctas) {
-        csr_index_kernel<<<(unsigned)((ctas + 1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_win_offsets, ctx->n_reads, g->total_slots,
-                                                                                   slots_per_cta, ctas, ctx->d_first_read);
+        const uint32_t tile_bases = (g->tile_entries - span_entries - 1) * 16;  // as csr_body computes it
+        csr_index_kernel<<<(unsigned)((ctas + 1 + 255) / 256), 256, 0, ctx->stream>>>(g->offsets, ctx->d_win_offsets, ctx->n_reads, g->total_slots,
+                                                                                   slots_per_cta, ctas, k, tile_bases, ctx->d_first_read, d_desc);
         CK(ctx, cudaGetLastError());
         ctx->launches++;
     }
@@ -1018,6 +1024,122 @@ extern "C" int32_t kmb_packed_get_kmers(kmb_ctx* ctx, uint32_t k, const uint64_t
     ctx->launches++;
     if ((rc = out_finish(ctx, ob))) return rc;
     if (ob.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return KMB_OK;
+}
+
+// ----------------------------------------------------------------------- SeqVector growth and views
+// SeqVector::with_capacity (seq_vector.rs:135-139): an empty packed sequence the context owns
+extern "C" int32_t kmb_batch_new_packed(kmb_ctx* ctx, uint64_t capacity_bases) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    drop_batch(ctx);
+    int32_t rc = grow(ctx, (void**)&ctx->own_packed, &ctx->own_packed_cap, (capacity_bases + 31) / 32 * 8 + 64);
+    if (rc) return rc;
+    ctx->d_bases = (const uint8_t*)ctx->own_packed; ctx->d_offsets = nullptr;
+    ctx->n_bytes = 0; ctx->n_reads = 1; ctx->fixed_len = 0; ctx->stride_len = 0; ctx->n_bases_flat = 0;
+    ctx->packed = true; ctx->have_batch = true;
+    return KMB_OK;
+}
+
+__global__ void __launch_bounds__(256) count_invalid_kernel(const uint8_t* chars, uint64_t n, unsigned long long* bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inv = i < n && encode_binary_u8_dev(chars[i]) == ~0ull;
+    const unsigned b = __ballot_sync(0xffffffffu, inv);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(bad, (unsigned long long)__popc(b));
+}
+// one thread per 64-bit word of the store that receives new bases: the word that was partly filled keeps its low bits
+__global__ void __launch_bounds__(256) push_chars_kernel(uint64_t* words, uint64_t old_len, const uint8_t* chars, uint64_t n) {
+    const uint64_t w0 = old_len / 32, wi = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t new_len = old_len + n;
+    if (wi * 32 >= new_len) return;
+    const uint64_t lo = max(wi * 32, old_len), hi = min(wi * 32 + 32, new_len);
+    uint64_t v = (wi == w0 && (old_len & 31)) ? words[wi] : 0ull;
+    for (uint64_t p = lo; p < hi; ++p) v |= (encode_binary_u8_dev(chars[p - old_len]) & 3ull) << (2 * (p & 31));
+    words[wi] = v;
+}
+
+// SeqVector::push_chars (seq_vector.rs:141-161)
+extern "C" int32_t kmb_packed_push_chars(kmb_ctx* ctx, const uint8_t* bases, uint64_t n) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (!ctx->packed || ctx->sliced || ctx->d_offsets || ctx->n_reads != 1 || ctx->d_bases != (const uint8_t*)ctx->own_packed)
+        return fail(ctx, KMB_ERR_STATE, "push_chars needs a context-owned packed batch of ONE sequence (kmb_batch_new_packed, or kmb_batch_repack of one read)");
+    if (n == 0) return KMB_OK;
+    if (!bases) return fail(ctx, KMB_ERR_INVALID_ARG, "bases is NULL");
+    const void* d_chars;
+    int32_t rc = in_prepare(ctx, 1, bases, n, &d_chars);
+    if (rc) return rc;
+    // Kmer::from panics on a byte outside ACGTacgt (naive_impl/mod.rs:35): checked before anything is written
+    CK(ctx, cudaMemsetAsync(ctx->d_digest + 3, 0, 8, ctx->stream));
+    count_invalid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_chars, n, ctx->d_digest + 3);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(ctx->h_digest + 3, ctx->d_digest + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_digest[3]) return fail(ctx, KMB_ERR_PANIC, "%llu bases are not ACGTacgt: SeqVector::push_chars would panic", ctx->h_digest[3]);
+    const uint64_t old_len = ctx->fixed_len, new_len = old_len + n;
+    const uint64_t old_words = (old_len + 31) / 32, new_words = (new_len + 31) / 32;
+    if (ctx->own_packed_cap < new_words * 8 + 64) {  // grow geometrically, keep what is there
+        uint64_t* bigger = nullptr;
+        const size_t cap = std::max<size_t>(new_words * 8 + 64, 2 * ctx->own_packed_cap);
+        CK(ctx, cudaMalloc((void**)&bigger, cap + 256));
+        if (old_words) CK(ctx, cudaMemcpyAsync(bigger, ctx->own_packed, old_words * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaFree(ctx->own_packed));
+        ctx->own_packed = bigger; ctx->own_packed_cap = cap;
+    }
+    const uint64_t touched = new_words - old_len / 32;
+    push_chars_kernel<<<(unsigned)((touched + 255) / 256), 256, 0, ctx->stream>>>(ctx->own_packed, old_len, (const uint8_t*)d_chars, n);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->d_bases = (const uint8_t*)ctx->own_packed;
+    ctx->fixed_len = new_len; ctx->stride_len = new_words * 32; ctx->n_bytes = new_words * 8; ctx->n_bases_flat = new_words * 32;
+    ctx->win_valid = false;
+    return KMB_OK;
+}
+
+// SeqVector::slice / SeqVectorSlice (seq_vector.rs:24-90): the batch becomes a view of bases [start, start + len) of one read
+extern "C" int32_t kmb_batch_slice(kmb_ctx* ctx, uint64_t read, uint64_t start, uint64_t len) {
+    NEED_CTX(ctx);
+    BIND(ctx);
+    NEED_BATCH(ctx);
+    if (!ctx->packed) return fail(ctx, KMB_ERR_STATE, "the resident batch is not packed (kmb_batch_repack first)");
+    if (!ctx->sliced) {
+        ctx->parent_offsets = ctx->d_offsets; ctx->parent_base_starts = ctx->d_base_starts;
+        ctx->parent_n_reads = ctx->n_reads; ctx->parent_fixed_len = ctx->fixed_len;
+    }
+    if (read >= ctx->parent_n_reads) return fail(ctx, KMB_ERR_INVALID_ARG, "read %llu out of range", (unsigned long long)read);
+    uint64_t read_len = ctx->parent_fixed_len, flat0 = read * ctx->stride_len;
+    if (ctx->parent_offsets) {  // ragged parent: this read's length and padded start live on the device
+        uint64_t h[3];
+        CK(ctx, cudaMemcpyAsync(h, ctx->parent_offsets + read, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(h + 2, ctx->parent_base_starts + read, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        read_len = h[1] - h[0];
+        flat0 = h[2];
+    }
+    // assert!(end <= self.len()) (seq_vector.rs:58); end - start underflows for start > end
+    if (start > read_len || len > read_len - start)
+        return fail(ctx, KMB_ERR_PANIC, "slice [%llu, %llu) exceeds the %llu bases of read %llu", (unsigned long long)start,
+                    (unsigned long long)(start + len), (unsigned long long)read_len, (unsigned long long)read);
+    if (!ctx->own_slice) CK(ctx, cudaMalloc((void**)&ctx->own_slice, 4 * 8 + 256));
+    const uint64_t h[4] = {0, len, flat0 + start, flat0 + start + len};
+    CK(ctx, cudaMemcpyAsync(ctx->own_slice, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));  // h is a stack array
+    ctx->d_offsets = ctx->own_slice; ctx->d_base_starts = ctx->own_slice + 2;
+    ctx->n_reads = 1; ctx->fixed_len = 0;
+    ctx->sliced = true; ctx->win_valid = false;
+    return KMB_OK;
+}
+
+extern "C" int32_t kmb_batch_unslice(kmb_ctx* ctx) {
+    NEED_CTX(ctx);
+    NEED_BATCH(ctx);
+    if (!ctx->sliced) return KMB_OK;
+    ctx->d_offsets = ctx->parent_offsets; ctx->d_base_starts = ctx->parent_base_starts;
+    ctx->n_reads = ctx->parent_n_reads; ctx->fixed_len = ctx->parent_fixed_len;
+    ctx->sliced = false; ctx->win_valid = false;
     return KMB_OK;
 }
 

@@ -67,6 +67,10 @@ extern "C" {
     pub fn kmb_batch_repack(ctx: *mut kmb_ctx, strict: i32) -> i32;
     pub fn kmb_batch_attach_packed(ctx: *mut kmb_ctx, dev_words: *const u64, n_words: u64, dev_offsets: *const u64, dev_word_offsets: *const u64, n_reads: u64, fixed_len: u64) -> i32;
     pub fn kmb_packed_get_kmers(ctx: *mut kmb_ctx, k: u32, reads: *const u64, pos: *const u64, n: u64, out: *mut u64) -> i32;
+    pub fn kmb_batch_new_packed(ctx: *mut kmb_ctx, capacity_bases: u64) -> i32;
+    pub fn kmb_packed_push_chars(ctx: *mut kmb_ctx, bases: *const u8, n: u64) -> i32;
+    pub fn kmb_batch_slice(ctx: *mut kmb_ctx, read: u64, start: u64, len: u64) -> i32;
+    pub fn kmb_batch_unslice(ctx: *mut kmb_ctx) -> i32;
     pub fn kmb_allreduce_u64(ctxs: *const *mut kmb_ctx, n_ctx: i32, dev_bufs: *const *mut u64, count: u64) -> i32;
     pub fn kmb_parse_fastx(text: *const c_char, n_bytes: u64, bases_out: *mut u8, bases_cap: u64, offsets_out: *mut u64, reads_cap: u64, n_reads: *mut u64, n_bases: *mut u64) -> i32;
     pub fn kmb_batch_ingest_fastx(ctx: *mut kmb_ctx, text: *const c_char, n_bytes: u64, n_reads_out: *mut u64, n_bases_out: *mut u64) -> i32;

@@ -131,3 +131,72 @@ def test_two_word_path_reads_the_packed_store(ctx, enc_name):
     a = ctx.upload(bases, offsets=offs).extract_canonical_wide(63, enc, digest=True, to="host")
     p = ctx.upload(bases, offsets=offs).to_packed().extract_canonical_wide(63, enc, digest=True, to="host")
     assert np.array_equal(a.canon, p.canon) and np.array_equal(a.hash, p.hash) and a.digest == p.digest
+
+
+def test_push_chars_grows_a_sequence_like_seqvector(ctx):
+    """SeqVector::with_capacity + push_chars (seq_vector.rs:135-161), pieces of every length class (the reference pushes a
+    partial first word and then whole words; the bit image is the concatenation either way): after every push the store
+    equals the oracle's SeqVector of everything pushed so far, and extraction / minimizers see the grown sequence."""
+    import kmers_b200 as kb
+    import oracle as ko
+    rng = np.random.default_rng(21)
+    b = ctx.new_packed(16)
+    total = b""
+    for n in (1, 31, 32, 33, 5, 64, 1000, 3, 4097):
+        piece = bytes(rng.choice(list(b"ACGTacgt"), size=n).astype(np.uint8))
+        b.push_chars(piece)
+        total += piece
+        words = b.download().view(np.uint64)
+        assert np.array_equal(words[: (len(total) + 31) // 32], ko.sv_from_bytes(total.upper()))
+    k = 31
+    res = b.extract_canonical(k, want_fw_rc=True, to="host")
+    ref = ko.extract_canonical(np.frombuffer(total, dtype=np.uint8), k, n_reads=1, fixed_len=len(total), want_fw_rc=True)
+    assert np.array_equal(res.canon, ref["canon"]) and np.array_equal(res.fw, ref["fw"]) and np.array_equal(res.hash, ref["hash"])
+    mm, pos = b.minimizers(31, 15)
+    rm, rp = ko.minimizers_batch(np.frombuffer(total, dtype=np.uint8), 31, 15, 15, n_reads=1, fixed_len=len(total))
+    assert np.array_equal(mm, rm) and np.array_equal(pos, rp)
+    with pytest.raises(kb.KmbPanic):  # Kmer::from panics on N: nothing is appended
+        b.push_chars(b"ACGTNACGT")
+    assert b.fixed_len == len(total) and np.array_equal(b.extract_canonical(k, to="host").canon, ref["canon"])
+    with pytest.raises(kb.KmbError):  # a batch of several reads is not a SeqVector
+        ctx.upload(b"ACGT" * 20, fixed_len=40).to_packed().push_chars(b"AC")
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_slice_is_a_view_of_one_read(ctx, ragged):
+    """SeqVector::slice / SeqVectorSlice (seq_vector.rs:24-90): get_kmer_u64, iter_kmers and iter_minimizers of a slice equal
+    those of the sub-sequence; unslice restores the batch."""
+    import kmers_b200 as kb
+    import oracle as ko
+    rng = np.random.default_rng(8 + ragged)
+    if ragged:
+        lens = rng.integers(200, 700, size=12)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        bases = np.frombuffer(bytes(rng.choice(list(b"ACGT"), size=int(offs[-1])).astype(np.uint8)), dtype=np.uint8)
+        batch = ctx.upload(bases, offsets=offs).to_packed()
+    else:
+        lens = np.full(12, 333)
+        offs = (np.arange(13) * 333).astype(np.uint64)
+        bases = np.frombuffer(bytes(rng.choice(list(b"ACGT"), size=12 * 333).astype(np.uint8)), dtype=np.uint8)
+        batch = ctx.upload(bases, fixed_len=333).to_packed()
+    whole = batch.extract_canonical(31, to="host").canon.copy()
+    for read, start, length in ((0, 0, int(lens[0])), (3, 17, 100), (7, 1, 31), (11, int(lens[11]) - 40, 40), (5, 50, 0), (2, 33, 30)):
+        sub = bases[int(offs[read]) + start: int(offs[read]) + start + length]
+        batch.slice(read, start, length)
+        res = batch.extract_canonical(31, want_fw_rc=True, to="host")
+        ref = ko.extract_canonical(sub, 31, n_reads=1, fixed_len=length, want_fw_rc=True)
+        assert res.n_slots == max(0, length - 30)
+        assert np.array_equal(res.fw, ref["fw"]) and np.array_equal(res.canon, ref["canon"]) and np.array_equal(res.hash, ref["hash"])
+        if length >= 31:
+            mm, pos = batch.minimizers(31, 15)
+            rm, rp = ko.minimizers_batch(sub, 31, 15, 15, n_reads=1, fixed_len=length)
+            assert np.array_equal(mm, rm) and np.array_equal(pos, rp)
+        if length >= 9:
+            p = np.arange(0, length - 8, 7, dtype=np.uint64)
+            got = batch.get_kmers(9, p)
+            want = [ko.sv_get_kmer_u64(ko.sv_from_bytes(sub.tobytes()), length, int(q), 9) for q in p]
+            assert got.tolist() == want
+    with pytest.raises(kb.KmbPanic):  # assert!(end <= self.len())
+        batch.slice(1, 10, int(lens[1]))
+    batch.unslice()
+    assert np.array_equal(batch.extract_canonical(31, to="host").canon, whole)
