@@ -311,7 +311,7 @@ def main():
     torch.cuda.set_stream(stream)  # torch work, the kernels and the timing events all share this stream
     ctx = kb.Context(local_rank, stream=stream.cuda_stream)
     cores = len(os.sched_getaffinity(0)) or 1
-    host_threads = max(1, cores // world)  # the ranks of one box share its cores
+    host_threads = max(1, cores // world - 1)  # the ranks of one box share its cores; one of a rank's cores drives the pipeline
     ctx.set_host_threads(host_threads)
     peak, peak_src = hbm_peak()
     i64 = lambda n: torch.empty(n, dtype=torch.int64, device="cuda")

@@ -183,7 +183,8 @@ int32_t kmb_histogram(kmb_ctx *ctx, uint32_t k, uint32_t flags, uint32_t hist_bi
  * The call chunks the reads and overlaps, on three streams: host-side packing of the ASCII bytes to 2 bits + 1 validity
  * bit per base by a pool of worker threads (3 bits/base cross PCIe instead of 8; for pageable input this doubles as the
  * staging copy), H2D, the extraction kernel, and the D2H of results.  When the input is pinned, chunks the packers have
- * not reached are also sent as raw ASCII whenever the link would otherwise idle.  Only format conversion and copies run
+ * not reached are also sent as raw ASCII whenever the link would otherwise idle (and with fewer than 6 worker threads --
+ * many ranks sharing one host, whose memory system is then the bottleneck -- pinned input is not packed at all).  Only format conversion and copies run
  * on the host: every k-mer is computed by the GPU kernel.  Synchronous.  This is the device-resident read-batch buffer
  * with pinned-host staging that BASELINE.json's north_star names. */
 int32_t kmb_extract_canonical_host(kmb_ctx *ctx, const uint8_t *host_bases, uint64_t n_reads,

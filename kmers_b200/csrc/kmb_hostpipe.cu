@@ -83,7 +83,8 @@ int32_t pipe_create(kmb_ctx* ctx) {
 unsigned default_threads(const kmb_ctx* ctx) {
     if (ctx->host_threads) return ctx->host_threads;
     if (const char* e = getenv("KMB_HOST_THREADS")) { const int n = atoi(e); if (n > 0) return (unsigned)n; }
-    return std::min(kmbhost::usable_cpus(), 32u);
+    const unsigned cpus = kmbhost::usable_cpus();  // one of them drives the pipeline (measured: 15 packers beat 16 on 16 cores)
+    return std::min(cpus > 1 ? cpus - 1 : 1u, 32u);
 }
 
 int32_t ensure_pool(kmb_ctx* ctx, HostPipe* p) {
@@ -132,7 +133,12 @@ int32_t run_pipeline(kmb_ctx* ctx, HostPipe* p, const Plan& pl) {
     const uint64_t L = pl.L, W = pl.W, rpc = pl.rpc, n_chunks = pl.n_chunks;
     const bool prepacked = pl.ascii == nullptr;
     const bool pinned_in = kmb_i_is_pinned_ptr(prepacked ? (const void*)pl.pre_bits : (const void*)pl.ascii);
-    const bool allow_pack = !prepacked && (env_flag("KMB_PIPE_PACK", true) || !pinned_in);
+    // Packing pays when the link is the bottleneck and there are threads to feed it.  With a handful of threads per rank --
+    // many ranks sharing one host -- the host's memory system is the bottleneck instead, and packing (read 1 B/base, write
+    // and re-read 0.375) only adds traffic: measured on 8 ranks x 3 threads, 77 ms per step against 65 ms for raw copies
+    // alone.  Pinned input then goes out as it is (pageable input still has to be staged by someone: the packers).
+    const bool pack_default = default_threads(ctx) >= 6;
+    const bool allow_pack = !prepacked && (env_flag("KMB_PIPE_PACK", pack_default) || !pinned_in);
     const bool allow_raw = !prepacked && pinned_in && (env_flag("KMB_PIPE_RAW", true) || !allow_pack);
     const bool host_out = (pl.out[0] && !pl.out_dev[0]) || (pl.out[1] && !pl.out_dev[1]);
     int32_t rc;

@@ -95,7 +95,7 @@ def main():
         for k_ in env:
             os.environ.pop(k_, None)
 
-    tset = sorted({max(1, cores // 8), max(1, cores // 4), max(1, cores // 2), cores})
+    tset = sorted({max(1, cores // 4), max(1, cores // 2), max(1, cores - 1), cores})
     for t in tset:
         run("hybrid (default) chunk 8 MB, device arrays", {}, t)
     for mb in ("4", "16", "32"):

@@ -298,6 +298,8 @@ def test_host_pipeline_single_paths(ctx, ko, monkeypatch, mode):
     import torch
     monkeypatch.setenv("KMB_PIPE_CHUNK_MB", "1")
     monkeypatch.setenv("KMB_PIPE_RAW" if mode == "pack_only" else "KMB_PIPE_PACK", "0")
+    if mode == "pack_only":
+        monkeypatch.setenv("KMB_PIPE_PACK", "1")  # (the default turns packing of pinned input off on hosts with few cores)
     n, L, k = 40_000, 150, 31
     bases, ref, rdig = _host_case(ko, n, L, k, thresh=2000)
     t = torch.empty(n * L, dtype=torch.uint8, pin_memory=True)

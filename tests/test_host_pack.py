@@ -86,3 +86,25 @@ def test_every_simd_variant_agrees(kb, isa):
     # the variant that ran is the requested one, or the best this CPU has below it
     assert out[0] in {"swar": ("swar",), "avx2": ("avx2", "swar"), "avx512bw": ("avx512bw", "avx2", "swar"),
                       "avx512gfni": ("avx512gfni", "avx512bw", "avx2", "swar")}[isa]
+
+
+def _aligned(n, dtype, align=64):
+    raw = np.empty(n * np.dtype(dtype).itemsize + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * np.dtype(dtype).itemsize].view(dtype)
+
+
+@pytest.mark.parametrize("n", [65536, 65536 + 64, 300_007, 1 << 20])
+def test_aligned_and_unaligned_destinations(kb, n):
+    """Cache-line aligned outputs of >= 64 Ki bases (the pipeline's pinned staging rings: the interleaved-stream path) and
+    destinations 4 bytes off a line give the reference bytes."""
+    rng = np.random.default_rng(n)
+    b = np.frombuffer(bytes(rng.choice(list(b"ACGTacgtNRY\n"), size=n, p=[.2, .2, .2, .2, .04, .04, .04, .04, .01, .01, .01, .01]).astype(np.uint8)), dtype=np.uint8)
+    nw = (n + 15) // 16
+    rb, ri = _reference(b)
+    bits, inv = kb.host_pack(b, _aligned(nw, np.uint32), _aligned(nw, np.uint16))
+    assert bits.ctypes.data % 64 == 0 and inv.ctypes.data % 64 == 0
+    assert np.array_equal(bits, rb) and np.array_equal(inv, ri)
+    ub = _aligned(nw + 1, np.uint32)[1:]  # 4 bytes off a line
+    bits2, inv2 = kb.host_pack(b, ub, _aligned(nw + 1, np.uint16)[1:])
+    assert np.array_equal(bits2, rb) and np.array_equal(inv2, ri)
