@@ -627,24 +627,25 @@ __global__ void __launch_bounds__(256) read_counts_kernel(const uint64_t* offset
     else counts[r] = (len + div - 1) / div;                             // packed words
 }
 
-// first_read[b] = read owning slot b * slots_per_cta (b < grid); first_read[grid] = read owning the last slot.
-// One thread per CTA of the extraction grid: the log2(n_reads)-deep searches all run concurrently here
-// instead of serially at the head of every extraction CTA.  The same thread works out the tile's staged stretch
-// (CsrTileDesc) when the whole tile fits one pass of tile_bases bases.
+// One thread per CTA of the extraction grid: the read owning the tile's first slot (a log2(n_reads)-deep search: all of them
+// run concurrently here instead of serially at the head of every extraction CTA), the reads owning its last slot and the
+// next tile's first, and the tile's staged stretch when the whole tile fits one pass of tile_bases bases -- everything a
+// CTA needs before its first fetch, in one 32-byte descriptor.
 __global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* offsets, const uint64_t* win_offsets, uint64_t n_reads, uint64_t total_slots,
                                                         uint64_t slots_per_cta, uint64_t grid, uint32_t k, uint32_t tile_bases,
-                                                        uint64_t* first_read, CsrTileDesc* tile_desc) {
+                                                        CsrTileDesc* tile_desc) {
     const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > grid) return;
-    const uint64_t slot = b < grid ? b * slots_per_cta : total_slots - 1;
+    if (b >= grid) return;
+    const uint64_t slot = b * slots_per_cta;
     const uint64_t r_lo = last_le(win_offsets, 0, n_reads - 1, slot);  // skips window-less reads: takes the last equal entry
-    first_read[b] = r_lo;
-    if (b == grid) return;
     const uint64_t slot_end = min(total_slots, slot + slots_per_cta);
     const uint64_t r_last = last_le(win_offsets, r_lo, n_reads - 1, slot_end - 1);
+    const uint64_t r_hi = slot_end < total_slots ? last_le(win_offsets, r_last, n_reads - 1, slot_end) : r_last;
     CsrTileDesc td;
     td.g0 = offsets[r_lo] + (slot - win_offsets[r_lo]);
-    td.r_last = r_last;
+    td.r_lo = r_lo;
+    td.d_last = (uint32_t)(r_last - r_lo);
+    td.d_hi = (uint32_t)min(r_hi - r_lo, (uint64_t)0xFFFFFFFFu);
     const uint64_t g_end = offsets[r_last] + (slot_end - 1 - win_offsets[r_last]) + k;
     td.span = g_end - td.g0 <= (uint64_t)tile_bases ? (uint32_t)(g_end - td.g0) : 0xFFFFFFFFu;
     td.pad = 0;

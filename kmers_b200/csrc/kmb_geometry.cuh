@@ -347,9 +347,11 @@ constexpr int kCsrGroup = 8;     // items per entry of the per-pass owner table
 // What a CTA of the ragged kernels needs to know before it can fetch anything, precomputed per tile by csr_index_kernel
 // for the common case that the tile's whole stretch fits one staged pass: the CTA then starts staging at once, with no
 // serial set-up by thread 0 and one barrier less.
-struct CsrTileDesc {
+struct alignas(16) CsrTileDesc {
     uint64_t g0;      // flat base index of the first base the tile needs
-    uint64_t r_last;  // read owning the tile's last slot
+    uint64_t r_lo;    // read owning the tile's first slot
+    uint32_t d_last;  // read owning the tile's last slot, counted from r_lo
+    uint32_t d_hi;    // read owning the NEXT tile's first slot (the last slot's, for the last tile), counted from r_lo
     uint32_t span;    // bases from g0 to the last window's last base; 0xFFFFFFFF: more than one pass (set up in the kernel)
     uint32_t pad;
 };
@@ -360,8 +362,7 @@ struct CsrGeom {
     uint64_t n_bases;             // length of the flat base index space (ASCII: n_bytes; packed: 4 * n_bytes)
     const uint64_t* offsets;      // n_reads + 1: flat base index of every read's first base
     const uint64_t* win_offsets;  // n_reads + 1, exclusive prefix of per-read window counts
-    const uint64_t* first_read;   // grid + 1: read owning each CTA's first slot (csr_index_kernel)
-    const CsrTileDesc* tile_desc; // grid entries (csr_index_kernel)
+    const CsrTileDesc* tile_desc; // grid entries (csr_index_kernel): everything a CTA needs before its first fetch, in ONE load
     uint64_t n_reads;
     uint64_t total_slots;
     uint32_t items_per_cta;
@@ -426,7 +427,11 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
     __shared__ uint64_t grp[kMaxItemsPerCta / kCsrGroup + 1];
 
     // reads this CTA can touch; their offsets go to shared memory when they fit (the common case)
-    const uint64_t R_lo = g.first_read[tile_idx], R_hi = g.first_read[tile_idx + 1];
+    const uint4 td_a = __ldg(reinterpret_cast<const uint4*>(g.tile_desc + tile_idx));
+    const uint4 td_b = __ldg(reinterpret_cast<const uint4*>(g.tile_desc + tile_idx) + 1);
+    CsrTileDesc td;
+    td.g0 = mk64(td_a.x, td_a.y); td.r_lo = mk64(td_a.z, td_a.w); td.d_last = td_b.x; td.d_hi = td_b.y; td.span = td_b.z;
+    const uint64_t R_lo = td.r_lo, R_hi = td.r_lo + td.d_hi;
     const uint64_t* off = g.offsets;  // tables indexed by absolute read number
     const uint64_t* win = g.win_offsets;
     if (R_hi - R_lo + 2 <= (uint64_t)kCsrCache + 2) {
@@ -444,10 +449,9 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
     // csr_index_kernel already worked out.  Staging starts at once, next to the loads of the offsets (one barrier for
     // both), and the per-group owner table is filled by the reads themselves -- every read marks the groups whose first
     // slot it owns -- instead of one binary search per group.
-    const CsrTileDesc td = g.tile_desc[tile_idx];
     if (off != g.offsets && td.span != 0xFFFFFFFFu) {
         CsrPass ps;
-        ps.slot_lo = slot_begin; ps.slot_hi = slot_end; ps.r_lo = R_lo; ps.r_hi = td.r_last; ps.g0 = td.g0; ps.span = td.span;
+        ps.slot_lo = slot_begin; ps.slot_hi = slot_end; ps.r_lo = R_lo; ps.r_hi = R_lo + td.d_last; ps.g0 = td.g0; ps.span = td.span;
         const uint32_t n_slots = (uint32_t)(ps.slot_hi - ps.slot_lo);
         const uint32_t n_items = Shape::n_items(n_slots);
         const uint32_t n_groups = (n_items + kCsrGroup - 1) / kCsrGroup;

@@ -542,15 +542,13 @@ static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, Cs
     if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
     l->grid = (unsigned)ctas;
     l->smem = (size_t)g->tile_entries * sizeof(uint2) + 2 * (size_t)(kCsrCache + 2) * sizeof(uint64_t);
-    // [ctas + 1 first reads | ctas tile descriptors]
-    if ((rc = grow(ctx, (void**)&ctx->d_first_read, &ctx->first_read_cap, (ctas + 1) * 8 + ctas * sizeof(CsrTileDesc)))) return rc;
-    g->first_read = ctx->d_first_read;
-    CsrTileDesc* d_desc = reinterpret_cast<CsrTileDesc*>(ctx->d_first_read + ctas + 1);
+    if ((rc = grow(ctx, (void**)&ctx->d_first_read, &ctx->first_read_cap, (ctas + 1) * sizeof(CsrTileDesc)))) return rc;
+    CsrTileDesc* d_desc = reinterpret_cast<CsrTileDesc*>(ctx->d_first_read);
     g->tile_desc = d_desc;
     if (ctas) {
         const uint32_t tile_bases = (g->tile_entries - span_entries - 1) * 16;  // as csr_body computes it
-        csr_index_kernel<<<(unsigned)((ctas + 1 + 255) / 256), 256, 0, ctx->stream>>>(g->offsets, ctx->d_win_offsets, ctx->n_reads, g->total_slots,
-                                                                                   slots_per_cta, ctas, k, tile_bases, ctx->d_first_read, d_desc);
+        csr_index_kernel<<<(unsigned)((ctas + 255) / 256), 256, 0, ctx->stream>>>(g->offsets, ctx->d_win_offsets, ctx->n_reads, g->total_slots,
+                                                                               slots_per_cta, ctas, k, tile_bases, d_desc);
         CK(ctx, cudaGetLastError());
         ctx->launches++;
     }

@@ -32,8 +32,10 @@ d = {h[i]: (u[i], v[i]) for i in range(len(h))}
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 rd = float(d["dram__bytes_read.sum"][1]) * scale[d["dram__bytes_read.sum"][0]]
 wr = float(d["dram__bytes_write.sum"][1]) * scale[d["dram__bytes_write.sum"][0]]
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (kernel_source_sha1: the hash of the CUDA sources the captured kernel was built from)
 out = {"dram_bytes_per_launch_at_bench_size": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
-       "algorithmic_bytes": 20_700_000_000,
+       "algorithmic_bytes": 20_700_000_000, "kernel_source_sha1": bench.kernel_source_sha1(),
        "source": f"profiles/{os.path.basename(raw)} (ncu --set full, one launch of the bench kernel, 10^7 x 150 bp, K=31): "
                  "dram__bytes_read.sum + dram__bytes_write.sum"}
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)

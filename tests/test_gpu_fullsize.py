@@ -1,6 +1,7 @@
 """BASELINE.json configs at their FULL sizes, checked through size-independent properties (the oracle cannot
 materialise 19 GB in seconds, so: digests from the multi-threaded oracle, sums of the materialised arrays,
 idempotence, hash-of-canonical, strand symmetry, and bit-exact comparison of random chunks)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -102,26 +103,41 @@ def test_config3_k63_two_words_full_size():
 
 
 def test_config4_long_reads_full_size():
-    """10^5 x 10 kbp with ~0.1 % N: digest vs the multi-threaded oracle, sums of arrays, chunk compare."""
+    """10^5 x 10 kbp with the full SURVEY 8(d) C4 mixture -- per read one run of N of 1..200 bases, ~0.1 % isolated N,
+    soft-masked (lower-case, still valid) 500-base spans on 5 % of the reads, IUPAC letters and newlines: the WHOLE input's
+    digest vs the multi-threaded oracle on the same bytes, sums of arrays, chunk compares."""
     import torch
     import kmers_b200 as kb
     import oracle as ko
+    import bench  # the mixture recipe the driver-clocked config-4 row uses
+    from kmers_b200.context import _ptr
     n, Lr = 100_000, 10_000
     with kb.Context(0, stream=torch.cuda.current_stream().cuda_stream) as ctx:
-        batch = ctx.generate(43, n, Lr, n_thresh20=1049)
+        flat = torch.empty(n * Lr, dtype=torch.uint8, device="cuda")
+        ctx.generate(43, n, Lr, n_thresh20=1049)
+        ctx._ck(ctx._lib.kmb_batch_download(ctx._h, _ptr(flat), n * Lr))
+        bench.c4_mixture(torch, np, flat, n, Lr)
+        bases = flat.cpu().numpy()
+        assert (bases == ord("N")).sum() > 1.0e7 and ((bases >= 97) & (bases <= 122)).sum() > 2.0e6  # runs of N, lower case
+        assert (bases == ord("\n")).sum() > 2000 and np.isin(bases, list(b"RYKM")).sum() > 2000
+        batch = ctx.attach(flat, fixed_len=Lr)
         res = batch.extract_canonical(K, digest=True, to="device")
         torch.cuda.synchronize()
         valid = res.canon != -1
         assert res.digest[0] == int(valid.sum().item())
         assert res.digest[1] == _u64sum(torch.where(valid, res.canon, torch.zeros_like(res.canon)))
-        bases = ko.generate_bases(43, 0, n * Lr, 1049)
         ref = ko.extract_canonical(bases, K, n_reads=n, fixed_len=Lr, n_threads=os.cpu_count() or 1, materialize=False)
         assert res.digest == (ref["n_valid"], ref["checksum_canon"], ref["checksum_hash"])
+        assert ref["n_valid"] < 0.97 * n * (Lr - K + 1)  # the N runs and isolated N invalidate > 3 % of the windows
         wr = Lr - K + 1
-        for r0 in (0, 77_777, n - 20):
+        for r0 in (0, 37 * 1000, 77_777, n - 20):
             ref = ko.extract_canonical(bases[r0 * Lr:(r0 + 20) * Lr], K, n_reads=20, fixed_len=Lr)
             assert np.array_equal(res.canon[r0 * wr:(r0 + 20) * wr].cpu().numpy().view(np.uint64), ref["canon"])
             assert np.array_equal(res.hash[r0 * wr:(r0 + 20) * wr].cpu().numpy().view(np.uint64), ref["hash"])
+        # the same bytes through the iterator-identical stream: its length is the digest's count
+        m = C.c_uint64()
+        ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, K, 0, None, None, None, None, 0, C.byref(m)))
+        assert int(m.value) == res.digest[0]
 
 
 def test_more_than_2_pow_32_slots():
