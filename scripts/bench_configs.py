@@ -246,9 +246,9 @@ def main():
     cpu_rows.append({"config": "config2 sample (2M reads) iterator + canonical + LexHash, materialised", "cores": cores, "kmers_per_s": ns * 120 / t})
     t = cpu_time(lambda: ko.bench_windows(hb, 31, n_reads=ns, fixed_len=150, n_threads=cores, materialize=False))
     cpu_rows.append({"config": "config2 sample (2M reads) bench-faithful per-window O(K) re-encode", "cores": cores, "kmers_per_s": ns * 120 / t})
-    n3 = 20_000 // scale
-    t = cpu_time(lambda: ko.extract_canonical_wide(hb[:n3 * 150], 63, n_reads=n3, fixed_len=150, want_hash=False), reps=1)
-    cpu_rows.append({"config": "config3 sample (20k reads) K=63 encode + swap-loop rev_comp per window (1 thread)", "cores": 1, "kmers_per_s": n3 * 88 / t})
+    n3 = 200_000 // scale
+    t = cpu_time(lambda: ko.extract_canonical_wide(hb[:n3 * 150], 63, n_reads=n3, fixed_len=150, want_hash=False, n_threads=cores), reps=1)
+    cpu_rows.append({"config": "config3 sample (200k reads) K=63 encode + swap-loop rev_comp per window", "cores": cores, "kmers_per_s": n3 * 88 / t})
     n4 = 20_000 // scale
     hb4 = ko.generate_bases(43, 0, n4 * 10_000, 1049)
     t = cpu_time(lambda: ko.extract_canonical(hb4, 31, n_reads=n4, fixed_len=10_000, n_threads=cores, materialize=False))
