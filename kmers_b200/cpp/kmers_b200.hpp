@@ -183,6 +183,62 @@ class Context {
         return {std::move(mm), std::move(off)};
     }
 
+    // Kmer::sub_kmer_word (naive_impl/kmer.rs:150-161)
+    std::vector<uint64_t> sub_kmer(const std::vector<uint64_t>& words, uint32_t k, uint32_t pos, uint32_t width) {
+        std::vector<uint64_t> out(words.size());
+        detail::check(ctx_, kmb_sub_kmer_words(ctx_, k, pos, width, words.data(), out.data(), words.size()));
+        return out;
+    }
+    // Kmer::append_base_u8 (naive_impl/kmer.rs:83-102) / prepend_base_u8 (:76-95): shifted words + the bases shifted off
+    std::pair<std::vector<uint64_t>, std::vector<uint8_t>> append_base_u8(const std::vector<uint64_t>& words, const std::string& bases, uint32_t k) {
+        std::vector<uint64_t> out(words.size());
+        std::vector<uint8_t> dropped(words.size());
+        detail::check(ctx_, kmb_append_base_words(ctx_, k, words.data(), reinterpret_cast<const uint8_t*>(bases.data()), 1, out.data(),
+                                                  dropped.data(), words.size()));
+        return {std::move(out), std::move(dropped)};
+    }
+    std::pair<std::vector<uint64_t>, std::vector<uint8_t>> prepend_base_u8(const std::vector<uint64_t>& words, const std::string& bases, uint32_t k) {
+        std::vector<uint64_t> out(words.size());
+        std::vector<uint8_t> dropped(words.size());
+        detail::check(ctx_, kmb_prepend_base_words(ctx_, k, words.data(), reinterpret_cast<const uint8_t*>(bases.data()), 1, out.data(),
+                                                   dropped.data(), words.size()));
+        return {std::move(out), std::move(dropped)};
+    }
+    // bitmer_to_bytes (kmer.rs:71-91): upper case, A0 C1 G2 T3
+    std::vector<std::string> bitmer_to_bytes(const std::vector<uint64_t>& mers, uint32_t len) {
+        std::string flat(mers.size() * len, '\0');
+        detail::check(ctx_, kmb_bitmer_to_bytes(ctx_, len, mers.data(), mers.size(), reinterpret_cast<uint8_t*>(&flat[0])));
+        std::vector<std::string> out(mers.size());
+        for (size_t i = 0; i < mers.size(); ++i) out[i] = flat.substr(i * len, len);
+        return out;
+    }
+    // Kmer::<P,K,B>::get / get_prefix (kmer.rs:46-53) on every array
+    template <class P, size_t B>
+    std::vector<uint8_t> get(const std::vector<std::array<P, B>>& arrays, uint32_t index) {
+        std::vector<uint8_t> out(arrays.size());
+        detail::check(ctx_, kmb_kmer_get(ctx_, sizeof(P) * 8, B, arrays.data(), arrays.size(), index, out.data()));
+        return out;
+    }
+    template <class P, size_t B>
+    std::vector<P> get_prefix(const std::vector<std::array<P, B>>& arrays, uint32_t len) {
+        std::vector<P> out(arrays.size());
+        detail::check(ctx_, kmb_kmer_get_prefix(ctx_, sizeof(P) * 8, B, arrays.data(), arrays.size(), len, out.data()));
+        return out;
+    }
+
+    // One call on reads in host memory (packed by worker threads, H2D / kernel / D2H overlapped): CanonicalKmerIterator +
+    // get_canonical_word + LexHasher for every read, results in host vectors
+    CanonicalKmers canonical_kmers_host(const uint8_t* bases, uint64_t n_reads, uint64_t fixed_len, uint32_t k) {
+        CanonicalKmers r;
+        const uint64_t n = fixed_len >= k ? n_reads * (fixed_len - k + 1) : 0;
+        r.canon.resize(n);
+        r.hash.resize(n);
+        kmb_digest d{};
+        detail::check(ctx_, kmb_extract_canonical_host(ctx_, bases, n_reads, fixed_len, k, 0, r.canon.data(), r.hash.data(), &d));
+        r.digest = {d.n_valid, d.checksum_canon, d.checksum_hash};
+        return r;
+    }
+
     // ---- batched Encoding<P,B> on arrays [P;B]
     // Encoding::encode / Kmer::<P,K,B>::new for n k-mers of K ASCII bytes each (encoding/naive.rs:116-124)
     template <class P, size_t K, class Enc>

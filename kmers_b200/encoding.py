@@ -84,3 +84,23 @@ def rev_comp(ctx, enc: int, k: int, images: np.ndarray, word_bits: int) -> np.nd
     images = np.ascontiguousarray(images, dtype=np.uint8)
     n, nb = images.shape
     return ctx.revcomp_words(int(enc), k, word_bits, images, n, nb * 8 // word_bits).reshape(n, nb)
+
+
+def get(ctx, images: np.ndarray, word_bits: int, index: int) -> np.ndarray:
+    """Batched `Kmer::<P,K,B>::get(index)` (kmer.rs:46-48) on (n, bytes) images -> n 2-bit codes."""
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    n, nb = images.shape
+    return ctx.kmer_get(word_bits, nb * 8 // word_bits, images, n, index)
+
+
+def get_prefix(ctx, images: np.ndarray, word_bits: int, length: int) -> np.ndarray:
+    """Batched `Kmer::<P,K,B>::get_prefix(len)` (kmer.rs:50-52; the reference's inclusive 0..=2*len bit range)
+    on (n, bytes) images -> (n, word_bits/8) little-endian words."""
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    n, nb = images.shape
+    return ctx.kmer_get_prefix(word_bits, nb * 8 // word_bits, images, n, length)
+
+
+def bitmer_to_bytes(ctx, mers, length: int) -> np.ndarray:
+    """Batched `bitmer_to_bytes` (kmer.rs:71-91): u64 words -> (n, length) upper-case ASCII."""
+    return ctx.bitmer_to_bytes(mers, length)

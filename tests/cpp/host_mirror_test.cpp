@@ -135,6 +135,44 @@ int main() {
         auto km = b.get_kmers_u64(3, {}, {0, 2, 4, 5});
         CHECK(km[0] == kmer_word("act") && km[1] == kmer_word("ttg") && km[2] == kmer_word("gat") && km[3] == KMB_SENTINEL);
     }
+    {  // naive_impl/kmer.rs:325-384 test_append / test_prepend
+        auto a = ctx.append_base_u8({kmer_word("att"), kmer_word("ttcga")}, "cg", 3);
+        CHECK(a.first[0] == kmer_word("ttc") && a.second[0] == 0 /* A */);
+        auto a5 = ctx.append_base_u8({kmer_word("ttcga")}, "g", 5);
+        CHECK(a5.first[0] == kmer_word("tcgag") && a5.second[0] == 3 /* T */);
+        auto p3 = ctx.prepend_base_u8({kmer_word("att")}, "c", 3);
+        CHECK(p3.first[0] == kmer_word("cat") && p3.second[0] == 3);
+        auto p5 = ctx.prepend_base_u8({kmer_word("ttcga")}, "g", 5);
+        CHECK(p5.first[0] == kmer_word("gttcg") && p5.second[0] == 0);
+    }
+    {  // naive_impl/kmer.rs:530-542 test_sub_kmer
+        const std::string s = "ACTTGAT";
+        for (size_t i = 0; i < s.size(); ++i)
+            for (size_t j = i; j < s.size(); ++j)
+                CHECK(ctx.sub_kmer({kmer_word(s)}, 7, i, j - i)[0] == kmer_word(s.substr(i, j - i)));
+    }
+    {  // kmer.rs:46-53 get / get_prefix on [u64;2] and kmer.rs:71-91 bitmer_to_bytes
+        const std::string s45 = "TAAGGATTCTAATCATAAGGATTCTAATCATAAGGATTCTAATCA";
+        auto a = ctx.encode<uint64_t, 45>(Naive::ACGT, reinterpret_cast<const uint8_t*>(s45.data()), 1);
+        const char* letters = "ACGT";
+        for (uint32_t i = 0; i < 45; ++i) CHECK(letters[ctx.get(a, i)[0]] == s45[i]);
+        CHECK(ctx.get_prefix(a, 5)[0] == (a[0][0] & 0x7ffull));  // the reference's inclusive 0..=2*len range
+        CHECK(ctx.bitmer_to_bytes({kmer_word("acttgat"), kmer_word("ttttttt")}, 7) == (std::vector<std::string>{"ACTTGAT", "TTTTTTT"}));
+    }
+    {  // the pipelined host call = upload + canonical_kmers on the same reads
+        std::string flat;
+        std::vector<std::string> reads;
+        for (int r = 0; r < 64; ++r) {
+            std::string x(50, 'A');
+            for (int i = 0; i < 50; ++i) x[i] = "ACGTN"[(r * 7 + i * i + i / 3) % (r % 5 == 0 ? 5 : 4)];
+            reads.push_back(x);
+            flat += x;
+        }
+        auto h = ctx.canonical_kmers_host(reinterpret_cast<const uint8_t*>(flat.data()), 64, 50, 21);
+        auto d = ctx.upload(reads).canonical_kmers(21);
+        CHECK(h.canon == d.canon && h.hash == d.hash && h.digest.n_valid == d.digest.n_valid &&
+              h.digest.checksum_canon == d.digest.checksum_canon);
+    }
     std::printf(failures ? "FAILED (%d)\n" : "OK\n", failures);
     return failures ? 1 : 0;
 }

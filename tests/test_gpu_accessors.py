@@ -151,3 +151,15 @@ def test_prefix_and_bitmer_goldens(ctx, ko):  # kmer.rs:186-203
         for i in range(0, 1000, 41):
             ko.lib().ko_bitmer_to_bytes(int(mers[i]), length, buf)
             assert got[i].tobytes() == bytes(buf)
+
+
+def test_encoding_module_accessors(ctx, ko):  # kmer.rs:186-203 through kmers_b200.encoding, the mirror of encoding::*
+    from kmers_b200 import encoding as enc
+    s = b"TAAGGATTCTAATCATAAGGATTCTAATCATAAGGATTCTAATCA"
+    img = enc.encode(ctx, enc.Naive.ACGT, np.frombuffer(s, dtype=np.uint8).reshape(1, -1), 64)
+    assert img.shape == (1, 16)
+    letters = b"ACGT"
+    assert bytes(letters[int(enc.get(ctx, img, 64, i)[0])] for i in range(len(s))) == s
+    word0 = int.from_bytes(img[0, :8].tobytes(), "little")
+    assert int.from_bytes(enc.get_prefix(ctx, img, 64, 5)[0].tobytes(), "little") == word0 & 0x7FF
+    assert enc.bitmer_to_bytes(ctx, [word0], 32).tobytes() == s[:32]
