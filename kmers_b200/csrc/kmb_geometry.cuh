@@ -186,12 +186,13 @@ __device__ __forceinline__ uint32_t div_w(uint32_t u, const FixedGeom& g, uint32
 // The item loop.  Plain engines stride over the items.  Two-phase engines need every thread of the CTA to reach
 // round_end (it holds barriers) the same number of times and from ONE call site (`__syncthreads` is an aligned
 // barrier: all lanes of a warp must execute the same instruction), so they run CTA-uniform rounds.
-template <bool ROUNDS, class Item, class RoundEnd>
-__device__ __forceinline__ void for_each_item(uint32_t n_items, Item&& item, RoundEnd&& round_end) {
+template <bool ROUNDS, class Item, class RoundBegin, class RoundEnd>
+__device__ __forceinline__ void for_each_item(uint32_t n_items, Item&& item, RoundBegin&& round_begin, RoundEnd&& round_end) {
     if constexpr (ROUNDS) {
         const uint32_t rounds = (n_items + blockDim.x - 1) / blockDim.x;
         for (uint32_t q_round = 0; q_round < rounds; ++q_round) {
             const uint32_t li = q_round * blockDim.x + threadIdx.x;
+            round_begin(q_round);
             if (li < n_items) item(li);
             __syncwarp();
             round_end(q_round);
@@ -223,50 +224,75 @@ __device__ __forceinline__ void defer(uint32_t li) {
     d.li[atomicAdd(&d.n, 1u)] = (uint16_t)li;
 }
 
-// One pass over the items of a staged tile.  `item(li, one, two, single)` classifies item li and calls exactly one of
-// the three handlers (single: once per window).  Two-phase engines (compaction) first count the valid windows of
-// every item, scan the counts CTA-wide, then emit at the scanned offsets.
+// Two-phase engines (compaction), first half of a pass: count the valid windows of every item of the staged tile and scan the
+// counts CTA-wide.  Ends behind a barrier.
 template <class Eng, class Item>
-__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item, bool last_pass = true) {
+__device__ __forceinline__ void count_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item) {
+    eng.begin_pass(n_items);
+    __syncthreads();
+    auto count_one = [&](uint32_t rel, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+        eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, nwin));
+    };
+    auto count_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t, uint32_t nwin, const ItemCtx& ic) {
+        eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
+                             count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin));
+    };
+    auto count_single = [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
+        eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1));
+    };
+    for_each_item<true>(n_items, [&](uint32_t li) { item(li, count_one, count_two, count_single); }, [](uint32_t) {}, [](uint32_t) {});
+    __syncthreads();
+    eng.scan(n_items);
+    __syncthreads();
+}
+
+// ... second half: emit at the scanned offsets, in CTA-uniform rounds.  Two-phase engines cannot put their dirty items off to
+// a second sweep (their output order is fixed by the scan), so they run every item through the checking variant: a few
+// instructions per window instead of both variants per warp.
+template <class Eng, class Item, class AfterRound>
+__device__ __forceinline__ void emit_pass(Eng& eng, const uint2* tile, uint32_t n_items, Item&& item, AfterRound&& after_round) {
     constexpr uint32_t kAll = (uint32_t)Eng::Shape::kSpanSlots;
-    // Two-phase engines cannot put their dirty items off to a second sweep (their output order is fixed by the scan), so
-    // they run every item through the checking variant: a few instructions per window instead of both variants per warp.
-    constexpr bool kAlwaysCheck = Eng::kTwoPhase && Eng::kValidate;
     auto emit_one = [&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
         const typename Eng::Span s = eng.load(tile, rel);
-        if (kAlwaysCheck || (Eng::kValidate && eng.dirty(s))) eng.template run<false, true>(s, s, kAll, slot0, nwin, ic);
+        if (Eng::kValidate) eng.template run<false, true>(s, s, kAll, slot0, nwin, ic);
         else eng.template run<false, false>(s, s, kAll, slot0, nwin, ic);
     };
     auto emit_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
         const typename Eng::Span a = eng.load(tile, rel_a);
         const typename Eng::Span b = eng.load(tile, rel_b);
-        if (kAlwaysCheck || (Eng::kValidate && (eng.dirty(a) || eng.dirty(b)))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
+        if (Eng::kValidate) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
         else eng.template run<true, false>(a, b, left, slot0, nwin, ic);
     };
     auto emit_single = [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); };
+    for_each_item<true>(n_items, [&](uint32_t li) { item(li, emit_one, emit_two, emit_single); },
+                        [&](uint32_t q_round) { eng.round_begin(q_round); },
+                        [&](uint32_t q_round) { eng.round_end(q_round, n_items); after_round(q_round); });
+}
 
+// One pass over the items of a staged tile.  `item(li, one, two, single)` classifies item li and calls exactly one of
+// the three handlers (single: once per window).  Two-phase engines (compaction) first count the valid windows of
+// every item, scan the counts CTA-wide, then emit at the scanned offsets.
+template <class Eng, class Item>
+__device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K, uint32_t n_items, Item&& item, bool last_pass = true) {
     if constexpr (Eng::kTwoPhase) {
-        eng.begin_pass(n_items);
-        __syncthreads();
-        auto count_one = [&](uint32_t rel, uint64_t, uint32_t nwin, const ItemCtx& ic) {
-            eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, nwin));
-        };
-        auto count_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t, uint32_t nwin, const ItemCtx& ic) {
-            eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
-                                 count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin));
-        };
-        auto count_single = [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
-            eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1));
-        };
-        for_each_item<true>(n_items, [&](uint32_t li) { item(li, count_one, count_two, count_single); }, [](uint32_t) {});
-        __syncthreads();
-        eng.scan(n_items);
-        __syncthreads();
+        count_pass(eng, tile, K, n_items, item);
         if (Eng::kCountOnly) return;
-        eng.publish(last_pass);  // the tile's count goes out at once; where its entries start is looked up as late as possible (round_end)
-        for_each_item<true>(n_items, [&](uint32_t li) { item(li, emit_one, emit_two, emit_single); },
-                            [&](uint32_t q_round) { eng.round_end(q_round, n_items); });
+        eng.publish(last_pass);  // the tile's count goes out at once
+        emit_pass(eng, tile, n_items, item, [](uint32_t) {});
     } else {
+        constexpr uint32_t kAll = (uint32_t)Eng::Shape::kSpanSlots;
+        auto emit_one = [&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+            const typename Eng::Span s = eng.load(tile, rel);
+            if (Eng::kValidate && eng.dirty(s)) eng.template run<false, true>(s, s, kAll, slot0, nwin, ic);
+            else eng.template run<false, false>(s, s, kAll, slot0, nwin, ic);
+        };
+        auto emit_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
+            const typename Eng::Span a = eng.load(tile, rel_a);
+            const typename Eng::Span b = eng.load(tile, rel_b);
+            if (Eng::kValidate && (eng.dirty(a) || eng.dirty(b))) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
+            else eng.template run<true, false>(a, b, left, slot0, nwin, ic);
+        };
+        auto emit_single = [&](uint32_t rel, uint64_t slot, const ItemCtx& ic) { eng.single(tile, rel, slot, ic); };
         // sweep 1: the common path (one clean span); everything else is noted
         auto fast_one = [&](uint32_t rel, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
             const typename Eng::Span s = eng.load(tile, rel);
@@ -274,7 +300,7 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
             else eng.template run<false, false>(s, s, kAll, slot0, nwin, ic);
         };
         auto later_two = [&](uint32_t, uint32_t, uint32_t, uint64_t, uint32_t, const ItemCtx& ic) { defer(ic.li); };
-        for_each_item<false>(n_items, [&](uint32_t li) { item(li, fast_one, later_two, emit_single); }, [](uint32_t) {});
+        for_each_item<false>(n_items, [&](uint32_t li) { item(li, fast_one, later_two, emit_single); }, [](uint32_t) {}, [](uint32_t) {});
         __syncthreads();
         // sweep 2: the noted items, one per lane
         const Deferred& d = deferred();
@@ -283,59 +309,82 @@ __device__ __forceinline__ void run_pass(Eng& eng, const uint2* tile, uint32_t K
     }
 }
 
+// What a CTA knows about one tile of the fixed geometry (CTA-uniform)
+struct FixedTile {
+    uint64_t slot_base;  // first output slot
+    uint64_t r_first;    // read of that slot
+    uint32_t n_slots;
+    uint32_t p_first;    // position of the tile's first window in read r_first
+    uint32_t mis;        // offset of the tile's first base inside tile entry 0
+    uint32_t n_items;
+};
+
+// the stretch of the flat stream that holds tile tile_idx's windows: first base and length in bases; fills t except mis / n_items
+__device__ __forceinline__ void fixed_tile_range(const FixedGeom& g, uint32_t K, uint32_t tile_idx, FixedTile& t, uint64_t& g_start, uint32_t& span) {
+    const uint32_t slots_per_cta = g.items_per_cta * kRun;
+    t.slot_base = (uint64_t)tile_idx * slots_per_cta;
+    t.n_slots = (uint32_t)min((uint64_t)slots_per_cta, g.total_slots - t.slot_base);
+    if (g.W == 1) t.r_first = t.slot_base;
+    else if (g.w_magic64) t.r_first = div_magic64(t.slot_base, g.w_magic64);
+    else t.r_first = t.slot_base / g.W;
+    t.p_first = (uint32_t)(t.slot_base - t.r_first * g.W);
+    g_start = t.r_first * g.L + t.p_first;
+    const uint32_t u_last = t.p_first + t.n_slots - 1;
+    const uint32_t q_last = div_w(u_last, g, slots_per_cta);
+    // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
+    span = q_last * g.L32 + (u_last - q_last * g.W32) - t.p_first + K;
+}
+
+// phase 1: pack the stretch of the flat stream that holds the tile's windows (no barrier)
+template <class Eng>
+__device__ __forceinline__ FixedTile fixed_stage(const FixedGeom& g, const EncDesc& enc, uint32_t K, uint2* tile, uint32_t tile_idx) {
+    FixedTile t;
+    uint64_t g_start;
+    uint32_t span;
+    fixed_tile_range(g, K, tile_idx, t, g_start, span);
+    t.mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile, g.inv);
+    t.n_items = Eng::Shape::n_items(t.n_slots);
+    return t;
+}
+
+// phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than kRun windows, a run
+// of single windows
+template <class Shape, class One, class Two, class Single>
+__device__ __forceinline__ void fixed_item(const FixedGeom& g, const FixedTile& t, uint32_t li, One&& one, Two&& two, Single&& single) {
+    const uint32_t slots_per_cta = g.items_per_cta * kRun;
+    const uint32_t fs = Shape::first(li);              // the item's first slot, counted from the CTA's
+    if (fs >= t.n_slots) return;
+    const uint32_t u = t.p_first + fs;                 // ... and from window 0 of read r_first
+    const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
+    const uint32_t pos = u - q * g.W32;                 // window position inside its read
+    const uint64_t slot0 = t.slot_base + fs;
+    const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, t.n_slots - fs);
+    const uint32_t rel = q * g.L32 + pos - t.p_first + t.mis;  // first base, relative to tile entry 0
+    const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
+    const ItemCtx ic{li, t.r_first + q, pos, t.r_first + q + 1};
+    if (left >= (uint32_t)Shape::kSpanSlots || left >= nwin) {
+        one(rel, slot0, nwin, ic);
+    } else if (g.W32 >= (uint32_t)Shape::kSpanSlots) {
+        // straddles exactly one boundary: slots s >= left start read q+1 at position s - left
+        two(rel, (q + 1) * g.L32 - t.p_first + t.mis - left, left, slot0, nwin, ic);
+    } else {
+        for (uint32_t s = 0; s < nwin; ++s) {
+            if (!Shape::owns(s)) continue;
+            const uint32_t us = u + s, qs = div_w(us, g, slots_per_cta), ps = us - qs * g.W32;
+            single(qs * g.L32 + ps - t.p_first + t.mis, slot0 + s, ItemCtx{li, t.r_first + qs, ps, 0});
+        }
+    }
+}
+
 template <class Eng>
 __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint32_t tile_idx) {
     const uint32_t K = eng.K();
-    const uint32_t slots_per_cta = g.items_per_cta * kRun;
-    const uint64_t slot_base = (uint64_t)tile_idx * slots_per_cta;
-    const uint32_t n_slots = (uint32_t)min((uint64_t)slots_per_cta, g.total_slots - slot_base);
-    uint64_t r_first;
-    if (g.W == 1) r_first = slot_base;
-    else if (g.w_magic64) r_first = div_magic64(slot_base, g.w_magic64);
-    else r_first = slot_base / g.W;
-    const uint32_t p_first = (uint32_t)(slot_base - r_first * g.W);  // position of the CTA's first window in its read
-
-    // ---- phase 1: pack the stretch of the flat stream that holds the CTA's windows
-    const uint64_t g_start = r_first * g.L + p_first;
-    const uint32_t u_last = p_first + n_slots - 1;
-    const uint32_t q_last = div_w(u_last, g, slots_per_cta);
-    // bases from the first window's first base to the last window's last base (mod 2^32 exact: small)
-    const uint32_t span = q_last * g.L32 + (u_last - q_last * g.W32) - p_first + K;
-    const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, g_start, span, Eng::kSpanEntries, enc, tile, g.inv);
+    const FixedTile t = fixed_stage<Eng>(g, enc, K, tile, tile_idx);
     if constexpr (!Eng::kTwoPhase) deferred_reset();
     __syncthreads();
-
-    // ---- phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than
-    //      kRun windows, a run of single windows
     using Shape = typename Eng::Shape;
-    const uint32_t n_items = Shape::n_items(n_slots);
-    auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
-        {
-            const uint32_t fs = Shape::first(li);              // the item's first slot, counted from the CTA's
-            if (fs >= n_slots) return;
-            const uint32_t u = p_first + fs;                   // ... and from window 0 of read r_first
-            const uint32_t q = div_w(u, g, slots_per_cta);     // reads crossed since r_first
-            const uint32_t pos = u - q * g.W32;                 // window position inside its read
-            const uint64_t slot0 = slot_base + fs;
-            const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, n_slots - fs);
-            const uint32_t rel = q * g.L32 + pos - p_first + mis;  // first base, relative to tile entry 0
-            const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
-            const ItemCtx ic{li, r_first + q, pos, r_first + q + 1};
-            if (left >= (uint32_t)Shape::kSpanSlots || left >= nwin) {
-                one(rel, slot0, nwin, ic);
-            } else if (g.W32 >= (uint32_t)Shape::kSpanSlots) {
-                // straddles exactly one boundary: slots s >= left start read q+1 at position s - left
-                two(rel, (q + 1) * g.L32 - p_first + mis - left, left, slot0, nwin, ic);
-            } else {
-                for (uint32_t s = 0; s < nwin; ++s) {
-                    if (!Shape::owns(s)) continue;
-                    const uint32_t us = u + s, qs = div_w(us, g, slots_per_cta), ps = us - qs * g.W32;
-                    single(qs * g.L32 + ps - p_first + mis, slot0 + s, ItemCtx{li, r_first + qs, ps, 0});
-                }
-            }
-        }
-    };
-    run_pass(eng, tile, K, n_items, item);
+    auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape>(g, t, li, one, two, single); };
+    run_pass(eng, tile, K, t.n_items, item);
 }
 
 // ---------------------------------------------------------------------------

@@ -36,6 +36,10 @@ cudaError_t launch_hist_smem(bool validate, bool digest, bool khi, const FixedGe
 // kmb_tu_compact.cu: iterator-identical compacted stream
 cudaError_t launch_compact(bool count_only, bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
                            cudaStream_t st, const EncDesc& enc, const CompactParams& ep);
+// fixed-length reads, emit launch: persistent software-pipelined kernel (l.smem = ONE tile buffer, l.grid = tiles)
+size_t compact_pipe_tile_budget();  // bytes one tile buffer may take so that four CTAs fit an SM
+cudaError_t launch_compact_pipe(bool validate, bool khi, const FixedGeom& fg, const Launch& l, int device, cudaStream_t st, const EncDesc& enc,
+                                const CompactParams& ep);
 cudaError_t launch_compact_fixup(const uint64_t* win_offsets, uint64_t W, uint64_t n_reads, uint64_t slots_per_cta, const unsigned long long* desc,
                                  uint64_t* emit_offsets, cudaStream_t st);
 cudaError_t launch_compact_backfill(const uint64_t* win_offsets, uint64_t n_reads, const unsigned long long* total_emitted,

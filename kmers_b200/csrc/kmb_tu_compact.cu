@@ -1,4 +1,6 @@
 // kmb_tu_compact.cu -- instantiates the compaction engines (sizing count; single-pass emit) on both geometries.
+#include <algorithm>
+
 #include "kmb_launch.h"
 
 namespace kmb {
@@ -33,6 +35,36 @@ cudaError_t launch_compact(bool count_only, bool validate, bool khi, const Fixed
                            cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
     return count_only ? launch_compact<true>(validate, khi, fg, cg, l, st, enc, ep)
                       : launch_compact<false>(validate, khi, fg, cg, l, st, enc, ep);
+}
+
+// 228 KiB of shared memory per SM, 1 KiB of it reserved per resident CTA: what one of four CTAs can have
+static constexpr size_t kPipeCtaSmem = (228 * 1024) / 4 - 1024;
+
+size_t compact_pipe_tile_budget() { return ((kPipeCtaSmem - sizeof(CompactPipeShared)) / 2) & ~(size_t)15; }
+
+cudaError_t launch_compact_pipe(bool validate, bool khi, const FixedGeom& fg, const Launch& l, int device, cudaStream_t st, const EncDesc& enc,
+                                const CompactParams& ep) {
+    const uint32_t tile_bytes = (uint32_t)((l.smem + 15) & ~(size_t)15);
+    const size_t smem = 2 * (size_t)tile_bytes + sizeof(CompactPipeShared);
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+#define KMB_CASE(V, H)                                                                                                  \
+    if (validate == V && khi == H) {                                                                                    \
+        auto kern = compact_fixed_pipe_kernel<CompactEng<V, H, false, true>>;                                           \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+        if (e != cudaSuccess) return e;                                                                                 \
+        int per_sm = 0;                                                                                                 \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kExtractThreads, smem);                        \
+        if (e != cudaSuccess) return e;                                                                                 \
+        /* resident CTAs only: each walks the tiles by ticket (correct for any grid; more CTAs than fit would just queue) */ \
+        const unsigned grid = (unsigned)std::min<uint64_t>(l.grid, (uint64_t)sms * (uint64_t)std::max(per_sm, 1));     \
+        kern<<<grid, kExtractThreads, smem, st>>>(fg, enc, ep, tile_bytes, l.grid);                                     \
+        return cudaGetLastError();                                                                                      \
+    }
+    KMB_CASE(true, true) KMB_CASE(true, false) KMB_CASE(false, true) KMB_CASE(false, false)
+#undef KMB_CASE
+    return cudaErrorInvalidValue;
 }
 
 // The emit kernel wrote every read's first-entry index counted from its TILE's first entry (the tile's start is the last thing

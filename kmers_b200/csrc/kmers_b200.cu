@@ -499,7 +499,8 @@ static uint32_t mask32(uint32_t nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u
 // fixed-length reads: slot-space geometry of fixed_kernel
 static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n_reads, uint64_t L, uint32_t k,
                             uint32_t span_entries, FixedGeom* g, Launch* l, uint64_t stride = 0, uint32_t layout = KMB_I_ASCII,
-                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 36 * 1024, const uint16_t* d_inv = nullptr) {
+                            uint32_t ipc_max = kItemsPerCta, size_t smem_max = 36 * 1024, const uint16_t* d_inv = nullptr,
+                            bool fine_steps = false) {
     if (stride == 0) stride = L;
     g->bases = d_bases; g->n_bytes = n_bytes; g->L = stride; g->L32 = (uint32_t)stride; g->packed = layout; g->inv = d_inv;
     g->W = L - k + 1;
@@ -519,7 +520,8 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
         const uint64_t span = slots + crossings * (k - 1 + (stride - L)) + k + 32;
         l->smem = (size_t)((span + 15) / 16 + span_entries + 2) * sizeof(uint2);
         if (l->smem <= smem_max || ipc <= 64) break;
-        ipc /= 2;
+        // whole rounds of kExtractThreads items while that is possible (fine_steps), else halves
+        ipc = fine_steps && ipc > 2 * kExtractThreads ? ipc - kExtractThreads : ipc / 2;
     }
     g->items_per_cta = ipc;
     const uint64_t items = (g->total_slots + kRun - 1) / kRun;
@@ -734,6 +736,16 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     ep.wc = make_winconst(k, enc);
     ep.out.desc = ctx->d_cta_counts; ep.out.ticket = d_ticket; ep.out.total = d_total;
     const bool counting_call = !canon_out && !hash_out && !pos_out && !emit_offsets_out;
+    // fixed-length reads are emitted by the persistent pipelined kernel: two tile buffers per CTA, so the tiles may be smaller
+    const bool pipe = !csr && !counting_call;
+    if (pipe && !make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len,
+                                 ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII, kItemsPerCta, compact_pipe_tile_budget(), nullptr, true))
+        return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
+    if (pipe && (rc = grow(ctx, (void**)&ctx->d_cta_counts, &ctx->cta_counts_cap, ((size_t)l.grid + 2) * 8))) return rc;
+    if (pipe) {
+        d_ticket = ctx->d_cta_counts + l.grid; d_total = d_ticket + 1;
+        ep.out.desc = ctx->d_cta_counts; ep.out.ticket = d_ticket; ep.out.total = d_total;
+    }
     if (counting_call) {
         // sizing: count only (reads the bases, writes nothing but the total)
         CK(ctx, cudaMemsetAsync(d_total, 0, 8, ctx->stream));
@@ -755,15 +767,20 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     ep.out.emit_offsets = (uint64_t*)oe.dev;
     ep.out.capacity = cap;
     ep.out.vec16 = ((((uintptr_t)oc.dev | (uintptr_t)oh.dev) & 15u) == 0 && ((uintptr_t)op.dev & 7u) == 0) ? 1u : 0u;
+    ep.out.all_vec = (ep.out.vec16 && oc.dev && oh.dev && op.dev) ? 1u : 0u;
     CK(ctx, cudaMemsetAsync(ctx->d_cta_counts, 0, ((size_t)l.grid + 2) * 8, ctx->stream));
-    CK(ctx, launch_compact(false, validate, khi, pf, pc, l, ctx->stream, enc, ep));
+    if (pipe) CK(ctx, launch_compact_pipe(validate, khi, fg, l, ctx->device, ctx->stream, enc, ep));
+    else CK(ctx, launch_compact(false, validate, khi, pf, pc, l, ctx->stream, enc, ep));
     ctx->launches++;
     if (oe.dev) {
-        // the kernel wrote tile-local first-entry indices: add the tiles' starts (their inclusive prefixes are in the descriptors now)
-        const uint64_t slots_per_cta = (uint64_t)(csr ? cg.items_per_cta : fg.items_per_cta) * kRun;
-        CK(ctx, launch_compact_fixup(csr ? ctx->d_win_offsets : nullptr, csr ? 0 : fg.W, ctx->n_reads, slots_per_cta, ctx->d_cta_counts,
-                                     (uint64_t*)oe.dev, ctx->stream));
-        ctx->launches++;
+        if (!pipe) {
+            // the kernel wrote tile-local first-entry indices: add the tiles' starts (their inclusive prefixes are in the descriptors
+            // now).  The pipelined kernel knows a tile's start before it emits and writes final indices itself.
+            const uint64_t slots_per_cta = (uint64_t)(csr ? cg.items_per_cta : fg.items_per_cta) * kRun;
+            CK(ctx, launch_compact_fixup(csr ? ctx->d_win_offsets : nullptr, csr ? 0 : fg.W, ctx->n_reads, slots_per_cta, ctx->d_cta_counts,
+                                         (uint64_t*)oe.dev, ctx->stream));
+            ctx->launches++;
+        }
         CK(ctx, cudaMemcpyAsync((uint64_t*)oe.dev + ctx->n_reads, d_total, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (csr) {
             CK(ctx, launch_compact_backfill(ctx->d_win_offsets, ctx->n_reads, d_total, (uint64_t*)oe.dev, ctx->stream));
