@@ -379,17 +379,6 @@ __global__ void __launch_bounds__(256) unpack_flat_kernel(const uint8_t* __restr
         unpack_flat_body<false, false>(cta_words, left, bit_base, cta_off, cta_p0, item_bits, bases_per_item, bpi_magic, dec, out, total_letters, n_blocks_cta);
 }
 
-// ---------------------------------------------------------------- Encoding::rev_comp::<K>
-// encoding/naive.rs:138-154 / xor10.rs:86-103: fields 0..K-1 are reversed and
-// complemented, bits >= 2K untouched.  One thread = one item of NW32 32-bit
-// groups (item_bytes may be less than 4*NW32 for u8/u16 word types).
-__device__ __forceinline__ uint32_t get32_signed(const uint32_t* w, int nw, int bitpos) {
-    if (bitpos <= -32) return 0;
-    if (bitpos < 0) return w[0] << (-bitpos);
-    const int idx = bitpos >> 5, sh = bitpos & 31;
-    const uint32_t lo = idx < nw ? w[idx] : 0u, hi = (idx + 1) < nw ? w[idx + 1] : 0u;
-    return __funnelshift_r(lo, hi, sh);
-}
 
 // how an item is read and written: widest natural vector when item size and addresses allow, else words, else bytes
 template <int NW32>
@@ -442,6 +431,34 @@ struct ItemIo {
     }
 };
 
+// Encoding::rev_comp::<K> (encoding/naive.rs:138-154: swap base slots i and K-1-i, complement both; fields >= K keep what
+// they held) on the NW32 32-bit words of one array.  Reversing the whole array field by field puts field f at
+// 16 NW32 - 1 - f; K - 1 - f is that shifted right by s = 2 (16 NW32 - K) bits, and the shift leaves exactly the low 2K bits
+// occupied.  s is the same for every item: its word part WO selects the code, so every index below is a constant
+// (a run-time word index into a register array costs a select chain per access: this kernel ran at 72 % ALU, 77 % of
+// the copy peak, with one get32 per output word).
+template <int NW32, int WO>
+__device__ __forceinline__ void revcomp_array(const uint32_t (&w)[NW32], uint32_t (&o)[NW32], uint32_t K, uint32_t cmask, uint32_t sb) {
+    uint32_t r[NW32];
+#pragma unroll
+    for (int j = 0; j < NW32; ++j) r[j] = pair_reverse32(w[NW32 - 1 - j] ^ cmask);
+#pragma unroll
+    for (int i = 0; i < NW32; ++i) {
+        const uint32_t lo = i + WO < NW32 ? r[i + WO] : 0u, hi = i + WO + 1 < NW32 ? r[i + WO + 1] : 0u;
+        const int nvalid = max(0, min(16, (int)K - 16 * i));  // fields of this word below K
+        const uint32_t vmask = nvalid == 16 ? 0xFFFFFFFFu : ((1u << (2 * nvalid)) - 1u);
+        o[i] = __funnelshift_r(lo, hi, sb) | (w[i] & ~vmask);
+    }
+}
+template <int NW32, int WO = 0>
+__device__ __forceinline__ void revcomp_dispatch(const uint32_t (&w)[NW32], uint32_t (&o)[NW32], uint32_t K, uint32_t cmask, uint32_t wo,
+                                                 uint32_t sb) {
+    if constexpr (WO + 1 < NW32) {
+        if (wo != (uint32_t)WO) return revcomp_dispatch<NW32, WO + 1>(w, o, K, cmask, wo, sb);
+    }
+    revcomp_array<NW32, WO>(w, o, K, cmask, sb);
+}
+
 // kRevItems items per thread, a warp's items interleaved (item = base + u * 32 + lane) so that every load and store
 // instruction stays coalesced while each thread keeps kRevItems independent loads in flight.
 constexpr int kRevItems = 4;
@@ -450,6 +467,7 @@ __global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, u
                                                             uint32_t item_bytes, uint32_t K, uint32_t cmask) {
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * kRevItems + (threadIdx.x & 31u);
     const ItemIo<NW32> io(in, out, item_bytes);  // item stride keeps every item's alignment class equal to the first's
+    const uint32_t s = 2u * (16u * NW32 - K);    // 2K <= 8 item_bytes <= 32 NW32 (checked on the host)
     uint32_t w[kRevItems][NW32];
 #pragma unroll
     for (int u = 0; u < kRevItems; ++u) {
@@ -461,13 +479,7 @@ __global__ void __launch_bounds__(256) revcomp_items_kernel(const uint8_t* in, u
         const uint64_t item = warp0 + (uint64_t)u * 32;
         if (item >= n_items) continue;
         uint32_t o[NW32];
-#pragma unroll
-        for (int i = 0; i < NW32; ++i) {
-            const int nvalid = max(0, min(16, (int)K - 16 * i));  // fields of this group below K
-            const uint32_t vmask = nvalid == 16 ? 0xFFFFFFFFu : ((1u << (2 * nvalid)) - 1u);
-            const uint32_t srcbits = get32_signed(w[u], NW32, 2 * ((int)K - 16 * i - 16));
-            o[i] = (pair_reverse32(srcbits ^ cmask) & vmask) | (w[u][i] & ~vmask);
-        }
+        revcomp_dispatch<NW32>(w[u], o, K, cmask, s >> 5, s & 31u);
         io.store(out + item * item_bytes, item_bytes, o);
     }
 }

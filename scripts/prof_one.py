@@ -14,7 +14,8 @@ from kmers_b200.context import _ptr
 
 what = sys.argv[1]
 timed = "--time" in sys.argv
-n, L, K = 4_000_000, 150, 31
+scale = float(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 1.0  # problem size, times the default
+n, L, K = int(4_000_000 * scale), 150, 31
 torch.cuda.set_device(0)
 stream = torch.cuda.Stream()
 ctx = kb.Context(0, stream=stream.cuda_stream)
@@ -58,7 +59,7 @@ elif what in ("csr", "full", "csr_var"):
     step = lambda: batch.extract_canonical(K, out=out)
 elif what == "revcomp":
     import numpy as np
-    ni = 32_000_000
+    ni = int(32_000_000 * scale)
     words = torch.randint(0, 2**62, (2 * ni,), dtype=torch.int64, device="cuda")
     outw = torch.empty_like(words)
     alg = ni * 32
@@ -68,13 +69,13 @@ elif what == "canon":
     out = kb.CanonicalKmers(k=K, n_slots=n * W, canon=i64(n * W), hash=None)
     step = lambda: batch.extract_canonical(K, out=out)
 elif what == "minword":
-    nk = 50_000_000
+    nk = int(50_000_000 * scale)
     words = torch.randint(0, 2**62, (nk,), dtype=torch.int64, device="cuda")
     mmw, mmo = torch.empty_like(words), torch.empty(nk, dtype=torch.int32, device="cuda")
     alg = nk * 20
     step = lambda: ctx._ck(ctx._lib.kmb_minimizer_words(ctx._h, 31, 15, 15, _ptr(words), nk, _ptr(mmw), _ptr(mmo)))
 elif what == "unpack":
-    ni = 25_000_000
+    ni = int(25_000_000 * scale)
     words = torch.randint(0, 2**62, (ni,), dtype=torch.int64, device="cuda")
     txt = torch.empty(ni * 31, dtype=torch.uint8, device="cuda")
     alg = ni * (8 + 31)
@@ -85,6 +86,14 @@ elif what == "compact1":  # the single emit launch with worst-case arrays
     cc, ch, cp, ce = i64(n_slots), i64(n_slots), torch.empty(n_slots, dtype=torch.int32, device="cuda"), i64(n + 1)
     cnt = C.c_uint64()
     step = lambda: ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, K, 0, _ptr(cc), _ptr(ch), _ptr(cp), _ptr(ce), n_slots, C.byref(cnt)))
+elif what == "copy":  # a plain device copy of the same size class, for the size dependence of the copy peak itself
+    nb = int(512_000_000 * scale)
+    src = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    dst = torch.empty_like(src)
+    alg = 2 * nb
+    def step():
+        with torch.cuda.stream(stream):
+            dst.copy_(src)
 elif what in ("pack8", "pack64"):
     alg = n * L + n * ((L + 31) // 32) * 8
     bits = int(what[4:])
