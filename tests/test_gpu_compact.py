@@ -220,3 +220,60 @@ def test_count_then_repack_then_emit(ctx):
     assert int(m.value) == cap  # a packed store holds no invalid base: every window is emitted, and none beyond the arrays
     dense = b.extract_canonical(k, to="host")
     assert np.array_equal(canon, dense.canon)
+
+
+@pytest.mark.parametrize("n_reads", [1, 60, 69, 137, 300, 341])  # 120 windows per read, 8192 per tile: 1, 1, 2, 3, 5 and 5 tiles
+def test_pipelined_kernel_tile_counts_subsets_and_alignment(ctx, n_reads):
+    """Fixed-length reads run through the persistent, software-pipelined kernel: its prologue (first tile of a CTA), the
+    steady state and the last tile; any subset of the three arrays; arrays that are not 16-byte aligned (scalar write-out);
+    a capacity that ends inside a tile."""
+    import torch
+    import oracle as ko
+    rng = np.random.default_rng(n_reads)
+    L, k = 150, 31
+    bases, _ = random_reads(rng, n_reads, L, L, p_bad=0.004)
+    want = _from_dense(ko, bases, k, n_reads=n_reads, fixed_len=L)
+    m = want[0].size
+    ctx.upload(bases, fixed_len=L)
+    lib, h = ctx._lib, ctx._h
+    nn = C.c_uint64()
+
+    def run(canon, hsh, pos, emit, cap):
+        torch.cuda.synchronize()
+        rc = lib.kmb_extract_compact(h, k, 0, _dp(canon), _dp(hsh), _dp(pos), _dp(emit), cap, C.byref(nn))
+        torch.cuda.synchronize()
+        return rc
+
+    def _dp(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def fresh(off=0):
+        cc = torch.full((m + 8,), -7, dtype=torch.int64, device="cuda")
+        ch = torch.full((m + 8,), -7, dtype=torch.int64, device="cuda")
+        cp = torch.full((m + 8,), -7, dtype=torch.int32, device="cuda")
+        ce = torch.full((n_reads + 1,), -7, dtype=torch.int64, device="cuda")
+        return cc[off:], ch[off:], cp[off:], ce
+
+    def same(t, ref, dtype):
+        return np.array_equal(t[:m].cpu().numpy().view(dtype), ref) and bool((t[m:] == -7).all())  # nothing written past the end
+
+    # every subset of the arrays, aligned (16-byte vector write-out, with and without the "all three" fast path)
+    for use in [(1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1)]:
+        cc, ch, cp, ce = fresh()
+        assert run(cc if use[0] else None, ch if use[1] else None, cp if use[2] else None, ce, m) == 0 and nn.value == m
+        assert not use[0] or same(cc, want[1], np.uint64)
+        assert not use[1] or same(ch, want[2], np.uint64)
+        assert not use[2] or same(cp, want[0], np.int32)
+        assert np.array_equal(ce.cpu().numpy().view(np.uint64), want[3])
+    # arrays 8 (4) bytes off a 16-byte (8-byte) boundary: the scalar write-out
+    cc, ch, cp, ce = fresh(off=1)
+    assert run(cc, ch, cp, ce, m) == 0 and nn.value == m
+    assert same(cc, want[1], np.uint64) and same(ch, want[2], np.uint64) and same(cp, want[0], np.int32)
+    # a capacity that ends inside a tile: the call fails, reports the count, and nothing is written at or beyond the capacity
+    if m > 10:
+        import kmers_b200 as kb
+        cap = m - min(m // 2, 5000) - 3
+        cc, ch, cp, ce = fresh()
+        assert run(cc, ch, cp, ce, cap) == kb._native.ERR_INVALID_ARG and nn.value == m
+        assert np.array_equal(cc[:cap].cpu().numpy().view(np.uint64), want[1][:cap]) and bool((cc[cap:] == -7).all())
+        assert np.array_equal(cp[:cap].cpu().numpy(), want[0][:cap]) and bool((cp[cap:] == -7).all())
