@@ -88,7 +88,18 @@ __global__ void __launch_bounds__(256) pack_fixed_kernel(const PackParams p, uin
 // into shared memory with aligned 16-byte loads, then a word is one funnel-shift extract of two packed entries --
 // or, where a read's region ends inside the word (u8 / u16 word types: regions are whole words of P, not of 32 bits),
 // four one-byte extracts.
-constexpr int kPackGroups = 2048;
+// (scripts/build_variant.sh: 1024 groups with 5 loads in flight, 2048 with 3 / 8 -- all 8 of a thread's 16-byte loads in flight
+//  at four CTAs per SM is the best of them, 74 against 70 % of the copy peak for u64 words)
+#ifndef KMB_PACK_GROUPS
+#define KMB_PACK_GROUPS 2048
+#endif
+#ifndef KMB_PACK_BATCH
+#define KMB_PACK_BATCH 8
+#endif
+#ifndef KMB_PACK_MINCTAS
+#define KMB_PACK_MINCTAS 4
+#endif
+constexpr int kPackGroups = KMB_PACK_GROUPS;
 
 struct PackTileParams {
     const uint8_t* bases;
@@ -114,7 +125,7 @@ __device__ __forceinline__ uint32_t div_obr(uint32_t u, const PackTileParams& p)
 // MODE 1: regions of >= 4 bytes that may end inside a word: two masked extracts per word, branch-free
 // MODE 2: regions of 1..3 bytes: byte by byte
 template <int MODE>
-__global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) {
+__global__ void __launch_bounds__(256, KMB_PACK_MINCTAS) pack_tile_kernel(const PackTileParams p) {
     extern __shared__ uint2 tile[];
     const uint64_t byte_base = (uint64_t)blockIdx.x * (4u * kPackGroups);
     const uint32_t n_out = (uint32_t)min((uint64_t)(4u * kPackGroups), p.total_bytes - byte_base);  // output bytes of this CTA
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(256) pack_tile_kernel(const PackTileParams p) 
     // MODE 1: one entry of margin in front -- the extract for the second read of a word starts before that read's first base
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u) + (MODE == 1 ? 16u : 0u);
     const uint32_t n_entries = (uint32_t)((s_end - s_start + mis + 15) >> 4) + 2;  // an extract reads 2 entries, possibly from the stretch's very end
-    stage_tile<false>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
+    stage_tile<false, KMB_PACK_BATCH>(p.bases, p.n_bytes, first - mis, n_entries, p.enc, tile);
     __syncthreads();
     // the 16 bases from tile position rel (relative to the staged stretch)
     auto extract = [&](uint32_t rel) -> uint32_t {

@@ -34,22 +34,22 @@ constexpr int kStageBatch = 3;                   // 16-byte loads a thread keeps
 // {packed bits, invalid mask} entries, 16 bases each.  Entry 0 starts at
 // first_al (16-byte aligned, at or below the first base needed).
 // ---------------------------------------------------------------------------
-template <bool VALIDATE>
+template <bool VALIDATE, int BATCH = kStageBatch>
 __device__ __forceinline__ void stage_tile(const uint8_t* bases, uint64_t n_bytes, const uint8_t* first_al,
                                            uint32_t n_entries, const EncDesc& enc, uint2* tile) {
     // CTA-uniform: does the whole stretch lie inside the batch?  (all but the edge CTAs)
     const bool inside = first_al >= bases && first_al + (size_t)n_entries * 16 <= bases + n_bytes;
     if (inside) {
         const uint4* src = reinterpret_cast<const uint4*>(first_al);
-        for (uint32_t v0 = threadIdx.x; v0 < n_entries; v0 += kStageBatch * blockDim.x) {
-            uint4 raw[kStageBatch];
+        for (uint32_t v0 = threadIdx.x; v0 < n_entries; v0 += BATCH * blockDim.x) {
+            uint4 raw[BATCH];
 #pragma unroll
-            for (int b = 0; b < kStageBatch; ++b) {  // all loads first: kStageBatch requests in flight per thread
+            for (int b = 0; b < BATCH; ++b) {  // all loads first: BATCH requests in flight per thread
                 const uint32_t v = v0 + b * blockDim.x;
                 if (v < n_entries) raw[b] = ld_stream_v4(src + v);
             }
 #pragma unroll
-            for (int b = 0; b < kStageBatch; ++b) {
+            for (int b = 0; b < BATCH; ++b) {
                 const uint32_t v = v0 + b * blockDim.x;
                 if (v < n_entries) {
                     PackedWord pw = pack16<VALIDATE>(raw[b]);
