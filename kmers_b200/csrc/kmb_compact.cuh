@@ -55,23 +55,38 @@ struct CompactParams {
     CompactOut out;
 };
 
+#ifndef KMB_COMPACT_MINCTAS
+#define KMB_COMPACT_MINCTAS 3
+#endif
 constexpr int kCompactRound = kExtractThreads * kRun;  // entries one round of items can emit (2048): 256 per warp
 constexpr int kCompactWarps = kExtractThreads / 32;
 constexpr int kWarpSlice = 32 * kRun + 2;  // the 256 entries a warp's 32 items can emit in a round, + 1 for the parity shift (put)
 constexpr int kLookBack = 8;               // PIPE: descriptors per lane and look-back step (256 earlier tiles per load latency)
-static_assert(kItemsPerCta * kRun < 65536, "per-tile offsets are 16-bit");
+// Items per tile of the pipelined kernel.  It runs three CTAs per SM (the 64 registers that four allow cost more in spills and
+// rebuilt addresses than the fourth CTA brings: 2.133 against 2.164 ms per 4 M reads), and the shared memory that frees goes
+// into larger tiles: what a CTA does once per tile -- ticket, staging loads, scan, the barriers between them -- is 16 % of
+// the instructions but a third of the stall samples.  Per 4 M reads: 1024 items 2.128 ms, 1536 2.080, 2048 2.014, 2304 (the
+// most that fits three CTAs) 1.981; two CTAs per SM with 3072 / 4096 items 2.115 / 2.144.
+#ifndef KMB_COMPACT_PIPE_ITEMS
+#define KMB_COMPACT_PIPE_ITEMS 2304
+#endif
+constexpr int kCompactPipeItems = KMB_COMPACT_PIPE_ITEMS;
+static_assert(kItemsPerCta * kRun < 65536 && kCompactPipeItems * kRun < 65536, "per-tile offsets are 16-bit");
+static_assert(kCompactPipeItems % kExtractThreads == 0, "whole rounds");
 
 // per-tile counters: PIPE keeps two (the tile being emitted and the one counted ahead)
-struct CompactBuf {
-    uint16_t cnt[kItemsPerCta + 2];          // per item: count, then (scan) exclusive offset inside the pass; [n_items] = total
-    uint32_t wr_off[kItemsPerCta / 32 + 2];  // exclusive offset of the first item of every warp-round (32 items), and the total
+template <int ITEMS>
+struct CompactBufT {
+    uint16_t cnt[ITEMS + 2];          // per item: count, then (scan) exclusive offset inside the pass; [n_items] = total
+    uint32_t wr_off[ITEMS / 32 + 2];  // exclusive offset of the first item of every warp-round (32 items), and the total
 };
 
 // Shared memory of the compaction kernels beyond the tile: per-item counts, and the staging buffers through which
 // a round's entries reach global memory as coalesced stores (each thread's <= 8 entries land at arbitrary,
 // unaligned indices; storing them directly would touch every 32-byte sector 4-8 times).
-struct CompactShared {
-    CompactBuf buf;
+template <int ITEMS>
+struct CompactSharedT {
+    CompactBufT<ITEMS> buf;
     uint32_t warp_tot[kCompactWarps];
     uint32_t tile_id;                            // the ticket just taken
     uint32_t lb_has[kCompactWarps];              // CTA-wide look-back: warp w's window holds a tile that knows its prefix
@@ -82,13 +97,14 @@ struct CompactShared {
     uint64_t hash[kCompactWarps * kWarpSlice];
     int32_t pos[kCompactWarps * kWarpSlice];
 };
+using CompactShared = CompactSharedT<kItemsPerCta>;
 constexpr size_t kCompactCountBytes = offsetof(CompactShared, canon);
 static_assert((kWarpSlice * sizeof(uint64_t)) % 16 == 0 && (kWarpSlice * sizeof(int32_t)) % 8 == 0, "slices stay aligned for vector loads");
 
 // PIPE: the second counter set and what the CTA remembers about its two tiles
 struct CompactPipeShared {
-    CompactShared s;
-    CompactBuf buf1;
+    CompactSharedT<kCompactPipeItems> s;
+    CompactBufT<kCompactPipeItems> buf1;
     FixedTile ft[2];
     unsigned long long base[2];   // where the tile's entries start
     uint32_t next_tile;           // the tile counted ahead, its count and its buffer: what warp 0 looks back for during an emit phase
@@ -96,8 +112,10 @@ struct CompactPipeShared {
     uint32_t next_b;
 };
 
-template <bool VALIDATE, bool KHI, bool COUNT_ONLY, bool PIPE = false>
+template <bool VALIDATE, bool KHI, bool COUNT_ONLY, bool PIPE = false, int ITEMS = kItemsPerCta>
 struct CompactEng {
+    using Shared = CompactSharedT<ITEMS>;
+    using Buf = CompactBufT<ITEMS>;
     using Params = CompactParams;
     using Span = kmb::Span;
     static constexpr bool kValidate = VALIDATE;
@@ -105,8 +123,8 @@ struct CompactEng {
     static constexpr bool kTwoPhase = true, kCountOnly = COUNT_ONLY;
     static constexpr int kSpanEntries = 4;
     const CompactParams& p;
-    CompactShared& sh;
-    CompactBuf* cb;              // the counters of the tile at hand
+    Shared& sh;
+    Buf* cb;                     // the counters of the tile at hand
     uint64_t pass_base = 0;      // valid windows of this tile's passes so far
     uint64_t cur_pass_base = 0;  // ... before the current pass
     uint64_t cta_base = 0;       // valid windows of all earlier tiles
@@ -118,7 +136,7 @@ struct CompactEng {
     bool fits = false;           // PIPE: the whole tile lies below p.out.capacity
     bool final_pass = false;     // thread 0: the tile's last pass has been counted and published
 
-    __device__ CompactEng(const CompactParams& params, CompactShared& shared) : p(params), sh(shared), cb(&shared.buf), n_tiles(gridDim.x) {}
+    __device__ CompactEng(const CompactParams& params, Shared& shared) : p(params), sh(shared), cb(&shared.buf), n_tiles(gridDim.x) {}
 
     // Take the next tile.  Called by all threads; the ticket order is the scheduling order, so every tile with a smaller
     // id has been taken by a CTA that is running, and look-back cannot wait for a CTA that is not resident.
@@ -190,7 +208,7 @@ struct CompactEng {
 
     // ---- PIPE
     // the counters and identity of the tile the next count / emit phase works on
-    __device__ __forceinline__ void bind(CompactBuf* buf, uint32_t tile) { cb = buf; tile_id = tile; pass_base = 0; cur_pass_base = 0; }
+    __device__ __forceinline__ void bind(Buf* buf, uint32_t tile) { cb = buf; tile_id = tile; pass_base = 0; cur_pass_base = 0; }
     // after count_pass of a tile counted ahead: its aggregate goes out at once (tile 0 starts at 0 and only ever holds a prefix)
     __device__ __forceinline__ void publish_count() const {
         if (threadIdx.x == 0 && tile_id > 0) desc_store(p.out.desc + tile_id, kDescAggregate | pass_base);
@@ -251,7 +269,7 @@ struct CompactEng {
 
     // exclusive scan of cnt[0 .. n_items) in place; cnt[n_items] = total.  Called by all threads between barriers.
     __device__ __forceinline__ void scan(uint32_t n_items) {
-        constexpr int PER = (kItemsPerCta + kExtractThreads - 1) / kExtractThreads;  // consecutive items per thread
+        constexpr int PER = (ITEMS + kExtractThreads - 1) / kExtractThreads;  // consecutive items per thread
         const uint32_t base = threadIdx.x * PER;
         uint32_t v[PER], sum = 0;
 #pragma unroll
@@ -456,7 +474,7 @@ __global__ void __launch_bounds__(kExtractThreads, 4) compact_fixed_kernel(const
 // Fixed-length reads, emit launch: persistent CTAs, software-pipelined over the tiles (see the head of this file).
 // Dynamic shared memory: [tile 0][tile 1] (tile_bytes each) then CompactPipeShared.  n_tiles descriptors.
 template <class Eng>
-__global__ void __launch_bounds__(kExtractThreads, 4) compact_fixed_pipe_kernel(const FixedGeom g, const EncDesc enc, const CompactParams ep,
+__global__ void __launch_bounds__(kExtractThreads, KMB_COMPACT_MINCTAS) compact_fixed_pipe_kernel(const FixedGeom g, const EncDesc enc, const CompactParams ep,
                                                                                uint32_t tile_bytes, uint32_t n_tiles) {
     extern __shared__ uint2 tile[];
     CompactPipeShared& ps = *reinterpret_cast<CompactPipeShared*>(reinterpret_cast<unsigned char*>(tile) + 2 * (size_t)tile_bytes);

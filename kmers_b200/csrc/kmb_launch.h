@@ -19,6 +19,11 @@ struct Launch {
 template <class Eng>
 inline cudaError_t launch_eng(const FixedGeom* fg, const CsrGeom* cg, const Launch& l, cudaStream_t st, const EncDesc& enc,
                               const typename Eng::Params& ep) {
+    if (l.smem > 36 * 1024) {  // with the kernels' static shared memory that may exceed the 48 KiB a launch gets without opting in
+        const cudaError_t e = fg ? cudaFuncSetAttribute(fixed_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem)
+                                 : cudaFuncSetAttribute(csr_kernel<Eng>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+        if (e != cudaSuccess) return e;
+    }
     if (fg) fixed_kernel<Eng><<<l.grid, kExtractThreads, l.smem, st>>>(*fg, enc, ep);
     else csr_kernel<Eng><<<l.grid, kExtractThreads, l.smem, st>>>(*cg, enc, ep);
     return cudaGetLastError();
@@ -37,7 +42,7 @@ cudaError_t launch_hist_smem(bool validate, bool digest, bool khi, const FixedGe
 cudaError_t launch_compact(bool count_only, bool validate, bool khi, const FixedGeom* fg, const CsrGeom* cg, const Launch& l,
                            cudaStream_t st, const EncDesc& enc, const CompactParams& ep);
 // fixed-length reads, emit launch: persistent software-pipelined kernel (l.smem = ONE tile buffer, l.grid = tiles)
-size_t compact_pipe_tile_budget();  // bytes one tile buffer may take so that four CTAs fit an SM
+size_t compact_pipe_tile_budget();  // bytes one tile buffer may take so that KMB_COMPACT_MINCTAS CTAs fit an SM
 cudaError_t launch_compact_pipe(bool validate, bool khi, const FixedGeom& fg, const Launch& l, int device, cudaStream_t st, const EncDesc& enc,
                                 const CompactParams& ep);
 cudaError_t launch_compact_fixup(const uint64_t* win_offsets, uint64_t W, uint64_t n_reads, uint64_t slots_per_cta, const unsigned long long* desc,

@@ -37,8 +37,8 @@ cudaError_t launch_compact(bool count_only, bool validate, bool khi, const Fixed
                       : launch_compact<false>(validate, khi, fg, cg, l, st, enc, ep);
 }
 
-// 228 KiB of shared memory per SM, 1 KiB of it reserved per resident CTA: what one of four CTAs can have
-static constexpr size_t kPipeCtaSmem = (228 * 1024) / 4 - 1024;
+// 228 KiB of shared memory per SM, 1 KiB of it reserved per resident CTA: what one of KMB_COMPACT_MINCTAS CTAs can have
+static constexpr size_t kPipeCtaSmem = (228 * 1024) / KMB_COMPACT_MINCTAS - 1024;
 
 size_t compact_pipe_tile_budget() { return ((kPipeCtaSmem - sizeof(CompactPipeShared)) / 2) & ~(size_t)15; }
 
@@ -51,7 +51,7 @@ cudaError_t launch_compact_pipe(bool validate, bool khi, const FixedGeom& fg, co
     if (e != cudaSuccess) return e;
 #define KMB_CASE(V, H)                                                                                                  \
     if (validate == V && khi == H) {                                                                                    \
-        auto kern = compact_fixed_pipe_kernel<CompactEng<V, H, false, true>>;                                           \
+        auto kern = compact_fixed_pipe_kernel<CompactEng<V, H, false, true, kCompactPipeItems>>;                                           \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
         if (e != cudaSuccess) return e;                                                                                 \
         int per_sm = 0;                                                                                                 \
