@@ -532,8 +532,13 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
 }
 
 // ragged reads: window offsets (cached per k), per-CTA first-read index, shared-memory layout of csr_kernel
-constexpr uint32_t kCsrItemsPerCta = 1536;  // the K <= 32 dense kernels on ragged reads (kmb_i_run_extract)
-static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, CsrGeom* g, Launch* l, uint32_t ipc = kItemsPerCta) {
+// Ragged reads: 1536 items per tile in the same 36.8 K-base staging buffer (reads of >= 24 bases on average fit one pass;
+// shorter ones take the multi-pass path as before) -- a CTA's serial head (descriptor, offsets, staging, owner table: two
+// dependent global loads and three barriers) is paid per tile.  Reads of 100..150 bp, K=31 canon+hash, ms per 4 M reads:
+// 1024 items 1.144, 1280 1.129, 1536 1.106, 1792 1.116, 2016 1.125, 2560 1.143 (a larger staging buffer changes nothing);
+// K=63 88.9 instead of 82.5 % of the copy peak, minimizers 72.8 instead of 69.5 %.  On fixed-length reads 1024 stays best.
+constexpr uint32_t kCsrItemsPerCta = 1536;
+static int32_t make_csr_geom(kmb_ctx* ctx, uint32_t k, uint32_t span_entries, CsrGeom* g, Launch* l, uint32_t ipc = kCsrItemsPerCta) {
     int32_t rc = ensure_win_offsets(ctx, k);
     if (rc) return rc;
     g->bases = ctx->d_bases; g->n_bytes = ctx->n_bytes; g->n_bases = ctx->n_bases_flat; g->packed = ctx->packed ? 1u : 0u;
@@ -603,10 +608,6 @@ int32_t kmb_i_run_extract(kmb_ctx* ctx, const uint8_t* d_bases, bool csr, uint64
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
     } else {
         if (n_bytes == 0 || n_reads == 0) return KMB_OK;
-        // ragged reads: 1536 items per tile in the same 36.8 K-base staging buffer (reads of >= 24 bases on average fit one pass;
-        // shorter ones take the multi-pass path as before) -- a CTA's serial head (descriptor, offsets, staging, owner table: two
-        // dependent global loads and three barriers) is paid per tile.  Reads of 100..150 bp, ms per 4 M reads: 1024 items 1.144,
-        // 1280 1.129, 1536 1.106, 1792 1.116, 2016 1.125, 2560 1.143 (a larger staging buffer changes nothing)
         int32_t r = make_csr_geom(ctx, k, 4, &cg, &l, big ? kMaxItemsPerCta : kCsrItemsPerCta);
         if (r) return r;
         if (cg.total_slots == 0) return KMB_OK;
@@ -728,7 +729,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     if (!csr) {
         if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
-    } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
+    } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l, kItemsPerCta))) {  // (the engine's shared-memory counters hold kItemsPerCta items)
         return rc;
     }
     const FixedGeom* pf = csr ? nullptr : &fg;
