@@ -1,2 +1,4 @@
 #!/bin/bash
-for so in "" exp_so/c3i2304.so exp_so/c2i3072.so exp_so/c2i4096.so; do KMERS_B200_SO=$so python scripts/prof_one.py compact1 --time | sed "s#^#${so:-default2048} #"; done
+timeout 600 python -m pytest tests/test_gpu_compact.py -m gpu -x -q 2>&1 | tail -2
+python scripts/prof_one.py compact1 --time
+python scripts/prof_one.py compact1 --time
