@@ -88,10 +88,11 @@ __global__ void __launch_bounds__(256) pack_fixed_kernel(const PackParams p, uin
 // into shared memory with aligned 16-byte loads, then a word is one funnel-shift extract of two packed entries --
 // or, where a read's region ends inside the word (u8 / u16 word types: regions are whole words of P, not of 32 bits),
 // four one-byte extracts.
-// (scripts/build_variant.sh: 1024 groups with 5 loads in flight, 2048 with 3 / 8 -- all 8 of a thread's 16-byte loads in flight
-//  at four CTAs per SM is the best of them, 74 against 70 % of the copy peak for u64 words)
+// (scripts/build_variant.sh, u64 / u8 words, % of the copy peak: 1024 groups with 5 loads in flight 66 / 57, 2048 with 3 loads
+//  70 / 61, 2048 with 8 74 / 62, 3072 67 / 61, 4096 with 8 loads at four CTAs per SM 76 / 63, 6144 at three and 8192 at two
+//  CTAs 68 / 62)
 #ifndef KMB_PACK_GROUPS
-#define KMB_PACK_GROUPS 2048
+#define KMB_PACK_GROUPS 4096
 #endif
 #ifndef KMB_PACK_BATCH
 #define KMB_PACK_BATCH 8
@@ -297,7 +298,11 @@ __device__ __forceinline__ void decode8(uint32_t c16, uint32_t dec, uint32_t& ou
     out1 = __byte_perm(dec, 0u, x >> 16);
 }
 
-constexpr int kUnpackBlocksPerThread = 4;
+// 16-byte blocks per thread (scripts/build_variant.sh; % of the copy peak at 50 M 31-mers): 2 71, 4 81, 8 91, 12 87, 16 87, 32 77
+#ifndef KMB_UNPACK_BLOCKS
+#define KMB_UNPACK_BLOCKS 8
+#endif
+constexpr int kUnpackBlocksPerThread = KMB_UNPACK_BLOCKS;
 
 // the <= 16 codes of letters [rel, rel + n) of the CTA's item stream (rel counted from the first letter of the CTA's first item)
 template <bool SAFE>

@@ -28,7 +28,11 @@ cudaError_t launch_minimizers(bool validate, const FixedGeom* fg, const CsrGeom*
 //   CLS 1  width <= 16: 32-bit rank, candidates walked right to left so that '<=' keeps the leftmost minimum
 //   CLS 2  wider      : 64-bit ranks (at most 16 candidates)
 // and every thread works on kMinWordsPerThread words at once.
-constexpr int kMinWordsPerThread = 4;
+// words per thread (% of the copy peak at 10^8 words, k=31 w=15): 2 70, 4 75, 6 79, 8 77, 12 77, 16 78
+#ifndef KMB_MINWORDS
+#define KMB_MINWORDS 6
+#endif
+constexpr int kMinWordsPerThread = KMB_MINWORDS;
 
 // 2^i as a constant-bank operand.  Integer shifts run on the ALU pipe, which this kernel saturates; IMAD runs on the FMA
 // pipe, which it leaves idle (both issue one warp instruction per 2 cycles per SM sub-partition).  A shift written as a

@@ -843,7 +843,9 @@ extern "C" int32_t kmb_minimizers(kmb_ctx* ctx, uint32_t k, uint32_t w, uint32_t
         Launch l;
         const bool csr = ctx->d_offsets != nullptr, validate = !(flags & KMB_F_NO_VALIDATE) && !ctx->packed;
         if (!csr) {
-            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII))
+            // (2048 items per tile: 86.4 instead of 85.3 % of the copy peak; the materialising K <= 32 kernels are best at 1024)
+            if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII,
+                                 2 * kItemsPerCta))
                 return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
         } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l))) {
             return rc;
@@ -1499,9 +1501,9 @@ extern "C" int32_t kmb_pack(kmb_ctx* ctx, int32_t enc_id, uint32_t word_bits, vo
             const uint64_t ctas = (t.total_bytes + 4 * kPackGroups - 1) / (4 * kPackGroups);
             if (ctas > 0x7FFFFFFFull) return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch");
             const size_t smem = (size_t)(kPackGroups + 10) * sizeof(uint2);
-            if ((t.obr & 3u) == 0) pack_tile_kernel<0><<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
-            else if (t.obr >= 4) pack_tile_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
-            else pack_tile_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
+            auto kern = (t.obr & 3u) == 0 ? pack_tile_kernel<0> : t.obr >= 4 ? pack_tile_kernel<1> : pack_tile_kernel<2>;
+            if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)ctas, 256, smem, ctx->stream>>>(t);
         } else if (!ctx->d_offsets) {
             p.out_bytes_per_read = ((ctx->fixed_len + bpw - 1) / bpw) * word_bytes;
             const uint64_t gpr = (p.out_bytes_per_read + 3) / 4;
