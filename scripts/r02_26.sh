@@ -1,2 +1,4 @@
 #!/bin/bash
-for so in exp_so/v16.so exp_so/v12.so exp_so/v32.so; do for w in unpack minword pack64 pack8; do KMERS_B200_SO=$so python scripts/prof_one.py $w --time --scale 2 | sed "s#^#${so:-default} #" | cut -c1-160; done; done
+timeout 600 python -m pytest tests/test_gpu_compact.py tests/test_gpu_fuzz.py -m gpu -x -q 2>&1 | tail -2
+python scripts/prof_one.py compact1 --time
+python scripts/prof_one.py compact1 --time
