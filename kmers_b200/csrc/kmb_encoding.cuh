@@ -676,7 +676,11 @@ __global__ void __launch_bounds__(256) csr_index_kernel(const uint64_t* offsets,
     td.d_hi = (uint32_t)min(r_hi - r_lo, (uint64_t)0xFFFFFFFFu);
     const uint64_t g_end = offsets[r_last] + (slot_end - 1 - win_offsets[r_last]) + k;
     td.span = g_end - td.g0 <= (uint64_t)tile_bases ? (uint32_t)(g_end - td.g0) : 0xFFFFFFFFu;
-    td.pad = 0;
+    // narrow: one pass, the reads' offsets fit the CTA's cache, and they span less than 2^31 bases and windows
+    const uint64_t p0 = slot - win_offsets[r_lo];
+    const bool narrow = td.span != 0xFFFFFFFFu && r_hi - r_lo + 2 <= (uint64_t)kCsrCache + 2 &&
+                        win_offsets[r_hi + 1] - win_offsets[r_lo] < (1ull << 31) && offsets[r_hi + 1] - offsets[r_lo] < (1ull << 31);
+    td.narrow = narrow ? (kCsrNarrow | (uint32_t)p0) : 0u;
     tile_desc[b] = td;
 }
 

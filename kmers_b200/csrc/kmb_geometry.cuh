@@ -14,6 +14,9 @@
 // bit/base, kmb_device.cuh), then runs its items from that tile: the common case (one clean span) in a first sweep, the
 // few two-span / dirty items densely in a second one (run_pass).
 #pragma once
+#ifndef KMB_CSR_NARROW
+#define KMB_CSR_NARROW 1
+#endif
 #include "kmb_device.cuh"
 
 namespace kmb {
@@ -402,8 +405,10 @@ struct alignas(16) CsrTileDesc {
     uint32_t d_last;  // read owning the tile's last slot, counted from r_lo
     uint32_t d_hi;    // read owning the NEXT tile's first slot (the last slot's, for the last tile), counted from r_lo
     uint32_t span;    // bases from g0 to the last window's last base; 0xFFFFFFFF: more than one pass (set up in the kernel)
-    uint32_t pad;
+    uint32_t narrow;  // bit 31: the tile's reads span < 2^31 bases and windows, so everything inside the tile is 32-bit arithmetic
+                      // relative to read r_lo; bits 30..0 then hold the position of the tile's first slot inside read r_lo
 };
+constexpr uint32_t kCsrNarrow = 0x80000000u;
 
 struct CsrGeom {
     const uint8_t* bases;
@@ -423,6 +428,15 @@ struct CsrGeom {
 __device__ __forceinline__ uint64_t last_le(const uint64_t* a, uint64_t lo, uint64_t hi, uint64_t v) {
     while (lo < hi) {
         const uint64_t mid = lo + ((hi - lo + 1) >> 1);
+        if (a[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ... the same on 32-bit tables
+__device__ __forceinline__ uint32_t last_le32(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t v) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
         if (a[mid] <= v) lo = mid; else hi = mid - 1;
     }
     return lo;
@@ -464,6 +478,41 @@ __device__ __forceinline__ void csr_item(uint32_t li, uint32_t n_slots, const Cs
     }
 }
 
+// The same for a "narrow" tile (CsrTileDesc::narrow): w32[i] / o32[i] = window / base offset of read r_lo + i counted from read
+// r_lo's, p0 = position of the tile's first slot inside read r_lo, grp32 = owner (relative to r_lo) of every group's first
+// slot.  Slots are compared in the biased coordinate fs + p0.  No 64-bit compare, subtract or shared-memory load is left on
+// the per-item path (the absolute read numbers of ItemCtx are only formed by the engines that use them).
+template <class Shape, class One, class Two, class Single>
+__device__ __forceinline__ void csr_item32(uint32_t li, uint32_t n_slots, uint32_t p0, uint64_t slot_begin, uint64_t r_lo, const uint32_t* w32,
+                                           const uint32_t* o32, const uint32_t* grp32, uint32_t mis, One&& one, Two&& two, Single&& single) {
+    const uint32_t fs = Shape::first(li);
+    if (fs >= n_slots) return;
+    const uint32_t fb = fs + p0;
+    const uint64_t slot0 = slot_begin + fs;
+    const uint32_t nwin = min((uint32_t)Shape::kSpanSlots, n_slots - fs);
+    uint32_t r = last_le32(w32, grp32[li / kCsrGroup], grp32[li / kCsrGroup + 1], fb);
+    const uint32_t pos = fb - w32[r];
+    const uint32_t left = w32[r + 1] - w32[r] - pos;  // windows left in read r (>= 1)
+    const uint32_t rel = o32[r] + pos - p0 + mis;     // the tile's stretch starts p0 bases into read r_lo
+    if (left >= nwin) {
+        one(rel, slot0, nwin, ItemCtx{li, r_lo + r, pos, 0});
+        return;
+    }
+    uint32_t r2 = r + 1;
+    while (w32[r2 + 1] == w32[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+    if (left + (w32[r2 + 1] - w32[r2]) >= nwin) {
+        two(rel, o32[r2] - p0 + mis - left, left, slot0, nwin, ItemCtx{li, r_lo + r, pos, r_lo + r2});
+        return;
+    }
+    // several short reads inside one item: window by window
+    uint32_t p = pos, w_r = w32[r + 1] - w32[r];
+    for (uint32_t s = 0; s < nwin; ++s) {
+        while (p >= w_r) { ++r; p = 0; w_r = w32[r + 1] - w32[r]; }
+        if (Shape::owns(s)) single(o32[r] + p - p0 + mis, slot0 + s, ItemCtx{li, r_lo + r, p, 0});
+        ++p;
+    }
+}
+
 template <class Eng>
 __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint64_t* c_off,
                                          uint64_t* c_win, CsrPass* pass, uint32_t tile_idx) {
@@ -480,7 +529,42 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
     const uint4 td_b = __ldg(reinterpret_cast<const uint4*>(g.tile_desc + tile_idx) + 1);
     CsrTileDesc td;
     td.g0 = mk64(td_a.x, td_a.y); td.r_lo = mk64(td_a.z, td_a.w); td.d_last = td_b.x; td.d_hi = td_b.y; td.span = td_b.z;
+    td.narrow = td_b.w;
     const uint64_t R_lo = td.r_lo, R_hi = td.r_lo + td.d_hi;
+    if ((td.narrow & kCsrNarrow) && KMB_CSR_NARROW) {
+        // The common case in 32 bits: one pass, the tile's reads cached as offsets relative to read R_lo.
+        const uint32_t p0 = td.narrow & ~kCsrNarrow;
+        const uint64_t win_lo = slot_begin - p0, off_lo = td.g0 - p0;  // = win_offsets[R_lo], offsets[R_lo]
+        uint32_t* w32 = reinterpret_cast<uint32_t*>(c_win);
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(c_off);
+        uint32_t* grp32 = reinterpret_cast<uint32_t*>(grp);
+        const uint32_t n = td.d_hi + 2;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            o32[i] = (uint32_t)(g.offsets[R_lo + i] - off_lo);
+            w32[i] = (uint32_t)(g.win_offsets[R_lo + i] - win_lo);
+        }
+        const uint32_t n_slots = (uint32_t)(slot_end - slot_begin);
+        const uint32_t n_items = Shape::n_items(n_slots);
+        const uint32_t n_groups = (n_items + kCsrGroup - 1) / kCsrGroup;
+        const uint32_t mis = stage_stretch<Eng::kValidate>(g.bases, g.n_bytes, g.packed, td.g0, td.span, Eng::kSpanEntries, enc, tile);
+        if constexpr (!Eng::kTwoPhase) deferred_reset();
+        __syncthreads();  // the offsets and the tile
+        constexpr uint32_t kGroupSlots = kCsrGroup * kRun;
+        for (uint32_t r = threadIdx.x; r <= td.d_last; r += blockDim.x) {  // every read marks the groups whose first slot it owns
+            const uint32_t a = max(w32[r], p0), b = min(w32[r + 1], p0 + n_slots);
+            if (b > a) {
+                const uint32_t t1 = (b - 1 - p0) / kGroupSlots;
+                for (uint32_t t = (a - p0 + kGroupSlots - 1) / kGroupSlots; t <= t1; ++t) grp32[t] = r;
+            }
+        }
+        if (threadIdx.x == 0) grp32[n_groups] = td.d_last;
+        __syncthreads();
+        auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
+            csr_item32<Shape>(li, n_slots, p0, slot_begin, R_lo, w32, o32, grp32, mis, one, two, single);
+        };
+        run_pass(eng, tile, K, n_items, item, true);
+        return;
+    }
     const uint64_t* off = g.offsets;  // tables indexed by absolute read number
     const uint64_t* win = g.win_offsets;
     if (R_hi - R_lo + 2 <= (uint64_t)kCsrCache + 2) {

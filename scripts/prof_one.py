@@ -20,10 +20,10 @@ torch.cuda.set_device(0)
 stream = torch.cuda.Stream()
 ctx = kb.Context(0, stream=stream.cuda_stream)
 i64 = lambda m: torch.empty(m, dtype=torch.int64, device="cuda")
-batch = ctx.generate(42, n, L, n_thresh20=1049 if what.startswith("compact") else 0)
+batch = ctx.generate(42, n, L, n_thresh20=1049 if "compact" in what else 0)
 W = L - K + 1
 n_slots = n * W
-if what == "csr_var":  # ragged reads of 100..150 bases cut from the same stream
+if what in ("csr_var", "csr_var_compact"):  # ragged reads of 100..150 bases cut from the same stream
     import numpy as np
     lens = np.random.default_rng(1).integers(100, 151, size=n).astype(np.uint64)
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
@@ -80,6 +80,13 @@ elif what == "unpack":
     txt = torch.empty(ni * 31, dtype=torch.uint8, device="cuda")
     alg = ni * (8 + 31)
     step = lambda: ctx._ck(ctx._lib.kmb_unpack(ctx._h, kb.ENC_ACGT, 64, _ptr(words), ni, 1, 31, _ptr(txt)))
+elif what in ("csr_compact", "csr_var_compact"):  # the ragged emit launch(es) with worst-case arrays
+    import ctypes as C
+    cc, ch, cp, ce = i64(n_slots), i64(n_slots), torch.empty(n_slots, dtype=torch.int32, device="cuda"), i64(n + 1)
+    cnt = C.c_uint64()
+    step = lambda: ctx._ck(ctx._lib.kmb_extract_compact(ctx._h, K, 0, _ptr(cc), _ptr(ch), _ptr(cp), _ptr(ce), n_slots, C.byref(cnt)))
+    step()
+    alg = (n_bases if what == "csr_var_compact" else n * L) + 20 * int(cnt.value) + 8 * n
 elif what == "compact1":  # the single emit launch with worst-case arrays
     import ctypes as C
     alg = None

@@ -7,7 +7,7 @@ what=${2:-"csr compact wide minimizers canon pack8"}
 mkdir -p gpurun_out/kernels_${tag}
 for w in $what; do
   case $w in
-    csr*) re="regex:csr_kernel";; compact*) re="regex:compact_fixed";; pack8|pack64) re="regex:pack_";; minword) re="regex:minimizer_words_kernel";;
+    csr*) re="regex:csr_kernel";; csr_var_compact|csr_compact) re="regex:compact_csr_kernel";; compact*) re="regex:compact_fixed";; pack8|pack64) re="regex:pack_";; minword) re="regex:minimizer_words_kernel";;
     unpack) re="regex:unpack_flat_kernel";; revcomp) re="regex:revcomp_items_kernel";; hist*) re="regex:hist_fixed_kernel";; *) re="regex:fixed_kernel";;
   esac
   timeout 300 ncu --set full --clock-control none --import-source on -k $re -s 2 -c 1 -f -o /tmp/prof_${w} \
