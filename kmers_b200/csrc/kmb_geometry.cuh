@@ -237,8 +237,9 @@ __device__ __forceinline__ void count_pass(Eng& eng, const uint2* tile, uint32_t
         eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, nwin));
     };
     auto count_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t, uint32_t nwin, const ItemCtx& ic) {
-        eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left) +
-                             count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin));
+        uint32_t c = count_valid_windows<Eng::kSpanEntries>(tile, rel_a, K, 0, left);
+        if (left < nwin) c += count_valid_windows<Eng::kSpanEntries>(tile, rel_b, K, left, nwin);
+        eng.count(ic.li, c);
     };
     auto count_single = [&](uint32_t rel, uint64_t, const ItemCtx& ic) {
         eng.count(ic.li, count_valid_windows<Eng::kSpanEntries>(tile, rel, K, 0, 1));
@@ -262,7 +263,8 @@ __device__ __forceinline__ void emit_pass(Eng& eng, const uint2* tile, uint32_t 
     };
     auto emit_two = [&](uint32_t rel_a, uint32_t rel_b, uint32_t left, uint64_t slot0, uint32_t nwin, const ItemCtx& ic) {
         const typename Eng::Span a = eng.load(tile, rel_a);
-        const typename Eng::Span b = eng.load(tile, rel_b);
+        typename Eng::Span b = a;
+        if (rel_b != rel_a) b = eng.load(tile, rel_b);  // (unified items: a one-span item comes with rel_b == rel_a)
         if (Eng::kValidate) eng.template run<true, true>(a, b, left, slot0, nwin, ic);
         else eng.template run<true, false>(a, b, left, slot0, nwin, ic);
     };
@@ -448,7 +450,7 @@ struct CsrPass {  // one staged stretch: slots [slot_lo, slot_hi) of reads [r_lo
 };
 
 // One work item of a ragged pass: which read(s) its slots belong to, then one span / two spans / window by window.
-template <class Shape, class One, class Two, class Single>
+template <class Shape, bool UNIFIED, class One, class Two, class Single>
 __device__ __forceinline__ void csr_item(uint32_t li, uint32_t n_slots, const CsrPass& ps, const uint64_t* off, const uint64_t* win,
                                          const uint64_t* grp, uint32_t mis, One&& one, Two&& two, Single&& single) {
     const uint32_t fs = Shape::first(li);
@@ -459,15 +461,33 @@ __device__ __forceinline__ void csr_item(uint32_t li, uint32_t n_slots, const Cs
     const uint64_t pos = slot0 - win[r];
     const uint64_t left = win[r + 1] - win[r] - pos;  // windows left in read r (>= 1)
     const uint32_t rel = (uint32_t)(off[r] + pos - ps.g0) + mis;
-    if (left >= nwin) {
-        one(rel, slot0, nwin, ItemCtx{li, r, pos, 0});
-        return;
-    }
-    uint64_t r2 = r + 1;
-    while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
-    if (left + (win[r2 + 1] - win[r2]) >= nwin) {
-        two(rel, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left, (uint32_t)left, slot0, nwin, ItemCtx{li, r, pos, r2});
-        return;
+    if constexpr (UNIFIED) {
+        // one call site for one-span and two-span items (see csr_item32)
+        uint64_t r2 = r;
+        uint32_t rel_b = rel, n_first = nwin;
+        bool fits = true;
+        if (left < nwin) {
+            r2 = r + 1;
+            while (win[r2 + 1] == win[r2]) ++r2;
+            fits = left + (win[r2 + 1] - win[r2]) >= nwin;
+            rel_b = (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left;
+            n_first = (uint32_t)left;
+        }
+        if (fits) {
+            two(rel, rel_b, n_first, slot0, nwin, ItemCtx{li, r, pos, r2});
+            return;
+        }
+    } else {
+        if (left >= nwin) {
+            one(rel, slot0, nwin, ItemCtx{li, r, pos, 0});
+            return;
+        }
+        uint64_t r2 = r + 1;
+        while (win[r2 + 1] == win[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+        if (left + (win[r2 + 1] - win[r2]) >= nwin) {
+            two(rel, (uint32_t)(off[r2] - ps.g0) + mis - (uint32_t)left, (uint32_t)left, slot0, nwin, ItemCtx{li, r, pos, r2});
+            return;
+        }
     }
     // several short reads inside one item: window by window
     uint64_t p = pos, w_r = win[r + 1] - win[r];
@@ -482,7 +502,7 @@ __device__ __forceinline__ void csr_item(uint32_t li, uint32_t n_slots, const Cs
 // r_lo's, p0 = position of the tile's first slot inside read r_lo, grp32 = owner (relative to r_lo) of every group's first
 // slot.  Slots are compared in the biased coordinate fs + p0.  No 64-bit compare, subtract or shared-memory load is left on
 // the per-item path (the absolute read numbers of ItemCtx are only formed by the engines that use them).
-template <class Shape, class One, class Two, class Single>
+template <class Shape, bool UNIFIED, class One, class Two, class Single>
 __device__ __forceinline__ void csr_item32(uint32_t li, uint32_t n_slots, uint32_t p0, uint64_t slot_begin, uint64_t r_lo, const uint32_t* w32,
                                            const uint32_t* o32, const uint32_t* grp32, uint32_t mis, One&& one, Two&& two, Single&& single) {
     const uint32_t fs = Shape::first(li);
@@ -494,15 +514,35 @@ __device__ __forceinline__ void csr_item32(uint32_t li, uint32_t n_slots, uint32
     const uint32_t pos = fb - w32[r];
     const uint32_t left = w32[r + 1] - w32[r] - pos;  // windows left in read r (>= 1)
     const uint32_t rel = o32[r] + pos - p0 + mis;     // the tile's stretch starts p0 bases into read r_lo
-    if (left >= nwin) {
-        one(rel, slot0, nwin, ItemCtx{li, r_lo + r, pos, 0});
-        return;
-    }
-    uint32_t r2 = r + 1;
-    while (w32[r2 + 1] == w32[r2]) ++r2;  // next read that has windows (exists: nwin > left)
-    if (left + (w32[r2 + 1] - w32[r2]) >= nwin) {
-        two(rel, o32[r2] - p0 + mis - left, left, slot0, nwin, ItemCtx{li, r_lo + r, pos, r_lo + r2});
-        return;
+    if constexpr (UNIFIED) {
+        // Engines that cannot put two-span items off to a second sweep (compaction: the scan fixes the order) would run the
+        // one-span AND the two-span handler in every warp that holds a straddling item -- on ragged reads that is every warp,
+        // in both sweeps.  Here both kinds go through ONE call of the two-span handler: a one-span item is a two-span item
+        // whose second span is its first and never used (n_first = nwin).
+        uint32_t r2 = r, rel_b = rel, n_first = nwin;
+        bool fits = true;
+        if (left < nwin) {
+            r2 = r + 1;
+            while (w32[r2 + 1] == w32[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+            fits = left + (w32[r2 + 1] - w32[r2]) >= nwin;
+            rel_b = o32[r2] - p0 + mis - left;
+            n_first = left;
+        }
+        if (fits) {
+            two(rel, rel_b, n_first, slot0, nwin, ItemCtx{li, r_lo + r, pos, r_lo + r2});
+            return;
+        }
+    } else {
+        if (left >= nwin) {
+            one(rel, slot0, nwin, ItemCtx{li, r_lo + r, pos, 0});
+            return;
+        }
+        uint32_t r2 = r + 1;
+        while (w32[r2 + 1] == w32[r2]) ++r2;  // next read that has windows (exists: nwin > left)
+        if (left + (w32[r2 + 1] - w32[r2]) >= nwin) {
+            two(rel, o32[r2] - p0 + mis - left, left, slot0, nwin, ItemCtx{li, r_lo + r, pos, r_lo + r2});
+            return;
+        }
     }
     // several short reads inside one item: window by window
     uint32_t p = pos, w_r = w32[r + 1] - w32[r];
@@ -517,6 +557,7 @@ template <class Eng>
 __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, Eng& eng, uint2* tile, uint64_t* c_off,
                                          uint64_t* c_win, CsrPass* pass, uint32_t tile_idx) {
     using Shape = typename Eng::Shape;
+    constexpr bool kUnified = Eng::kTwoPhase;  // (see csr_item32)
     const uint32_t K = eng.K();
     const uint64_t slots_per_cta = (uint64_t)g.items_per_cta * kRun;
     const uint64_t slot_begin = (uint64_t)tile_idx * slots_per_cta;
@@ -560,7 +601,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         if (threadIdx.x == 0) grp32[n_groups] = td.d_last;
         __syncthreads();
         auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
-            csr_item32<Shape>(li, n_slots, p0, slot_begin, R_lo, w32, o32, grp32, mis, one, two, single);
+            csr_item32<Shape, kUnified>(li, n_slots, p0, slot_begin, R_lo, w32, o32, grp32, mis, one, two, single);
         };
         run_pass(eng, tile, K, n_items, item, true);
         return;
@@ -602,7 +643,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         if (threadIdx.x == 0) grp[n_groups] = ps.r_hi;
         __syncthreads();
         auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
-            csr_item<Shape>(li, n_slots, ps, off, win, grp, mis, one, two, single);
+            csr_item<Shape, kUnified>(li, n_slots, ps, off, win, grp, mis, one, two, single);
         };
         run_pass(eng, tile, K, n_items, item, true);
         return;
@@ -653,7 +694,7 @@ __device__ __forceinline__ void csr_body(const CsrGeom& g, const EncDesc& enc, E
         __syncthreads();
 
         auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) {
-            csr_item<Shape>(li, n_slots, ps, off, win, grp, mis, one, two, single);
+            csr_item<Shape, kUnified>(li, n_slots, ps, off, win, grp, mis, one, two, single);
         };
         run_pass(eng, tile, K, n_items, item, ps.slot_hi == slot_end);
         __syncthreads();  // the next pass overwrites the tile
