@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kExtractThreads, KMB_COMPACT_MINCTAS) compact_
         const FixedTile ft = fixed_stage<Eng>(g, enc, K, tl, t);
         if (threadIdx.x == 0) ps.ft[b] = ft;
         eng.bind(b ? &ps.buf1 : &ps.s.buf, t);
-        auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape>(g, ft, li, one, two, single); };
+        auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape, true>(g, ft, li, one, two, single); };
         count_pass(eng, tl, K, ft.n_items, item);  // (its first barrier is the one behind the staging)
         eng.publish_count();
         return (uint32_t)eng.pass_base;
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kExtractThreads, KMB_COMPACT_MINCTAS) compact_
             const uint32_t rounds = (ft.n_items + kExtractThreads - 1) / kExtractThreads;
             eng.bind(b ? &ps.buf1 : &ps.s.buf, cur);
             eng.begin_emit(cur_total, ps.base[b], has_next ? min(1u, rounds - 1u) : 0xFFFFFFFFu);
-            auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape>(g, ft, li, one, two, single); };
+            auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape, true>(g, ft, li, one, two, single); };
             emit_pass(eng, tile + b * tile_entries, ft.n_items, item, [](uint32_t) {});
         }
         if (!has_next) break;

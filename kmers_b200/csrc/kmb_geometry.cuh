@@ -177,6 +177,7 @@ struct FixedGeom {
     uint32_t items_per_cta; // host-chosen so the staged stretch fits shared memory
     uint32_t packed;        // 0: ASCII; 1: 2-bit packed words, SeqVector layout; 2: flat 2-bit stream + invalid masks (`inv`)
     const uint16_t* inv;    // packed == 2: one 16-bit invalid mask per 32-bit word of `bases`
+    uint32_t unified;       // W >= kRun and not a multiple of it: every read has a straddling item (see fixed_item)
 };
 
 // u / W for a small u (u < W + slots per CTA): 0/1 when W is large, else multiply-high
@@ -354,7 +355,7 @@ __device__ __forceinline__ FixedTile fixed_stage(const FixedGeom& g, const EncDe
 
 // phase 2: every item is one span, two spans (straddles a read boundary) or, for reads with fewer than kRun windows, a run
 // of single windows
-template <class Shape, class One, class Two, class Single>
+template <class Shape, bool UNIFIED_OK, class One, class Two, class Single>
 __device__ __forceinline__ void fixed_item(const FixedGeom& g, const FixedTile& t, uint32_t li, One&& one, Two&& two, Single&& single) {
     const uint32_t slots_per_cta = g.items_per_cta * kRun;
     const uint32_t fs = Shape::first(li);              // the item's first slot, counted from the CTA's
@@ -367,6 +368,12 @@ __device__ __forceinline__ void fixed_item(const FixedGeom& g, const FixedTile& 
     const uint32_t rel = q * g.L32 + pos - t.p_first + t.mis;  // first base, relative to tile entry 0
     const uint32_t left = g.W32 - pos;                   // windows left in this read (>= 1)
     const ItemCtx ic{li, t.r_first + q, pos, t.r_first + q + 1};
+    if (UNIFIED_OK && g.unified) {
+        // two-phase engines when every read has a straddling item: one call site for both kinds of item (as csr_item32)
+        const bool straddles = left < nwin;
+        two(rel, straddles ? (q + 1) * g.L32 - t.p_first + t.mis - left : rel, straddles ? left : nwin, slot0, nwin, ic);
+        return;
+    }
     if (left >= (uint32_t)Shape::kSpanSlots || left >= nwin) {
         one(rel, slot0, nwin, ic);
     } else if (g.W32 >= (uint32_t)Shape::kSpanSlots) {
@@ -388,7 +395,7 @@ __device__ __forceinline__ void fixed_body(const FixedGeom& g, const EncDesc& en
     if constexpr (!Eng::kTwoPhase) deferred_reset();
     __syncthreads();
     using Shape = typename Eng::Shape;
-    auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape>(g, t, li, one, two, single); };
+    auto item = [&](uint32_t li, auto&& one, auto&& two, auto&& single) { fixed_item<Shape, Eng::kTwoPhase>(g, t, li, one, two, single); };
     run_pass(eng, tile, K, t.n_items, item);
 }
 

@@ -506,6 +506,7 @@ static bool make_fixed_geom(const uint8_t* d_bases, uint64_t n_bytes, uint64_t n
     g->W = L - k + 1;
     if (g->W > 0xFFFF0000ull) return false;  // one read of > 4.29 Gbases: split it (window positions are 32-bit inside a CTA)
     g->W32 = (uint32_t)g->W;
+    g->unified = (g->W >= (uint64_t)kRun && g->W % kRun != 0) ? 1u : 0u;
     g->total_slots = n_reads * g->W;
     g->w_magic = g->W32 > 1 ? (uint32_t)((1ull << 32) / g->W32 + 1) : 0;
     // slot / W by multiplication is exact while slot * W < 2^64; otherwise the kernel divides

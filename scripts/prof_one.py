@@ -15,7 +15,7 @@ from kmers_b200.context import _ptr
 what = sys.argv[1]
 timed = "--time" in sys.argv
 scale = float(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 1.0  # problem size, times the default
-n, L, K = int(4_000_000 * scale), 150, 31
+n, L, K = int(4_000_000 * scale), 150, (int(sys.argv[sys.argv.index("--k") + 1]) if "--k" in sys.argv else 31)
 torch.cuda.set_device(0)
 stream = torch.cuda.Stream()
 ctx = kb.Context(0, stream=stream.cuda_stream)
