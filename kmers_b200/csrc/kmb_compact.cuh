@@ -71,6 +71,10 @@ constexpr int kLookBack = 8;               // PIPE: descriptors per lane and loo
 #define KMB_COMPACT_PIPE_ITEMS 2304
 #endif
 constexpr int kCompactPipeItems = KMB_COMPACT_PIPE_ITEMS;
+#ifndef KMB_COMPACT_CSR_ITEMS
+#define KMB_COMPACT_CSR_ITEMS 1536  // ragged reads, one tile per CTA: as the dense ragged kernels (kCsrItemsPerCta); still three CTAs per SM
+#endif
+constexpr int kCompactCsrItems = KMB_COMPACT_CSR_ITEMS;
 static_assert(kItemsPerCta * kRun < 65536 && kCompactPipeItems * kRun < 65536, "per-tile offsets are 16-bit");
 static_assert(kCompactPipeItems % kExtractThreads == 0, "whole rounds");
 
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(kExtractThreads, 3) compact_csr_kernel(const C
     __shared__ CsrPass pass;
     uint64_t* c_off = reinterpret_cast<uint64_t*>(tile + g.tile_entries);
     uint64_t* c_win = c_off + (kCsrCache + 2);
-    CompactShared& sh = *reinterpret_cast<CompactShared*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);
+    typename Eng::Shared& sh = *reinterpret_cast<typename Eng::Shared*>(reinterpret_cast<unsigned char*>(tile) + tile_bytes);
     Eng eng(ep, sh);
     csr_body(g, enc, eng, tile, c_off, c_win, &pass, eng.take_tile());
     eng.finish();

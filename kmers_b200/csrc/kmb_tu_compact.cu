@@ -10,7 +10,8 @@ static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, 
                                   cudaStream_t st, const EncDesc& enc, const CompactParams& ep) {
     // dynamic shared memory = the geometry's tile (+ tables), 16-byte aligned, then CompactShared: above 48 KiB -> opt in
     const uint32_t tile_bytes = (uint32_t)((l.smem + 15) & ~(size_t)15);
-    const size_t smem = tile_bytes + (COUNT_ONLY ? kCompactCountBytes : sizeof(CompactShared));
+    const size_t smem = tile_bytes + (fg ? (COUNT_ONLY ? kCompactCountBytes : sizeof(CompactShared))
+                                         : (COUNT_ONLY ? offsetof(CompactSharedT<kCompactCsrItems>, canon) : sizeof(CompactSharedT<kCompactCsrItems>)));
 #define KMB_CASE(V, H)                                                                                                  \
     if (validate == V && khi == H) {                                                                                    \
         cudaError_t e;                                                                                                  \
@@ -19,9 +20,9 @@ static cudaError_t launch_compact(bool validate, bool khi, const FixedGeom* fg, 
             if (e != cudaSuccess) return e;                                                                             \
             compact_fixed_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*fg, enc, ep, tile_bytes); \
         } else {                                                                                                        \
-            e = cudaFuncSetAttribute(compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = cudaFuncSetAttribute(compact_csr_kernel<CompactEng<V, H, COUNT_ONLY, false, kCompactCsrItems>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                             \
-            compact_csr_kernel<CompactEng<V, H, COUNT_ONLY>><<<l.grid, kExtractThreads, smem, st>>>(*cg, enc, ep, tile_bytes); \
+            compact_csr_kernel<CompactEng<V, H, COUNT_ONLY, false, kCompactCsrItems>><<<l.grid, kExtractThreads, smem, st>>>(*cg, enc, ep, tile_bytes); \
         }                                                                                                               \
         return cudaGetLastError();                                                                                      \
     }

@@ -730,7 +730,7 @@ extern "C" int32_t kmb_extract_compact(kmb_ctx* ctx, uint32_t k, uint32_t flags,
     if (!csr) {
         if (!make_fixed_geom(ctx->d_bases, ctx->n_bytes, ctx->n_reads, ctx->fixed_len, k, 4, &fg, &l, ctx->stride_len, ctx->packed ? KMB_I_SEQVECTOR : KMB_I_ASCII))
             return fail(ctx, KMB_ERR_INVALID_ARG, "batch too large for one launch (or a read above 4.29 Gbases)");
-    } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l, kItemsPerCta))) {  // (the engine's shared-memory counters hold kItemsPerCta items)
+    } else if ((rc = make_csr_geom(ctx, k, 4, &cg, &l, kCompactCsrItems))) {  // (the engine's shared-memory counters hold that many items)
         return rc;
     }
     const FixedGeom* pf = csr ? nullptr : &fg;
