@@ -375,7 +375,15 @@ int32_t host_common(kmb_ctx* ctx, const uint8_t* ascii, const uint32_t* pre_bits
         // chunk: ~8 MiB of reads (3 bits/base of it cross the link when packed) and, when the results go back to the
         // host, no more output than the ring buffers should hold; a multiple of 16 reads keeps chunk starts on packed-word
         // boundaries and the output slots 32-byte aligned
-        uint64_t rpc = (env_mb("KMB_PIPE_CHUNK_MB", 8) << 20) / fixed_len;
+        // Reads that arrive packed only cross the link: larger chunks get closer to the copy floor (10^7 x 150 bp, ms per call:
+        // 4 MiB 13.7, 8 MiB 12.0, 16 MiB 11.1, 32 MiB 10.8, 64 MiB 10.6; floor 10.1) -- as long as there are enough chunks left
+        // to overlap; ASCII reads also go through the packers, where 8 MiB is best (4 MiB 14.0, 8 MiB 13.3, 16 MiB 14.6, 32 MiB 16.5).
+        uint64_t chunk_bases = env_mb("KMB_PIPE_CHUNK_MB", 0) << 20;
+        if (chunk_bases == 0) {
+            chunk_bases = 8ull << 20;
+            if (!ascii) chunk_bases = std::min<uint64_t>(32ull << 20, std::max<uint64_t>(4ull << 20, n_reads * fixed_len / 16));
+        }
+        uint64_t rpc = chunk_bases / fixed_len;
         const bool host_out = (out_canon && !pl.out_dev[0]) || (out_hash && !pl.out_dev[1]);
         if (host_out) rpc = std::min<uint64_t>(rpc, (env_mb("KMB_PIPE_OUT_MB", 64) << 20) / (W * 8));
         rpc = std::max<uint64_t>(16, rpc / 16 * 16);
